@@ -1,0 +1,135 @@
+/*
+ * symtensor_b200 -- C-ABI of the B200-native backend for symtensor's symmetrized-contraction hot path.
+ *
+ * The reference (Eike-Flath/symtensor) is pure Python and has no FFI: its hot path is reached through
+ * class-level registries (`SymmetricTensor.implements` / `implements_ufunc.outer`,
+ * symtensor/base.py:259-322, 1057-1063).  The functions below are what a backend mixin registered there
+ * binds (INTEGRATION.md shows the ctypes stub); each entry cites the reference code it replaces, paths
+ * relative to the reference repository.
+ *
+ * Conventions
+ *  - plain C types only; every function returns an `st_status` (0 = ok) and never throws;
+ *    `st_last_error()` returns a thread-local message for the last non-zero status;
+ *  - pointers named `d_*` are DEVICE pointers owned by the caller (e.g. torch CUDA tensors), `h_*` are host
+ *    pointers; `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream); all device work is
+ *    stream-ordered and the call returns without synchronising unless stated;
+ *  - the library keeps no per-call state; it caches one immutable "plan" (class table, binomial table) per
+ *    (device, rank, dim), mirroring the reference's lazily built `pos_dict[(rank, dim)]`
+ *    (symtensor/permcls_symtensor.py:422-445);
+ *  - `rank` <= ST_MAX_RANK.  Positions / sizes are int64.
+ *
+ * Packed layouts
+ *  ST_LAYOUT_PERMCLS  one contiguous buffer holding the reference's `_data` dict
+ *                     (symtensor/permcls_symtensor.py:546-547): classes in `_perm_classes(rank)` order
+ *                     (symtensor/utils.py:839-856, 1000-1002); inside a class the `σindex_iter` order
+ *                     (symtensor/permcls_symtensor.py:288-347).  Class c starts at `offsets[c]`
+ *                     (multiple of ST_CLASS_ALIGN elements, zero padded) as returned by st_class_table.
+ *  ST_LAYOUT_FLAT     the single 1-D array of `FlatSymmetricTensor`, in
+ *                     `itertools.combinations_with_replacement(range(dim), rank)` order
+ *                     (symtensor/flat_symtensor.py:39-50, 219-220).
+ */
+#ifndef SYMTENSOR_B200_H
+#define SYMTENSOR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_MAX_RANK 16
+#define ST_CLASS_ALIGN 32 /* elements; class starts are padded to this (256 B fp64 / 128 B fp32) */
+
+#define ST_LAYOUT_PERMCLS 0
+#define ST_LAYOUT_FLAT 1
+
+typedef enum {
+  ST_OK = 0,
+  ST_ERR_INVALID = 1,     /* bad argument (maps to ValueError in the Python mixin) */
+  ST_ERR_CUDA = 2,        /* a CUDA runtime call failed (RuntimeError) */
+  ST_ERR_UNSUPPORTED = 3, /* valid request this build cannot serve (NotImplementedError) */
+  ST_ERR_OVERFLOW = 4     /* a size does not fit int64 (OverflowError) */
+} st_status;
+
+int st_version(void);
+const char* st_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Class tables (host side, no GPU needed).
+ * Replaces utils._perm_classes / _all_index_counts (symtensor/utils.py:839-856, 1000-1002),
+ * utils._get_permclass_size (:925-933), utils.get_permclass_multiplicity / multinom (:207-223, 760-776)
+ * and SymmetricTensor.indep_size (symtensor/base.py:833-844).  Exact integer arithmetic.
+ * ------------------------------------------------------------------------------------------------ */
+/* number of permutation classes p(rank); negative on error */
+int st_num_classes(int rank);
+/* parts   [ncls * rank]  class c = parts[c*rank .. c*rank+nparts[c]) (descending), rest zero
+ * nparts  [ncls]         number of distinct index values l of class c
+ * sizes   [ncls]         stored components s_c (0 when l > dim)
+ * mults   [ncls]         multiplicity gamma_c = rank!/prod(m_k!)
+ * offsets [ncls + 1]     start of class c in the ST_LAYOUT_PERMCLS buffer; offsets[ncls] = padded total
+ * Any output pointer may be NULL. */
+int st_class_table(int rank, int64_t dim, int32_t* parts, int32_t* nparts, int64_t* sizes, int64_t* mults,
+                   int64_t* offsets);
+/* C(dim + rank - 1, rank) */
+int st_indep_size(int rank, int64_t dim, int64_t* out);
+
+/* Host rank / unrank of single indices (used by the mixin's __getitem__/__setitem__, replaces the
+ * position registry PosRegistry/_convert_dense_index, symtensor/permcls_symtensor.py:422-479, and
+ * get_index_representative :375-381, utils._get_permclass symtensor/utils.py:878-889).
+ * idx: `rank` values in [0, dim), any order.  cls: class ordinal in st_class_table order. */
+int st_host_permcls_rank(int rank, int64_t dim, const int32_t* idx, int32_t* cls, int64_t* pos);
+/* writes the representative multi-index (rank values) of component `pos` of class `cls` */
+int st_host_permcls_unrank(int rank, int64_t dim, int32_t cls, int64_t pos, int32_t* idx);
+/* flat_symtensor.index_of_multicombination (symtensor/flat_symtensor.py:39-50); idx any order */
+int st_host_flat_rank(int rank, int64_t dim, const int32_t* idx, int64_t* pos);
+int st_host_flat_unrank(int rank, int64_t dim, int64_t pos, int32_t* idx);
+
+/* ------------------------------------------------------------------------------------------------
+ * GPU index-class enumerator (bulk).  Replaces the Python generators σindex_iter / _sub_σindex_iter
+ * (symtensor/permcls_symtensor.py:288-347), indep_iter_repindex (:958-960), the PosRegistry lookups
+ * (:422-479) and flat indep_iter_repindex / index_of_multicombination (symtensor/flat_symtensor.py:39-50,
+ * 219-220).  Bit-exact with the reference's storage order.
+ * ------------------------------------------------------------------------------------------------ */
+/* d_idx_out[(p - begin) * rank + k] = k-th entry of the representative multi-index of component p of
+ * class `cls`, for p in [begin, begin + count). */
+int st_permcls_unrank(int rank, int64_t dim, int32_t cls, int64_t begin, int64_t count, int32_t* d_idx_out,
+                      void* stream);
+/* n arbitrary multi-indices d_idx[n * rank] -> class ordinal and position inside the class */
+int st_permcls_rank(int rank, int64_t dim, int64_t n, const int32_t* d_idx, int32_t* d_cls_out,
+                    int64_t* d_pos_out, void* stream);
+int st_flat_unrank(int rank, int64_t dim, int64_t begin, int64_t count, int32_t* d_idx_out, void* stream);
+int st_flat_rank(int rank, int64_t dim, int64_t n, const int32_t* d_idx, int64_t* d_pos_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * contract_all_indices_with_vector  (symtensor/symalg.py:505-527):
+ *     s = sum_{i1..ir} A[i1..ir] x[i1]...x[ir]
+ *       = sum_classes gamma_c * sum_p A_c[p] * prod_j x[v_j(p)]^{m_j}
+ * over the packed coordinates [begin, end) of the buffer (whole tensor: begin = 0, end = total).  Ranges
+ * let callers shard the tensor over GPUs or stream it from the host; `d_packed` points at coordinate
+ * `begin` (i.e. the local shard), begin must be a multiple of ST_CLASS_ALIGN.
+ * d_out receives ONE value (the partial sum of the range), written by a second deterministic pass.
+ * d_workspace: st_contract_vec_workspace_bytes() bytes of device scratch (no initialisation needed).
+ * The caller handles the reference's early exits (len(x) != dim -> ValueError, all-zero x -> 0).
+ * ------------------------------------------------------------------------------------------------ */
+int64_t st_contract_vec_workspace_bytes(void);
+int st_contract_vec_f64(int layout, int rank, int64_t dim, const double* d_packed, int64_t begin, int64_t end,
+                        const double* d_x, double* d_out, void* d_workspace, void* stream);
+int st_contract_vec_f32(int layout, int rank, int64_t dim, const float* d_packed, int64_t begin, int64_t end,
+                        const float* d_x, float* d_out, void* d_workspace, void* stream);
+/* Same op with HOST buffers: streams the packed range through pinned staging buffers in chunks, overlapping
+ * the host->device copies with the kernel, and returns the value on the host (synchronises). */
+int st_contract_vec_host_f64(int layout, int rank, int64_t dim, const double* h_packed, int64_t total,
+                             const double* h_x, double* h_out);
+int st_contract_vec_host_f32(int layout, int rank, int64_t dim, const float* h_packed, int64_t total,
+                             const float* h_x, float* h_out);
+
+/* kernel variant selection for benchmarking / tests: 0 = auto, 1 = generic per-element enumerator,
+ * 2 = tail-table segmented kernel.  Process-wide. */
+int st_set_vec_variant(int variant);
+/* number of kernel launches issued by this library since load (bench.py reports it) */
+int64_t st_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYMTENSOR_B200_H */

@@ -1,0 +1,103 @@
+"""The symmetric-algebra dispatch surface: same names, argument meaning and errors as ``symtensor.symalg``.
+
+    contract_all_indices_with_vector(A, x)      symtensor/symalg.py:505-527
+    contract_all_indices_with_matrix(A, W)      symtensor/symalg.py:475-496
+    tensordot(a, b, axes=2)                     symtensor/symalg.py:427-459   (symmetrized)
+    multiply.outer(a, b) / add / subtract       symtensor/symalg.py:101-171, 193-195, 294-316
+
+Each call is routed to the implementation registered by the argument classes (subclasses first, then left to
+right -- ``ufunc_dispatch``'s rule, symalg.py:120-171).  Unlike the reference there is NO dense fallback: the
+reference's defaults densify to ``d**r`` and average ``r!`` transposes on the CPU; here an op without a
+registered CUDA implementation raises ``TypeError``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .base import SymmetricTensor, result_array  # noqa: F401  (re-exported)
+
+
+def _ordered_providers(args):
+    """Distinct SymmetricTensor types among ``args``, subclasses ahead of their superclasses."""
+    out = []
+    for a in args:
+        t = type(a)
+        if not isinstance(a, SymmetricTensor) or t in out:
+            continue
+        for i, u in enumerate(out):
+            if t is not u and issubclass(t, u):
+                out.insert(i, t)
+                break
+        else:
+            out.append(t)
+    return out
+
+
+class _ArrayFunction:
+    """A dispatched function object; it is also the registry key (like NumPy's public wrappers)."""
+
+    def __init__(self, name, dispatcher, doc):
+        self.__name__ = name
+        self.__qualname__ = name
+        self.__doc__ = doc
+        self._dispatcher = dispatcher
+
+    def __call__(self, *args, **kwargs):
+        relevant = self._dispatcher(*args, **kwargs)
+        for t in _ordered_providers(relevant):
+            impl = t._HANDLED_FUNCTIONS.get(self)
+            if impl is None:
+                continue
+            res = impl(*args, **kwargs)
+            if res is not NotImplemented:
+                return res
+        raise TypeError(f"no implementation of symalg.{self.__name__} for argument types "
+                        f"{[type(a).__name__ for a in relevant]} (symtensor_b200 has no dense CPU fallback)")
+
+    def __repr__(self):
+        return f"<symalg function {self.__name__}>"
+
+
+contract_all_indices_with_vector = _ArrayFunction(
+    "contract_all_indices_with_vector", lambda symtensor, x: (symtensor, x),
+    "sum_{i1..ir} A[i1..ir] x[i1]...x[ir]; returns a rank-0 tensor of A's class (int 0 for an all-zero x).")
+
+contract_all_indices_with_matrix = _ArrayFunction(
+    "contract_all_indices_with_matrix", lambda symtensor, W: (symtensor, W),
+    "C[j1..jr] = sum A[i1..ir] W[i1,j1]...W[ir,jr]; returns a tensor of A's class.")
+
+tensordot = _ArrayFunction(
+    "tensordot", lambda a, b, axes=2: (a, b),
+    "Symmetrized tensordot: Sym(sum over `axes` contracted index pairs).")
+
+
+class UfuncWrapper:
+    """``symalg.multiply`` etc.: calling it is the plain NumPy ufunc, ``.outer`` is the symmetrized outer
+    product dispatched through the classes' ``_HANDLED_UFUNCS['outer']`` registries."""
+
+    def __init__(self, ufunc):
+        self.ufunc = ufunc
+        self.__name__ = ufunc.__name__
+        self.signature = ufunc.signature
+
+    def __call__(self, *args, **kwargs):
+        return self.ufunc(*args, **kwargs)
+
+    def outer(self, a, b, **kwargs):
+        for t in _ordered_providers((a, b)):
+            impl = t._HANDLED_UFUNCS["outer"].get(self)
+            if impl is None:
+                continue
+            res = impl(self, a, b, **kwargs)
+            if res is not NotImplemented:
+                return res
+        raise TypeError(f"no implementation of symalg.{self.__name__}.outer for argument types "
+                        f"({type(a).__name__}, {type(b).__name__}) (symtensor_b200 has no dense CPU fallback)")
+
+    def __repr__(self):
+        return f"<symalg ufunc {self.__name__}>"
+
+
+add = UfuncWrapper(np.add)
+subtract = UfuncWrapper(np.subtract)
+multiply = UfuncWrapper(np.multiply)
