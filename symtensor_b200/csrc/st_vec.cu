@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "st_common.cuh"
@@ -26,9 +27,13 @@
 
 namespace st {
 
-static const int kTailThreads = 512;
 static const int kMaxCtas = 148 * 8;
-static const int64_t kItemElems = 32768;  // coordinates per work item (multiple of ST_CLASS_ALIGN)
+static const int kMaxPartials = 4096;   // fp64 partial sums per launch (one per work item / per CTA)
+static const int kTailThreads = 512;    // 16 warps per CTA, one CTA per SM (the tail table fills shared memory)
+static const int kStageBytes = 1024;    // two 16-byte cp.async per lane
+// tuning knobs (st_set_tuning): work items per CTA, ring depth
+static int g_items_per_cta = 8;
+static int g_ring_stages = 4;
 
 template <typename T>
 struct VecArgs {
@@ -39,7 +44,9 @@ struct VecArgs {
   int64_t begin, end;
   double* partials;  // [gridDim.x]
   int64_t n_items;
-  int32_t tbl_cap;   // table entries that fit the dynamic shared memory
+  int64_t item_elems;  // packed coordinates per work item (multiple of ST_CLASS_ALIGN)
+  unsigned long long* counter;  // [2]: next work item, finished CTAs (library-owned, per stream, self-resetting)
+  int32_t tbl_cap;     // table entries that fit the dynamic shared memory
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -48,8 +55,8 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// block-wide sum -> partials[blockIdx.x]; `red` has one slot per warp
-__device__ __forceinline__ void block_store_partial(double v, double* red, double* partials) {
+// block-wide sum -> *dst; `red` has one slot per warp
+__device__ __forceinline__ void block_store_partial(double v, double* red, double* dst) {
   v = warp_sum(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (lane == 0) red[warp] = v;
@@ -57,7 +64,7 @@ __device__ __forceinline__ void block_store_partial(double v, double* red, doubl
   if (warp == 0) {
     double s = lane < nw ? red[lane] : 0.0;
     s = warp_sum(s);
-    if (lane == 0) partials[blockIdx.x] = s;
+    if (lane == 0) *dst = s;
   }
 }
 
@@ -115,26 +122,53 @@ __global__ void __launch_bounds__(256) vec_generic_kernel(VecArgs<T> a) {
       acc += v * w;
     }
   }
-  block_store_partial(acc, red, a.partials);
+  block_store_partial(acc, red, a.partials + blockIdx.x);
 }
 
-template <typename T>
+// One warp streams segment positions [q0, q1): unrank the start with the whole warp, then the staged walk.
+template <typename T, int NST>
+__device__ __forceinline__ double walk_range_staged(const PlanView& P, const TailStrategy& S, const T* tbl, const T* xr,
+                                                    const int32_t* blen, double wE, const T* __restrict__ Aseg, int64_t q0, int64_t q1,
+                                                    int lane, T* ring) {
+  int32_t u0[ST_MAX_RANK];
+  comb_unrank_warp(P.binom, P.rank, q0, S.Rt, S.gt, u0, lane);
+  return walk_range<T, NST, true>(P, S, tbl, xr, blen, wE, Aseg, q0, q1, lane, ring, u0);
+}
+
+// Shared memory: [T / private xr tables][xr: dim][xs: dim][blen: dim x i32][ring: nwarps x NST x 512 B][ctrl]
+template <typename T, int NST>
 __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* tbl = reinterpret_cast<T*>(smem_raw);
-  T* xr = tbl + a.tbl_cap;
-  T* xs = xr + a.P.dim;
-  TailCtrl* ctl = reinterpret_cast<TailCtrl*>(smem_raw + ((size_t)(a.tbl_cap + 2 * a.P.dim) * sizeof(T) + 15) / 16 * 16);
   const PlanView& P = a.P;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int nwarps = kTailThreads / 32;
+  T* tbl = reinterpret_cast<T*>(smem_raw);
+  T* priv = tbl + (size_t)warp * P.dim;  // this warp's private xr table (tau == 1 classes); aliases the shared table
+  size_t off = ((size_t)a.tbl_cap * sizeof(T) + 15) / 16 * 16;
+  T* xr = reinterpret_cast<T*>(smem_raw + off);
+  T* xs = xr + P.dim;
+  off = (off + 2 * (size_t)P.dim * sizeof(T) + 15) / 16 * 16;
+  int32_t* blen = reinterpret_cast<int32_t*>(smem_raw + off);
+  off = (off + (size_t)P.dim * sizeof(int32_t) + 15) / 16 * 16;
+  T* ring = reinterpret_cast<T*>(smem_raw + off + (size_t)warp * NST * kStageBytes);
+  off += (size_t)nwarps * NST * kStageBytes;
+  TailCtrl* ctl = reinterpret_cast<TailCtrl*>(smem_raw + off);
   if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
-  for (int i = threadIdx.x; i < P.dim; i += blockDim.x) xs[i] = a.x[i];
-  __syncthreads();
-  double total = 0.0;
+  for (int i = threadIdx.x; i < P.dim; i += kTailThreads) xs[i] = a.x[i];
+  int priv_cls = -1;       // (class, segment) the private table was built for -- warp-uniform
+  int64_t priv_seg = -1;
+  double priv_wE = 0.0;
 
-  for (int64_t item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-    const int64_t c0 = a.begin + item * kItemElems;
-    const int64_t c1 = (c0 + kItemElems < a.end) ? c0 + kItemElems : a.end;
+  while (true) {
+    // ---- dynamic scheduling: CTAs claim work items from a global counter (slow regions cannot pile up on one CTA)
+    __syncthreads();
+    if (threadIdx.x == 0) ctl->item = (long long)atomicAdd(a.counter, 1ULL);
+    __syncthreads();
+    const int64_t item = ctl->item;
+    if (item >= a.n_items) break;
+    double total = 0.0;
+    const int64_t c0 = a.begin + item * a.item_elems;
+    const int64_t c1 = (c0 + a.item_elems < a.end) ? c0 + a.item_elems : a.end;
     int64_t coord = c0;
     while (coord < c1) {
       const int ci = class_of_coord(P, coord);
@@ -145,61 +179,88 @@ __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a)
       const TailStrategy S = a.strat[ci];
       const T* Acls = a.A + (C.offset - a.begin);
       if (S.tau == 1) {
-        // ---- mode B: warps split the class range; each warp walks its segments on its own
+        // ---- private tables: warps split the class range; each warp walks its segments on its own
+        if (ctl->cur_cls != -1) {  // CTA-uniform: the private tables overwrite the shared table
+          __syncthreads();
+          if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
+          __syncthreads();
+        }
         const int64_t len = pend - pos;
         int64_t per = (len + nwarps - 1) / nwarps;
         per = (per + 31) / 32 * 32;
         int64_t w0 = pos + (int64_t)warp * per;
         const int64_t w1 = (w0 + per < pend) ? w0 + per : pend;
-        int32_t E[ST_MAX_RANK];
         while (w0 < w1) {
           const int64_t sidx = w0 / S.seg;
           const int64_t sbase = sidx * S.seg;
           const int64_t q1 = (S.seg < w1 - sbase) ? S.seg : w1 - sbase;
-          const double wE = unrank_earlier<T>(P, C, sidx, xs, E);
-          walk_piece<T, false>(P, S, nullptr, nullptr, xs, E, wE, Acls + sbase, w0 - sbase, q1, lane, total);
+          if (priv_cls != ci || priv_seg != sidx) {
+            int32_t E[ST_MAX_RANK];
+            priv_wE = unrank_earlier<T>(P, C, sidx, xs, E);
+            __syncwarp();
+            for (int uu = lane; uu < S.Rt; uu += 32) priv[uu] = xrel_pow<T>(xs, E, S.nE, S.mu, uu);
+            __syncwarp();
+            priv_cls = ci;
+            priv_seg = sidx;
+          }
+          total += walk_range_staged<T, NST>(P, S, priv, priv, nullptr, priv_wE, Acls + sbase, w0 - sbase, q1, lane, ring);
           w0 = sbase + q1;
         }
         pos = pend;
       } else {
-        // ---- mode A: the CTA shares one table per segment
+        // ---- shared table: the CTA builds T once per segment
         while (pos < pend) {
           const int64_t sidx = pos / S.seg;
           const int64_t sbase = sidx * S.seg;
           const int64_t q0 = pos - sbase;
           const int64_t q1 = (S.seg < pend - sbase) ? S.seg : pend - sbase;
           if (ctl->cur_cls != ci || ctl->cur_seg != sidx) {  // CTA-uniform
-            __syncthreads();  // everybody is done with the previous table
+            __syncthreads();  // everybody is done with the previous tables
             if (threadIdx.x == 0) {
               ctl->wE = unrank_earlier<T>(P, C, sidx, xs, ctl->E);
               ctl->cur_cls = ci;
               ctl->cur_seg = sidx;
             }
+            priv_cls = -1;  // the shared table overwrites the private ones
             __syncthreads();
-            for (int uu = threadIdx.x; uu < S.Rt; uu += blockDim.x) xr[uu] = xrel_pow<T>(xs, ctl->E, S.nE, S.mu, uu);
+            for (int uu = threadIdx.x; uu < S.Rt; uu += kTailThreads) {
+              xr[uu] = xrel_pow<T>(xs, ctl->E, S.nE, S.mu, uu);
+              blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
+            }
             __syncthreads();
             {  // T[q] over the tau-combinations of range(Rt); each thread fills a contiguous slice
-              const int64_t per = (S.tbl_n + blockDim.x - 1) / blockDim.x;
+              const int64_t per = (S.tbl_n + kTailThreads - 1) / kTailThreads;
               const int64_t q = (int64_t)threadIdx.x * per;
               build_table_slice<T>(P, S, xr, tbl, q, (q + per < S.tbl_n) ? q + per : S.tbl_n);
             }
             __syncthreads();
           }
-          // warps split the piece [q0, q1) evenly (multiples of 32 keep sector alignment between warps)
+          // warps split the piece [q0, q1) evenly (multiples of 32 components)
           const int64_t len = q1 - q0;
           int64_t per = (len + nwarps - 1) / nwarps;
           per = (per + 31) / 32 * 32;
           const int64_t w0 = q0 + (int64_t)warp * per;
           const int64_t w1 = (w0 + per < q1) ? w0 + per : q1;
-          if (w0 < w1) walk_piece<T, true>(P, S, tbl, xr, xs, ctl->E, ctl->wE, Acls + sbase, w0, w1, lane, total);
+          if (w0 < w1) total += walk_range_staged<T, NST>(P, S, tbl, xr, blen, ctl->wE, Acls + sbase, w0, w1, lane, ring);
           pos = sbase + q1;
         }
       }
       coord = C.offset + pos;
     }
+    // one partial per ITEM (not per CTA): the final sum does not depend on which CTA processed which item
+    __syncthreads();
+    block_store_partial(total, ctl->red, a.partials + item);
   }
-  __syncthreads();
-  block_store_partial(total, ctl->red, a.partials);
+  // self-cleaning counters: the last CTA to finish resets them for the next launch on this stream
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(a.counter + 1, 1ULL);
+    if (ticket == gridDim.x - 1) {
+      a.counter[0] = 0ULL;
+      a.counter[1] = 0ULL;
+      __threadfence();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -209,10 +270,10 @@ static int g_variant = 0;
 int g_force_tau = 0;  // test hook: force the tail length (0 = cost model)
 
 struct StratKey {
-  int dev, rank, esize;
+  int dev, rank, esize, nst;
   int64_t dim;
   bool operator<(const StratKey& o) const {
-    return std::tie(dev, rank, esize, dim) < std::tie(o.dev, o.rank, o.esize, o.dim);
+    return std::tie(dev, rank, esize, nst, dim) < std::tie(o.dev, o.rank, o.esize, o.nst, o.dim);
   }
 };
 struct StratEntry {
@@ -235,15 +296,17 @@ static double dbinom(const HostPlan* hp, int64_t n, int k) {
 //   table builds   ~0.5 per entry, amortised over a segment (multi-run classes) or over a CTA's share of the
 //                  class (single-run classes, table built once per CTA)
 // Pure host function (also used by the CPU emulation harness in tests/emu).
-bool compute_tail_strategy(const HostPlan* hp, int esize, std::vector<TailStrategy>& st, int32_t* tbl_cap, size_t* smem_bytes) {
+bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, int nst, std::vector<TailStrategy>& st, int32_t* tbl_cap, size_t* smem_bytes) {
   const int rank = hp->rank;
   const int64_t dim = hp->dim;
-  const size_t smem_budget = 200 * 1024;
-  const size_t fixed = (size_t)2 * dim * esize + sizeof(TailCtrl) + 64;
+  const size_t smem_budget = 224 * 1024;
+  // everything but the table: xr, xs, blen, the cp.async rings, control block, alignment slack
+  const size_t fixed = (size_t)2 * dim * esize + (size_t)dim * 4 + (size_t)nwarps * nst * kStageBytes + sizeof(TailCtrl) + 128;
   if (fixed + 32 * esize > smem_budget) return false;  // x itself does not fit shared memory
   const int64_t cap = (int64_t)((smem_budget - fixed) / esize);
+  if (cap < (int64_t)nwarps * dim) return false;  // the per-warp private tables (which alias the table) must fit
   st.assign(hp->ncls, TailStrategy());
-  int64_t tbl_max = 32;
+  int64_t tbl_max = std::max<int64_t>(32, (int64_t)nwarps * dim);
   for (int c = 0; c < hp->ncls; ++c) {
     const ClassDesc& C = hp->h_cls[c];
     TailStrategy& S = st[c];
@@ -264,7 +327,7 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, std::vector<TailStrate
       const double avg_block = (double)S.seg / (nheads > 0 ? nheads : 1);
       double cost;
       if (tau == 1) {
-        cost = 0.3 + 0.03 * S.nE + 40.0 / avg_block + (S.nE ? 400.0 / (double)S.seg : 0.0);
+        cost = 0.2 + 40.0 / avg_block + (S.nE ? (400.0 + 0.5 * S.Rt) / (double)S.seg : 0.0);
       } else {
         const double amort = (S.nE == 0) ? std::max(1.0, (double)C.size / 296.0) : (double)S.seg;
         cost = 0.2 + 30.0 / avg_block + (0.5 * tn + 2000.0) / amort;
@@ -279,18 +342,24 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, std::vector<TailStrate
     if (S.tau > 1) tbl_max = std::max(tbl_max, S.tbl_n);
   }
   *tbl_cap = (int32_t)((tbl_max + 31) / 32 * 32);
-  *smem_bytes = ((size_t)(*tbl_cap + 2 * dim) * esize + 15) / 16 * 16 + sizeof(TailCtrl);
+  {
+    size_t off = ((size_t)*tbl_cap * esize + 15) / 16 * 16;
+    off = (off + 2 * (size_t)dim * esize + 15) / 16 * 16;
+    off = (off + (size_t)dim * 4 + 15) / 16 * 16;
+    off += (size_t)nwarps * nst * kStageBytes;
+    *smem_bytes = off + sizeof(TailCtrl);
+  }
   return true;
 }
 
-static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
+static int get_strategy(int rank, int64_t dim, int esize, int nst, StratEntry* out) {
   const HostPlan* hp = get_host_plan(rank, dim);
   if (!hp) return ST_ERR_INVALID;
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_smu);
-  StratKey key{dev, rank, esize, dim};
+  StratKey key{dev, rank, esize, nst, dim};
   auto it = g_strats.find(key);
   if (it != g_strats.end()) { *out = it->second; return ST_OK; }
   StratEntry e;
@@ -298,7 +367,7 @@ static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
   e.tbl_cap = 32;
   e.smem_bytes = 0;
   std::vector<TailStrategy> st;
-  e.supported = compute_tail_strategy(hp, esize, st, &e.tbl_cap, &e.smem_bytes);
+  e.supported = compute_tail_strategy(hp, esize, kTailThreads / 32, nst, st, &e.tbl_cap, &e.smem_bytes);
   if (e.supported) {
     rc = check_cuda(cudaMalloc(&e.d_strat, sizeof(TailStrategy) * hp->ncls), "cudaMalloc(strategy)");
     if (rc) return rc;
@@ -321,6 +390,67 @@ static int sm_count() {
   return n;
 }
 
+// one {next item, finished CTAs} counter pair per (device, stream); zeroed once, reset by the kernel itself
+static std::mutex g_cmu;
+static std::map<std::pair<int, cudaStream_t>, unsigned long long*> g_counters;
+static int get_counter(cudaStream_t stream, unsigned long long** out) {
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_cmu);
+  auto key = std::make_pair(dev, stream);
+  auto it = g_counters.find(key);
+  if (it != g_counters.end()) { *out = it->second; return ST_OK; }
+  unsigned long long* d = nullptr;
+  rc = check_cuda(cudaMalloc(&d, 2 * sizeof(unsigned long long)), "cudaMalloc(counter)");
+  if (rc) return rc;
+  rc = check_cuda(cudaMemset(d, 0, 2 * sizeof(unsigned long long)), "cudaMemset(counter)");
+  if (rc) return rc;
+  g_counters[key] = d;
+  *out = d;
+  return ST_OK;
+}
+
+template <typename T, int NST>
+static int launch_tail_t(VecArgs<T>& a, const StratEntry& se, int64_t len, int* grid_out, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(vec_tail_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+                        "cudaFuncSetAttribute");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  // One resident CTA per SM claims work items dynamically; the item size gives every CTA about
+  // `g_items_per_cta` items: large enough to amortise the per-warp unrank, small enough to balance the tail.
+  const int64_t quantum = 32 * (kTailThreads / 32);
+  int64_t grid = std::min<int64_t>((int64_t)sm_count(), kMaxCtas);
+  grid = std::max<int64_t>(1, std::min<int64_t>(grid, (len + quantum - 1) / quantum));
+  int64_t nitems = std::min<int64_t>(grid * g_items_per_cta, kMaxPartials);
+  int64_t item = (len + nitems - 1) / nitems;
+  item = (item + quantum - 1) / quantum * quantum;
+  a.item_elems = item;
+  a.n_items = (len + item - 1) / item;
+  grid = std::min<int64_t>(grid, a.n_items);
+  {
+    int rc = get_counter(stream, &a.counter);
+    if (rc) return rc;
+  }
+  vec_tail_kernel<T, NST><<<(int)grid, kTailThreads, se.smem_bytes, stream>>>(a);
+  *grid_out = (int)a.n_items;  // number of partials written
+  return ST_OK;
+}
+
+template <typename T>
+static int launch_tail(VecArgs<T>& a, const StratEntry& se, int nst, int64_t len, int* grid_out, cudaStream_t stream) {
+  switch (nst) {
+    case 2: return launch_tail_t<T, 2>(a, se, len, grid_out, stream);
+    case 3: return launch_tail_t<T, 3>(a, se, len, grid_out, stream);
+    case 6: return launch_tail_t<T, 6>(a, se, len, grid_out, stream);
+    case 8: return launch_tail_t<T, 8>(a, se, len, grid_out, stream);
+    default: return launch_tail_t<T, 4>(a, se, len, grid_out, stream);
+  }
+}
+
 // Launch the main pass over [begin, end): writes `*grid_out` fp64 partials to `partials`.
 template <typename T>
 static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, int64_t begin, int64_t end, const T* d_x,
@@ -341,35 +471,41 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   a.begin = begin;
   a.end = end;
   a.partials = partials;
-  a.n_items = (end - begin + kItemElems - 1) / kItemElems;
+  a.n_items = 1;
+  a.item_elems = end - begin;
   a.tbl_cap = 0;
+  a.counter = nullptr;
   *grid_out = 1;
   if (end == begin) return check_cuda(cudaMemsetAsync(partials, 0, sizeof(double), stream), "cudaMemsetAsync");
   StratEntry se;
   se.supported = false;
+  int nst = 6;
   if (layout == ST_LAYOUT_PERMCLS && rank > 0 && g_variant != 1) {
-    rc = get_strategy(rank, dim, (int)sizeof(T), &se);
+    // the tables come first: take the tail lengths the cost model picks with the smallest ring, then the deepest
+    // ring (up to g_ring_stages; 4 stages = 3 KB in flight per warp) that still leaves room for those tables
+    StratEntry base;
+    rc = get_strategy(rank, dim, (int)sizeof(T), 2, &base);
     if (rc) return rc;
+    se = base;
+    nst = 2;
+    if (base.supported) {
+      const int cand[4] = {8, 6, 4, 3};
+      for (int i = 0; i < 4; ++i) {
+        if (cand[i] > g_ring_stages) continue;
+        StratEntry e2;
+        rc = get_strategy(rank, dim, (int)sizeof(T), cand[i], &e2);
+        if (rc) return rc;
+        if (e2.supported && e2.tbl_cap == base.tbl_cap) { se = e2; nst = cand[i]; break; }
+      }
+    }
     if (!se.supported && g_variant == 2) { set_error("tail-table kernel unavailable for dim %lld", (long long)dim); return ST_ERR_UNSUPPORTED; }
   }
   if (se.supported) {
     a.strat = se.d_strat;
     a.tbl_cap = se.tbl_cap;
-    static bool attr_set[2] = {false, false};
-    const int ai = sizeof(T) == 8 ? 0 : 1;
-    if (!attr_set[ai]) {
-      rc = check_cuda(cudaFuncSetAttribute(vec_tail_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024), "cudaFuncSetAttribute");
-      if (rc) return rc;
-      attr_set[ai] = true;
-    }
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, vec_tail_kernel<T>, kTailThreads, se.smem_bytes);
-    if (per_sm < 1) per_sm = 1;
-    int grid = (int)std::min<int64_t>((int64_t)sm_count() * per_sm, a.n_items);
-    grid = std::min(grid, kMaxCtas);
-    vec_tail_kernel<T><<<grid, kTailThreads, se.smem_bytes, stream>>>(a);
+    rc = launch_tail<T>(a, se, nst, end - begin, grid_out, stream);
+    if (rc) return rc;
     count_launch();
-    *grid_out = grid;
     return check_cuda(cudaGetLastError(), "vec_tail_kernel");
   }
   const int64_t n = end - begin;
@@ -463,12 +599,12 @@ static int contract_vec_host(int layout, int rank, int64_t dim, const T* h_packe
   const int64_t expect = layout == ST_LAYOUT_PERMCLS ? hp->h_offsets[hp->ncls] : hp->flat_size;
   if (total != expect) { set_error("packed length %lld, expected %lld", (long long)total, (long long)expect); return ST_ERR_INVALID; }
   std::lock_guard<std::mutex> lk(g_hmu);
-  const int64_t chunk_elems = (int64_t)(kChunkBytes / sizeof(T)) / kItemElems * kItemElems;
+  const int64_t chunk_elems = (int64_t)(kChunkBytes / sizeof(T)) / 32768 * 32768;
   const int64_t n_chunks = std::max<int64_t>(1, (total + chunk_elems - 1) / chunk_elems);
   HostStage* st = nullptr;
-  int rc = get_stage((size_t)dim * sizeof(T), (size_t)n_chunks * kMaxCtas, &st);
+  int rc = get_stage((size_t)dim * sizeof(T), (size_t)n_chunks * kMaxPartials, &st);
   if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(st->d_ws, 0, (size_t)n_chunks * kMaxCtas * sizeof(double), st->s_comp), "cudaMemsetAsync(ws)");
+  rc = check_cuda(cudaMemsetAsync(st->d_ws, 0, (size_t)n_chunks * kMaxPartials * sizeof(double), st->s_comp), "cudaMemsetAsync(ws)");
   if (rc) return rc;
   if (dim > 0) {
     rc = check_cuda(cudaMemcpyAsync(st->d_x, h_x, (size_t)dim * sizeof(T), cudaMemcpyHostToDevice, st->s_comp), "cudaMemcpyAsync(x)");
@@ -489,12 +625,12 @@ static int contract_vec_host(int layout, int rank, int64_t dim, const T* h_packe
     if (rc) return rc;
     int grid = 1;
     rc = vec_partials<T>(layout, rank, dim, reinterpret_cast<const T*>(st->d_buf[b]), begin, end, reinterpret_cast<const T*>(st->d_x),
-                         st->d_ws + c * kMaxCtas, &grid, st->s_comp);
+                         st->d_ws + c * kMaxPartials, &grid, st->s_comp);
     if (rc) return rc;
     rc = check_cuda(cudaEventRecord(st->computed[b], st->s_comp), "cudaEventRecord");
     if (rc) return rc;
   }
-  rc = vec_finalize<T>(st->d_ws, (int)(n_chunks * kMaxCtas), reinterpret_cast<T*>(st->d_out), st->s_comp);
+  rc = vec_finalize<T>(st->d_ws, (int)(n_chunks * kMaxPartials), reinterpret_cast<T*>(st->d_out), st->s_comp);
   if (rc) return rc;
   rc = check_cuda(cudaMemcpyAsync(st->h_out, st->d_out, sizeof(T), cudaMemcpyDeviceToHost, st->s_comp), "cudaMemcpyAsync(out)");
   if (rc) return rc;
@@ -510,7 +646,22 @@ using namespace st;
 
 extern "C" {
 
-int64_t st_contract_vec_workspace_bytes(void) { return (int64_t)sizeof(double) * kMaxCtas; }
+int64_t st_contract_vec_workspace_bytes(void) { return (int64_t)sizeof(double) * kMaxPartials; }
+
+int st_set_tuning(const char* key, int64_t value) {
+  if (!key) { set_error("null key"); return ST_ERR_INVALID; }
+  const std::string k(key);
+  if (k == "vec_ring_stages" && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8)) { g_ring_stages = (int)value; return ST_OK; }
+  if (k == "vec_items_per_cta" && value >= 1 && value <= 64) { g_items_per_cta = (int)value; return ST_OK; }
+  if (k == "vec_force_tau" && value >= 0 && value <= ST_MAX_RANK) {
+    g_force_tau = (int)value;
+    std::lock_guard<std::mutex> lk(g_smu);
+    g_strats.clear();  // strategies are rebuilt on next use (device tables of old entries are leaked: test hook)
+    return ST_OK;
+  }
+  set_error("unknown tuning key '%s' or value %lld out of range", key, (long long)value);
+  return ST_ERR_INVALID;
+}
 
 int st_set_vec_variant(int variant) {
   if (variant < 0 || variant > 2) { set_error("variant must be 0, 1 or 2"); return ST_ERR_INVALID; }

@@ -33,17 +33,21 @@ ST_HD T ld_stream(const T* p) {
 // ------------------------------------------------------------------------------------------------------
 // A class is a sequence of SEGMENTS (one per assignment E of the earlier runs, `seg` components each); inside
 // a segment the last run is an increasing g_t-combination u of the Rt relabelled values not in E; its first
-// hn values are the "head", the last tau the "tail".  Two modes per class (host cost model):
-//   mode A (tau >= 2)  tail weights come from the shared-memory table T (rebuilt by the CTA when E changes);
-//   mode B (tau == 1)  the tail weight of relabelled value u is x[actual(u)]^mu, computed by the lane -- no
-//                      table, no CTA synchronisation; used when segments are too short to amortise a table.
-// Shared memory: [T table: tbl_cap x T][xr: dim x T (xrel^mu, mode A)][xs: dim x T (copy of x)][ctrl]
+// hn values are the "head", the last tau the "tail".  For a fixed head the tail components are one contiguous
+// BLOCK of memory whose weights are a contiguous slice of the table
+//     T[q] = prod_{u in q-th tau-combination of range(Rt)} xr[u],      xr[u] = x[actual(u)]^mu .
+// Two table ownerships per class (host cost model):
+//   shared  (tau >= 2)  T and xr live once per CTA and are rebuilt (with __syncthreads) when E changes;
+//   private (tau == 1)  T == xr, one copy per warp, rebuilt by the warp itself when it enters a new segment --
+//                       used when segments are too short to amortise a CTA-wide rebuild.
+// Shared memory: [T: tbl_cap x T][xr: dim x T][xs: dim x T (copy of x)][private xr: nwarps x dim x T][ctrl]
 struct TailCtrl {
   double red[32];
   double wE;               // gamma * prod over earlier runs x[v]^m
   int32_t E[ST_MAX_RANK];  // values of the earlier runs, ascending
   int32_t cur_cls;
   int64_t cur_seg;
+  long long item;          // work item broadcast (dynamic scheduling)
 };
 
 // earlier runs of segment `sidx`: values (ascending, in E) and the weight gamma * prod x[v]^m
@@ -86,67 +90,215 @@ ST_HD T xrel_pow(const T* __restrict__ xs, const int32_t* E, int nE, int mu, int
   return p;
 }
 
-// One warp streams segment positions [q0, q1) of a segment whose first component is Aseg[0].
-// MODE_A: tail weights from `tbl` (tau-combination table) and head factors from `xr`;
-// MODE_B: tau == 1, weights computed from xs / E.
-template <typename T, bool MODE_A>
-ST_HD void walk_piece(const PlanView& P, const TailStrategy& S, const T* __restrict__ tbl,
-                                           const T* __restrict__ xr, const T* __restrict__ xs, const int32_t* E, double wE,
-                                           const T* __restrict__ Aseg, int64_t q0, int64_t q1, int lane, double& total) {
-  const int64_t* bt = P.binom;
+// ------------------------------------------------------------------------------------------------------
+// walk_range: one warp's walk over segment positions [q0, q1) of one segment.
+//
+// Memory and index arithmetic are DECOUPLED.  On the device the components are streamed through a per-warp
+// shared-memory ring with cp.async (16-byte copies, NST stages of 1 KB, NST-1 in flight while one is
+// consumed) in fixed stages that ignore block boundaries; the walk is handed one 32-wide SLOT of consecutive
+// components at a time and multiplies it against the "pieces" (block ∩ range) that overlap it:
+//     weight(idx) = hw * tbl[toff + idx]   for idx in [pb, pe)
+// A warp-uniform odometer produces the pieces: the common step -- increment the last head value -- costs a
+// handful of instructions (fast path); carries take the general path over the local arrays u[] / pref[].
+// All hot state is in scalar locals (registers); only u[] and pref[] are indexed dynamically.
+// `tbl` is the tail table (T for tau >= 2, xr for tau == 1), `xr` the head-factor table, `blen` the optional
+// table  blen[u] = C(Rt-1-u, tau)  of block lengths (nullptr: computed from the binomial table).
+// STAGED = false reads the components directly (CPU emulation in tests/emu, which replays this code lane by
+// lane; on the device it serves as the reference path for tiny ranges).
+// ------------------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define ST_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+#else
+#define ST_ASSUME_SHARED(p)
+#endif
+#ifdef __CUDACC__
+__device__ __forceinline__ void st_cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void st_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void st_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
+
+template <typename T, int NST, bool STAGED>
+ST_HD double walk_range(const PlanView& P, const TailStrategy& S, const T* __restrict__ tbl, const T* __restrict__ xr,
+                        const int32_t* __restrict__ blen, double wE, const T* __restrict__ Aseg, int64_t q0, int64_t q1, int lane,
+                        T* ring, const int32_t* u_init) {
+  ST_ASSUME_SHARED(tbl);
+  ST_ASSUME_SHARED(xr);
+  const int64_t* __restrict__ bt = P.binom;
   const int rk = P.rank;
   const int gt = S.gt, hn = S.hn, tau = S.tau, Rt = S.Rt;
-  int32_t u[ST_MAX_RANK];
-  comb_unrank(bt, rk, q0, Rt, gt, u);
-  int64_t tq = comb_rank(bt, rk, u + hn, Rt, tau);  // table index of the current tail
-  double pref[ST_MAX_RANK + 1];                      // pref[i] = wE * prod_{j<i} xrel[u[j]]^mu
+  const int tbl_n = (int)S.tbl_n;
+  const int n = (int)(q1 - q0);
+  int32_t u[ST_MAX_RANK];        // head combination (relabelled values), warp-uniform; slow path only
+  double pref[ST_MAX_RANK + 1];  // pref[i] = wE * prod_{j<i} xr[u[j]];                 slow path only
+  if (u_init) { for (int i = 0; i < gt; ++i) u[i] = u_init[i]; }
+  else comb_unrank(bt, rk, q0, Rt, gt, u);
+  const int tq = (int)comb_rank(bt, rk, u + hn, Rt, tau);  // table index of the first tail
   pref[0] = wE;
-  for (int i = 0; i < hn; ++i)
-    pref[i + 1] = pref[i] * (double)(MODE_A ? xr[u[i]] : xrel_pow<T>(xs, E, S.nE, S.mu, u[i]));
-  int64_t pos = q0;
-  const int64_t tbl_n = S.tbl_n;
-  while (true) {
-    const int64_t left = q1 - pos;
-    int64_t cnt = tbl_n - tq;  // the block ends where the table ends
-    if (cnt > left) cnt = left;
-    const T* __restrict__ ap = Aseg + pos;
-    T s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    int64_t i = lane;
-    if (MODE_A) {
-      // coalesced dot product  <A[block], T[slice]>
-      const T* __restrict__ tp = tbl + tq;
-      for (; i + 96 < cnt; i += 128) {
-        const T a0 = ld_stream(ap + i), a1 = ld_stream(ap + i + 32), a2 = ld_stream(ap + i + 64), a3 = ld_stream(ap + i + 96);
-        s0 += a0 * tp[i];
-        s1 += a1 * tp[i + 32];
-        s2 += a2 * tp[i + 64];
-        s3 += a3 * tp[i + 96];
-      }
-      for (; i < cnt; i += 32) s0 += ld_stream(ap + i) * tp[i];
+  for (int i = 0; i < hn; ++i) pref[i + 1] = pref[i] * (double)xr[u[i]];
+  int u_last = hn ? u[hn - 1] : -1;           // == u[hn-1]
+  double pref_prev = hn ? pref[hn - 1] : wE;  // == pref[hn-1]
+  double hw = pref[hn];
+  int pb = 0;                                  // current piece [pb, pe), positions relative to q0
+  int pe = (tbl_n - tq < n) ? tbl_n - tq : n;
+  int toff = tq;
+  T s = T(0);          // per-lane partial of the current piece
+  double total = 0.0;  // per-lane running total
+
+  // next block: lexicographic successor of the head combination
+  auto advance = [&]() {
+    pb = pe;
+    if (hn == 0) { pe = n; return; }  // defensive: a segment with hn == 0 is a single block
+    if (u_last + 1 <= Rt - tau - 1) {
+      ++u_last;  // fast path: no carry
     } else {
-      for (; i + 32 < cnt; i += 64) {
-        const T a0 = ld_stream(ap + i), a1 = ld_stream(ap + i + 32);
-        s0 += a0 * xrel_pow<T>(xs, E, S.nE, S.mu, (int32_t)(tq + i));
-        s1 += a1 * xrel_pow<T>(xs, E, S.nE, S.mu, (int32_t)(tq + i + 32));
-      }
-      for (; i < cnt; i += 32) s0 += ld_stream(ap + i) * xrel_pow<T>(xs, E, S.nE, S.mu, (int32_t)(tq + i));
+      u[hn - 1] = u_last;
+      int j = hn - 1;
+      while (j >= 0 && u[j] + 1 > Rt - (gt - j)) --j;
+      if (j < 0) { pe = n; return; }  // defensive: cannot happen inside a segment
+      ++u[j];
+      for (int k = j + 1; k < hn; ++k) u[k] = u[k - 1] + 1;
+      for (int k = j; k < hn - 1; ++k) pref[k + 1] = pref[k] * (double)xr[u[k]];
+      u_last = u[hn - 1];
+      pref_prev = pref[hn - 1];
     }
-    total += pref[hn] * ((double)(s0 + s1) + (double)(s2 + s3));
-    pos += cnt;
-    if (pos >= q1) break;
-    // next head (warp-uniform): increment u[hn-1], carrying while no room is left for the rest of the run
-    int j = hn - 1;
-    while (j >= 0 && u[j] + 1 > Rt - (gt - j)) --j;
-    if (j < 0) break;  // defensive: cannot happen inside a segment
-    ++u[j];
-    for (int k = j + 1; k < hn; ++k) u[k] = u[k - 1] + 1;
-    for (int k = j; k < hn; ++k)
-      pref[k + 1] = pref[k] * (double)(MODE_A ? xr[u[k]] : xrel_pow<T>(xs, E, S.nE, S.mu, u[k]));
-    // first tail of the new head is (b+1, b+2, ..), b = u[hn-1]: table index tbl_n - C(Rt-1-b, tau)
-    tq = tbl_n - binom_at(bt, rk, Rt - 1 - u[hn - 1], tau);
+    hw = pref_prev * (double)xr[u_last];
+    // first tail of the new head is (b+1, b+2, ..), b = u_last: block length C(Rt-1-b, tau), at the table's end
+    const int bl = tau == 1 ? Rt - 1 - u_last : (blen ? blen[u_last] : (int)binom_at(bt, rk, Rt - 1 - u_last, tau));
+    toff = tbl_n - bl - pb;
+    pe = (bl < n - pb) ? pb + bl : n;
+  };
+  // consume the slot [base, slot_end): this lane holds component base + lane in v (0 beyond slot_end)
+  auto slot = [&](int base, int slot_end, T v) {
+    const int idx = base + lane;
+    while (true) {
+      const bool in = (idx >= pb) & (idx < pe);
+      const T tv = tbl[toff + (in ? idx : pb)];
+      s += (in ? v : T(0)) * tv;
+      if (pe >= slot_end) break;  // the piece covers the rest of the slot
+      total += hw * (double)s;
+      s = T(0);
+      advance();
+    }
+  };
+
+  const T* __restrict__ ap = Aseg + q0;
+  bool staged = false;
+#ifdef __CUDA_ARCH__
+  staged = STAGED;
+  if (STAGED) {
+    constexpr int VEC = 16 / (int)sizeof(T);  // components per 16-byte vector
+    constexpr int STAGE_E = 2 * 32 * VEC;     // a stage is 1 KB: two 16-byte vectors per lane
+    // consume one stage [base, slot_end) held at shared address `sp`
+    auto vslot = [&](const T* __restrict__ sp, int base, int slot_end) {
+      if (pb <= base && pe >= base + STAGE_E && slot_end == base + STAGE_E) {
+        // warp-uniform fast path: one piece covers the whole stage; each lane multiplies two 16-byte vectors
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int off = h * 32 * VEC + lane * VEC;
+          const float4 raw = *reinterpret_cast<const float4*>(sp + off);
+          const T* __restrict__ tp = tbl + (toff + base + off);
+          if (sizeof(T) == 8) {
+            s += (T)__hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x)) * tp[0];
+            s += (T)__hiloint2double(__float_as_int(raw.w), __float_as_int(raw.z)) * tp[VEC - 1];
+          } else {
+            s += (T)raw.x * tp[0];
+            s += (T)raw.y * tp[1 % VEC];
+            s += (T)raw.z * tp[2 % VEC];
+            s += (T)raw.w * tp[3 % VEC];
+          }
+        }
+        return;
+      }
+      // general path, piece-major: lanes stride the components of each piece that overlaps the stage
+      while (true) {
+        const int lo = pb > base ? pb : base, hi = pe < slot_end ? pe : slot_end;
+        const T* __restrict__ tp = tbl + toff;
+        for (int idx = lo + lane; idx < hi; idx += 32) s += sp[idx - base] * tp[idx];
+        if (pe >= slot_end) break;
+        total += hw * (double)s;
+        s = T(0);
+        advance();
+      }
+    };
+    int a0 = (int)(((16u - (unsigned)((uintptr_t)ap & 15u)) & 15u) / sizeof(T));  // components before 16-byte alignment
+    if (a0 > n) a0 = n;
+    if (a0 > 0) slot(0, a0, lane < a0 ? ld_stream(ap + lane) : T(0));
+    const int nb = (n - a0) / VEC * VEC;  // body: whole 16-byte vectors
+    const int nchunks = (nb + STAGE_E - 1) / STAGE_E;
+    const int body_end = a0 + nb;
+    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
+    const char* __restrict__ gp = reinterpret_cast<const char*>(ap + a0 + lane * VEC);  // this lane's next vector to fetch
+    int e_next = lane * VEC;                                                             // its component index in the body
+    auto fetch = [&](int stage) {
+      if (e_next < nb) st_cp_async16(ring_s + stage * 1024, gp);
+      if (e_next + 32 * VEC < nb) st_cp_async16(ring_s + stage * 1024 + 512, gp + 512);
+      st_cp_async_commit();
+      gp += 1024;
+      e_next += STAGE_E;
+    };
+#pragma unroll
+    for (int c = 0; c < NST - 1; ++c) fetch(c);
+    int st = 0;           // stage holding chunk c
+    int st_in = NST - 1;  // stage receiving chunk c + NST - 1
+    int cbase = a0;
+    for (int c = 0; c < nchunks; ++c) {
+      fetch(st_in);
+      st_cp_async_wait<NST - 1>();
+      __syncwarp();
+      const int cend = (cbase + STAGE_E < body_end) ? cbase + STAGE_E : body_end;
+      vslot(ring + st * STAGE_E, cbase, cend);
+      __syncwarp();  // the stage is overwritten by the copy issued in the next iteration
+      st = (st + 1 == NST) ? 0 : st + 1;
+      st_in = (st_in + 1 == NST) ? 0 : st_in + 1;
+      cbase += STAGE_E;
+    }
+    if (body_end < n) slot(body_end, n, body_end + lane < n ? ld_stream(ap + body_end + lane) : T(0));
   }
+#endif
+  if (!staged) {
+    for (int base = 0; base < n; base += 32) {
+      const int idx = base + lane;
+      slot(base, (base + 32 < n) ? base + 32 : n, idx < n ? ap[idx] : T(0));
+    }
+  }
+  return total + hw * (double)s;
 }
 
+template <typename T>
+ST_HD double walk_range_direct(const PlanView& P, const TailStrategy& S, const T* tbl, const T* xr, const int32_t* blen, double wE,
+                               const T* Aseg, int64_t q0, int64_t q1, int lane) {
+  return walk_range<T, 2, false>(P, S, tbl, xr, blen, wE, Aseg, q0, q1, lane, nullptr, nullptr);
+}
+
+#ifdef __CUDACC__
+// Warp-cooperative inverse of comb_rank: every lane tests one candidate value per step (ballot), so a
+// combination is unranked in a few steps instead of g binary searches of ~40 64-bit instructions per probe.
+// All lanes return the same combination.  Must be called by a full, converged warp.
+__device__ __forceinline__ void comb_unrank_warp(const int64_t* __restrict__ tbl, int rank, int64_t r, int n, int g, int32_t* c, int lane) {
+  int prev = -1;
+  for (int i = 0; i < g; ++i) {
+    const int k = g - i;
+    const int64_t all = binom_at(tbl, rank, n - 1 - prev, k);
+    // largest v in [prev + 1, n - k] with  all - C(n - v, k) <= r ; the predicate is monotone (true ... true false ...)
+    int v = prev + 1;
+    while (true) {
+      const int cand = v + lane;
+      const bool ok = cand <= n - k && all - binom_at(tbl, rank, n - cand, k) <= r;
+      const unsigned m = __ballot_sync(0xffffffffu, ok);
+      const int cnt = __popc(m);
+      v += cnt;
+      if (cnt < 32) break;
+    }
+    v -= 1;  // last candidate that satisfied the predicate (v = prev + 1 always does)
+    r -= all - binom_at(tbl, rank, n - v, k);
+    c[i] = v;
+    prev = v;
+  }
+}
+#endif
 
 // T[q] = prod of xr over the q-th tau-combination of range(Rt), for q in [q, qe): contiguous slice of one thread
 template <typename T>

@@ -11,7 +11,7 @@
 #include "../../symtensor_b200/csrc/st_vec_core.cuh"
 
 namespace st {
-bool compute_tail_strategy(const HostPlan* hp, int esize, std::vector<TailStrategy>& st, int32_t* tbl_cap, size_t* smem_bytes);
+bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, int nst, std::vector<TailStrategy>& st, int32_t* tbl_cap, size_t* smem_bytes);
 extern int g_force_tau;
 }
 
@@ -27,11 +27,12 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
   int32_t tbl_cap = 0;
   size_t smem = 0;
   g_force_tau = force_tau;
-  const bool ok = compute_tail_strategy(hp, (int)sizeof(T), strat, &tbl_cap, &smem);
+  const bool ok = compute_tail_strategy(hp, (int)sizeof(T), nwarps, 6, strat, &tbl_cap, &smem);
   g_force_tau = 0;
   if (!ok) return 3;
   if (taus_out) for (int c = 0; c < hp->ncls; ++c) taus_out[c] = strat[c].tau;
   std::vector<T> tbl(tbl_cap), xr(dim + 1), xs(dim + 1);
+  std::vector<int32_t> blen(dim + 1);
   for (int64_t i = 0; i < dim; ++i) xs[i] = x[i];
   const int64_t n_items = (end - begin + item_elems - 1) / item_elems;
   double grand = 0.0;
@@ -61,13 +62,15 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
             int64_t w0 = pos + (int64_t)warp * per;
             const int64_t w1 = (w0 + per < pend) ? w0 + per : pend;
             int32_t E[ST_MAX_RANK];
+            std::vector<T> priv(dim + 1);
             while (w0 < w1) {
               const int64_t sidx = w0 / S.seg;
               const int64_t sbase = sidx * S.seg;
               const int64_t q1 = (S.seg < w1 - sbase) ? S.seg : w1 - sbase;
               const double wE = unrank_earlier<T>(P, C, sidx, xs.data(), E);
+              for (int uu = 0; uu < S.Rt; ++uu) priv[uu] = xrel_pow<T>(xs.data(), E, S.nE, S.mu, uu);
               for (int lane = 0; lane < 32; ++lane)
-                walk_piece<T, false>(P, S, nullptr, nullptr, xs.data(), E, wE, Acls + sbase, w0 - sbase, q1, lane, lane_total[warp * 32 + lane]);
+                lane_total[warp * 32 + lane] += walk_range_direct<T>(P, S, priv.data(), priv.data(), nullptr, wE, Acls + sbase, w0 - sbase, q1, lane);
               w0 = sbase + q1;
             }
           }
@@ -82,7 +85,10 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
               ctl_wE = unrank_earlier<T>(P, C, sidx, xs.data(), ctlE);
               cur_cls = ci;
               cur_seg = sidx;
-              for (int uu = 0; uu < S.Rt; ++uu) xr[uu] = xrel_pow<T>(xs.data(), ctlE, S.nE, S.mu, uu);
+              for (int uu = 0; uu < S.Rt; ++uu) {
+                xr[uu] = xrel_pow<T>(xs.data(), ctlE, S.nE, S.mu, uu);
+                blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
+              }
               const int nthreads = nwarps * 32;
               const int64_t per = (S.tbl_n + nthreads - 1) / nthreads;
               for (int t = 0; t < nthreads; ++t) {
@@ -98,7 +104,7 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
               const int64_t w1 = (w0 + per < q1) ? w0 + per : q1;
               if (w0 < w1)
                 for (int lane = 0; lane < 32; ++lane)
-                  walk_piece<T, true>(P, S, tbl.data(), xr.data(), xs.data(), ctlE, ctl_wE, Acls + sbase, w0, w1, lane, lane_total[warp * 32 + lane]);
+                  lane_total[warp * 32 + lane] += walk_range_direct<T>(P, S, tbl.data(), xr.data(), blen.data(), ctl_wE, Acls + sbase, w0, w1, lane);
             }
             pos = sbase + q1;
           }
