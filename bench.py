@@ -5,8 +5,8 @@ components, 549.5 MB), reported as packed components/s plus the achieved fractio
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one full vector contraction of the resident packed tensor (main kernel + deterministic finalize,
-and for N > 1 the scalar NCCL all-reduce).  N > 1 (launched by torchrun, one rank per GPU): WEAK scaling -- the
+One "step" = one full vector contraction of the resident packed tensor (ONE kernel launch: streaming pass with the
+deterministic finalize fused in; for N > 1 followed by the scalar NCCL all-reduce).  N > 1 (launched by torchrun, one rank per GPU): WEAK scaling -- the
 packed coordinate range of a rank-4 tensor whose dimension grows with N (200, 238, 283, 337: ~6.9e7 components
 per GPU) is split into N contiguous 32-aligned slices, one per GPU; x is replicated; the only collective is the
 all-reduce of the partial sums.  The strong-scaling figure (the dim-200 tensor itself cut N ways) is reported in
@@ -332,7 +332,7 @@ def run_gpu(args):
                        "l2": "input (549 MB per GPU) is larger than the 126 MB L2: no flush needed", "result": result},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n_comps), "peak_source": peak_src,
-                         "kernel": "vec_tail_kernel<double> (+ vec_finalize_kernel, timed together per step)",
+                         "kernel": "vec_tail_kernel<double, 4> (one launch per step: streaming pass with the fused deterministic finalize)",
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks.summary(),
             "gpu_launches": int(launches),

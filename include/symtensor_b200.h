@@ -126,8 +126,8 @@ int st_contract_vec_host_f32(int layout, int rank, int64_t dim, const float* h_p
 /* kernel variant selection for benchmarking / tests: 0 = auto, 1 = generic per-element enumerator,
  * 2 = tail-table segmented kernel.  Process-wide. */
 int st_set_vec_variant(int variant);
-/* tuning hooks (process-wide; defaults are the tuned values): "vec_ring_stages" in {2, 3, 4, 6, 8},
- * "vec_items_per_cta" in [1, 64], "vec_force_tau" in [0, ST_MAX_RANK] (0 = cost model). */
+/* tuning hooks (process-wide; defaults are the tuned values): "vec_tile_bytes" in [1024, 2^28],
+ * "vec_force_tau" in [0, ST_MAX_RANK] (0 = cost model). */
 int st_set_tuning(const char* key, int64_t value);
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 int64_t st_launch_count(void);

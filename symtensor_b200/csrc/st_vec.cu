@@ -28,12 +28,12 @@
 namespace st {
 
 static const int kMaxCtas = 148 * 8;
-static const int kMaxPartials = 4096;   // fp64 partial sums per launch (one per work item / per CTA)
+static const int kMaxPartials = 4096;   // fp64 partial sums per launch (one per warp of the grid / per CTA)
 static const int kTailThreads = 512;    // 16 warps per CTA, one CTA per SM (the tail table fills shared memory)
-static const int kStageBytes = 1024;    // two 16-byte cp.async per lane
-// tuning knobs (st_set_tuning): work items per CTA, ring depth
-static int g_items_per_cta = 8;
-static int g_ring_stages = 4;
+static int g_batch_slots = 4;           // 16-byte vectors per lane and batch; two batches in flight (tuning knob)
+static const int kBinomSmemMax = 40 * 1024;  // the binomial table is copied to shared memory when it is at most this big
+// tuning knob (st_set_tuning): bytes per tile
+static int g_tile_bytes = 16 * 1024;
 
 template <typename T>
 struct VecArgs {
@@ -42,11 +42,17 @@ struct VecArgs {
   const T* A;        // points at packed coordinate `begin`
   const T* x;
   int64_t begin, end;
-  double* partials;  // [gridDim.x]
-  int64_t n_items;
-  int64_t item_elems;  // packed coordinates per work item (multiple of ST_CLASS_ALIGN)
-  unsigned long long* counter;  // [2]: next work item, finished CTAs (library-owned, per stream, self-resetting)
+  double* partials;  // [warps of the grid] (tail kernel) / [gridDim.x] (generic kernel)
+  T* out;            // fused finalize: the last CTA to finish adds the partials in index order (nullptr: caller finalizes)
+  int64_t tile_elems;  // components per tile (multiple of ST_CLASS_ALIGN)
+  const DirEntry* dir;         // tile directory (nullptr: unrank every tile start)
+  const int64_t* tile_base;    // [ncls + 1] first directory entry of each class
+  const DirEntry* sdir;        // per-component directory of the small classes (nullptr: unrank)
+  const int64_t* sbase;        // [ncls + 1] first sdir entry of each class
+  unsigned long long* counter;  // finished CTAs (library-owned, per stream, self-resetting)
   int32_t tbl_cap;     // table entries that fit the dynamic shared memory
+  int32_t binom_smem;  // entries of the binomial table to copy to shared memory (0: use the global copy)
+  int32_t cdesc_smem;  // copy the class descriptors to shared memory
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(256) vec_generic_kernel(VecArgs<T> a) {
   const PlanView& P = a.P;
   double acc = 0.0;
   for (int64_t c = a.begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < a.end; c += (int64_t)gridDim.x * blockDim.x) {
-    const double v = (double)ld_stream(a.A + (c - a.begin));
+    const double v = (double)__ldcs(a.A + (c - a.begin));
     if (LAYOUT == ST_LAYOUT_PERMCLS) {
       const int ci = class_of_coord(P, c);
       const ClassDesc& C = P.cls[ci];
@@ -125,21 +131,66 @@ __global__ void __launch_bounds__(256) vec_generic_kernel(VecArgs<T> a) {
   block_store_partial(acc, red, a.partials + blockIdx.x);
 }
 
-// One warp streams segment positions [q0, q1): unrank the start with the whole warp, then the staged walk.
-template <typename T, int NST>
-__device__ __forceinline__ double walk_range_staged(const PlanView& P, const TailStrategy& S, const T* tbl, const T* xr,
-                                                    const int32_t* blen, double wE, const T* __restrict__ Aseg, int64_t q0, int64_t q1,
-                                                    int lane, T* ring) {
-  int32_t u0[ST_MAX_RANK];
-  comb_unrank_warp(P.binom, P.rank, q0, S.Rt, S.gt, u0, lane);
-  return walk_range<T, NST, true>(P, S, tbl, xr, blen, wE, Aseg, q0, q1, lane, ring, u0);
+// Per-class record kept in shared memory (everything the scheduling loop needs, so that it never waits on a
+// global load).
+struct ClsInfo {
+  int64_t offset, size;
+  int64_t tile_base;  // tiles of the classes before this one (whole tensor): index into the tile directory
+  int64_t sbase;      // components of the SMALL classes before this one: index into the per-component directory
+  TailStrategy S;
+};
+
+// GPU index enumerator, bulk form: the values of the component at the start of every tile
+__global__ void vec_dir_kernel(PlanView P, int64_t tile, const int64_t* __restrict__ tile_base, int64_t ntiles, DirEntry* __restrict__ dir) {
+  const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (t >= ntiles) return;
+  int lo = 0, hi = P.ncls - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_base[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  const ClassDesc& C = P.cls[lo];
+  const int64_t pos = (t - tile_base[lo]) * tile;
+  DirEntry e;
+  for (int i = 0; i < ST_MAX_RANK; ++i) e.v[i] = 0;
+  if (pos < C.size) {
+    int32_t vals[ST_MAX_RANK];
+    permcls_unrank_vals(P, C, pos, vals);
+    for (int i = 0; i < C.nvals; ++i) e.v[i] = (uint16_t)vals[i];
+  }
+  dir[t] = e;
 }
 
-// Shared memory: [T / private xr tables][xr: dim][xs: dim][blen: dim x i32][ring: nwarps x NST x 512 B][ctrl]
-template <typename T, int NST>
+// CTA-wide build of the shared tail table (xr must be in place and visible); ends with a barrier
+template <typename T>
+__device__ __forceinline__ void build_shared_table(const PlanView& P, const TailStrategy& S, const T* xr, T* tbl) {
+  int64_t nA, nB;
+  table_scratch(P.binom, P.rank, S.Rt, S.tau, &nA, &nB);
+  for (int t = 2; t <= S.tau; ++t) {
+    const T* src = t == 2 ? xr : table_level_buffer<T>(tbl, S.tbl_n, nA, S.tau, t - 1);
+    T* dst = table_level_buffer<T>(tbl, S.tbl_n, nA, S.tau, t);
+    build_table_level<T>(P.binom, P.rank, S.Rt, t, xr, src, dst, threadIdx.x, kTailThreads);
+    __syncthreads();
+  }
+}
+
+// Scheduling (device part of the plan): the packed range is walked CLASS BY CLASS (a class is one phase: its
+// tables are built once, then no CTA-wide barrier is needed until the next class).  Inside a class the work is
+// cut into TILES of `tile` components (16 KB) numbered in address order, and tile t belongs to warp
+// (t mod W) of the grid (W = all warps): at any moment the whole grid reads one compact window of a few tens
+// of MB that slides through the tensor, which is what the memory system wants (wide windows lose up to 2x,
+// tools/membench), every warp streams independently of the others (no per-tile barrier, no atomics), and the
+// per-warp sums are added in a fixed order -- the result is deterministic.
+//   mode A  (tau == 1: per-warp private tables; or a single-segment class: one shared table per class)
+//           tiles are per warp;
+//   mode B  (tau >= 2 and several segments: the shared table T depends on the segment) chunks of 16 tiles are
+//           per CTA, T is rebuilt with __syncthreads when the segment changes, warps split the chunk.
+// Shared memory: [T / private xr tables][xr: dim][xs: dim][blen: dim x i32][binomial table (optional)]
+//                [ClsInfo x ncls][ctrl]
+template <typename T, int U>
 __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const PlanView& P = a.P;
+  PlanView P = a.P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nwarps = kTailThreads / 32;
   T* tbl = reinterpret_cast<T*>(smem_raw);
@@ -150,65 +201,201 @@ __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a)
   off = (off + 2 * (size_t)P.dim * sizeof(T) + 15) / 16 * 16;
   int32_t* blen = reinterpret_cast<int32_t*>(smem_raw + off);
   off = (off + (size_t)P.dim * sizeof(int32_t) + 15) / 16 * 16;
-  T* ring = reinterpret_cast<T*>(smem_raw + off + (size_t)warp * NST * kStageBytes);
-  off += (size_t)nwarps * NST * kStageBytes;
+  int64_t* binom_s = reinterpret_cast<int64_t*>(smem_raw + off);
+  off += (size_t)a.binom_smem * sizeof(int64_t);
+  ClsInfo* cls_s = reinterpret_cast<ClsInfo*>(smem_raw + off);
+  off += (size_t)P.ncls * sizeof(ClsInfo);
+  ClassDesc* cdesc_s = reinterpret_cast<ClassDesc*>(smem_raw + off);  // class descriptors (when a.cdesc_smem)
+  off += a.cdesc_smem ? (size_t)P.ncls * sizeof(ClassDesc) : 0;
+  off = (off + 15) / 16 * 16;
+  WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw + off)[warp];
+  off += (size_t)nwarps * sizeof(WarpScratch);
   TailCtrl* ctl = reinterpret_cast<TailCtrl*>(smem_raw + off);
   if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
   for (int i = threadIdx.x; i < P.dim; i += kTailThreads) xs[i] = a.x[i];
+  if (a.binom_smem) {
+    for (int i = threadIdx.x; i < a.binom_smem; i += kTailThreads) binom_s[i] = a.P.binom[i];
+    P.binom = binom_s;
+  }
+  if (a.cdesc_smem) {
+    const int nw = (int)(sizeof(ClassDesc) / 4) * P.ncls;
+    for (int i = threadIdx.x; i < nw; i += kTailThreads) reinterpret_cast<int32_t*>(cdesc_s)[i] = reinterpret_cast<const int32_t*>(a.P.cls)[i];
+    P.cls = cdesc_s;
+  }
+  for (int c = threadIdx.x; c < P.ncls; c += kTailThreads) {
+    cls_s[c].offset = a.P.cls[c].offset;
+    cls_s[c].size = a.P.cls[c].size;
+    cls_s[c].tile_base = a.tile_base ? a.tile_base[c] : 0;
+    cls_s[c].sbase = a.sbase ? a.sbase[c] : 0;
+    cls_s[c].S = a.strat[c];
+  }
+  __syncthreads();
   int priv_cls = -1;       // (class, segment) the private table was built for -- warp-uniform
   int64_t priv_seg = -1;
   double priv_wE = 0.0;
+  const int64_t W = (int64_t)gridDim.x * nwarps;         // warps of the grid
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // this warp
+  const int64_t tile = a.tile_elems;
+  int64_t tile_base = 0;  // tiles of the classes before the current one (rotates the tile -> warp map)
+  double total = 0.0;
+  constexpr int kBatchElems = U * 32 * (16 / (int)sizeof(T));
+  T bufA[U][16 / sizeof(T)], bufB[U][16 / sizeof(T)];  // the stream's two register batches (see walk_range)
 
-  while (true) {
-    // ---- dynamic scheduling: CTAs claim work items from a global counter (slow regions cannot pile up on one CTA)
-    __syncthreads();
-    if (threadIdx.x == 0) ctl->item = (long long)atomicAdd(a.counter, 1ULL);
-    __syncthreads();
-    const int64_t item = ctl->item;
-    if (item >= a.n_items) break;
-    double total = 0.0;
-    const int64_t c0 = a.begin + item * a.item_elems;
-    const int64_t c1 = (c0 + a.item_elems < a.end) ? c0 + a.item_elems : a.end;
-    int64_t coord = c0;
-    while (coord < c1) {
-      const int ci = class_of_coord(P, coord);
+  // ---- phase 0: SMALL classes (tau == 0 in the strategy), one component per thread with a full unrank of its
+  // index (the bulk form of the index enumerator): no tables, no barriers, all the grid's threads at once.
+  // The per-lane sums stay in `total` (fixed thread -> component map: deterministic).
+  {
+    int64_t sm_base = 0;  // components of the small classes before the current one
+    const int64_t nthreads = W * 32, tid = gw * 32 + lane;
+    for (int ci = 0; ci < P.ncls; ++ci) {
+      if (cls_s[ci].S.tau != 0) continue;
+      const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
+      const int64_t lo = (a.begin > coff ? a.begin : coff) - coff;
+      const int64_t hi = (a.end < coff + csize ? a.end : coff + csize) - coff;
+      if (lo >= hi) continue;
       const ClassDesc& C = P.cls[ci];
-      int64_t pos = coord - C.offset;
-      if (pos >= C.size) { coord = P.offsets[ci + 1]; continue; }  // padding up to the next class
-      const int64_t pend = (C.size < c1 - C.offset) ? C.size : c1 - C.offset;
-      const TailStrategy S = a.strat[ci];
-      const T* Acls = a.A + (C.offset - a.begin);
-      if (S.tau == 1) {
-        // ---- private tables: warps split the class range; each warp walks its segments on its own
-        if (ctl->cur_cls != -1) {  // CTA-uniform: the private tables overwrite the shared table
-          __syncthreads();
-          if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
-          __syncthreads();
+      const T* Acls = a.A + (coff - a.begin);
+      const int nvals = C.nvals;
+      const double gamma = (double)C.gamma;
+      for (int64_t p = lo + (tid - sm_base % nthreads + nthreads) % nthreads; p < hi; p += nthreads) {
+        const double v = (double)__ldcs(Acls + p);
+        double w = gamma;
+        if (a.sdir != nullptr) {
+          // the component's values come from the per-component directory of the small classes (written once per
+          // plan by the index enumerator): no unrank, no thread-local arrays
+          const uint4* q = reinterpret_cast<const uint4*>(a.sdir + (cls_s[ci].sbase + p));
+          const uint4 e0 = __ldg(q), e1 = __ldg(q + 1);
+          const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+          for (int k = 0; k < ST_MAX_RANK; ++k) {
+            if (k < nvals) {
+              const int val = (int)((words[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+              const double xv = (double)xs[val];
+              const int m = C.mult[k];
+              for (int mm = 0; mm < m; ++mm) w *= xv;
+            }
+          }
+        } else {
+          int32_t vals[ST_MAX_RANK];
+          permcls_unrank_vals(P, C, p, vals);
+          for (int k = 0; k < nvals; ++k) {
+            const double xv = (double)xs[vals[k]];
+            for (int m = 0; m < C.mult[k]; ++m) w *= xv;
+          }
         }
-        const int64_t len = pend - pos;
-        int64_t per = (len + nwarps - 1) / nwarps;
-        per = (per + 31) / 32 * 32;
-        int64_t w0 = pos + (int64_t)warp * per;
-        const int64_t w1 = (w0 + per < pend) ? w0 + per : pend;
-        while (w0 < w1) {
-          const int64_t sidx = w0 / S.seg;
+        total += v * w;
+      }
+      sm_base += hi - lo;
+    }
+  }
+
+  for (int ci = 0; ci < P.ncls; ++ci) {
+    if (cls_s[ci].S.tau == 0) continue;  // done in phase 0
+    const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
+    // positions [lo, hi) of class ci inside the launch range
+    const int64_t lo = (a.begin > coff ? a.begin : coff) - coff;
+    const int64_t hi = (a.end < coff + csize ? a.end : coff + csize) - coff;
+    if (lo >= hi) continue;
+    const TailStrategy S = cls_s[ci].S;
+    const ClassDesc& C = P.cls[ci];
+    const T* Acls = a.A + (coff - a.begin);
+    const int64_t k0 = lo / tile, k1 = (hi + tile - 1) / tile;  // tiles k0 .. k1-1, tile k = [k*tile, (k+1)*tile)
+    if (S.tau == 1 || S.nE == 0) {
+      // ---- mode A
+      if (S.tau >= 2) {
+        // one shared table for the whole class (no earlier runs)
+        __syncthreads();  // everybody is done with the previous tables
+        if (threadIdx.x == 0) {
+          ctl->wE = unrank_earlier<T>(P, C, 0, xs, ctl->E, ws);
+          ctl->cur_cls = ci;
+          ctl->cur_seg = 0;
+        }
+        priv_cls = -1;  // the shared table overwrites the private ones
+        for (int uu = threadIdx.x; uu < S.Rt; uu += kTailThreads) {
+          xr[uu] = xrel_pow<T>(xs, ctl->E, 0, S.mu, uu);
+          blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
+        }
+        __syncthreads();
+        build_shared_table<T>(P, S, xr, tbl);
+      } else if (ctl->cur_cls != -1) {  // CTA-uniform: the private tables overwrite the shared table
+        __syncthreads();
+        if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
+        __syncthreads();
+      }
+      const double wE0 = ctl->wE;
+      const int64_t dbase = cls_s[ci].tile_base;
+      int64_t j = (gw - tile_base % W + W) % W;  // first tile of this class that belongs to this warp
+      uint4 dn0 = make_uint4(0, 0, 0, 0), dn1 = dn0;  // the next tile's directory entry, fetched one tile ahead
+      auto fetch_entry = [&](int64_t t) {
+        const uint4* q = reinterpret_cast<const uint4*>(a.dir + t);
+        dn0 = __ldg(q);
+        dn1 = __ldg(q + 1);
+      };
+      if (a.dir && k0 + j < k1) fetch_entry(dbase + k0 + j);
+      bool preloaded = false;
+      int32_t* E = ws.E;
+      int32_t* u0 = ws.u0;
+      for (; k0 + j < k1; j += W) {
+        int64_t w0 = (k0 + j) * tile;
+        int64_t w1 = w0 + tile;
+        const bool have_dir = a.dir != nullptr && w0 >= lo;  // the tile starts inside the launch range
+        if (w0 < lo) w0 = lo;
+        if (w1 > hi) w1 = hi;
+        __syncwarp();
+        reinterpret_cast<uint4*>(&ws.de)[0] = dn0;
+        reinterpret_cast<uint4*>(&ws.de)[1] = dn1;
+        __syncwarp();
+        const DirEntry& de = ws.de;
+        if (a.dir && k0 + j + W < k1) fetch_entry(dbase + k0 + j + W);  // latency hidden behind this tile
+        if (S.tau >= 2) {
+          if (have_dir) {  // single-run class: the entry is the combination itself
+            for (int i = 0; i < S.gt; ++i) u0[i] = de.v[i];
+          }
+          // stream across tiles: this tile requests the first two batches of the warp's next tile when both
+          // are whole tiles (even number of batches, 16-byte aligned starts)
+          const int64_t nk = k0 + j + W;
+          const bool chain = (w1 - w0 == tile) && nk < k1 && nk * tile >= lo && (nk + 1) * tile <= hi && (tile % (2 * kBatchElems) == 0);
+          total += walk_range<T, U>(P, S, tbl, xr, blen, wE0, Acls, w0, w1, lane, have_dir ? u0 : nullptr, bufA, bufB, preloaded,
+                                    chain ? Acls + nk * tile : nullptr, ws);
+          preloaded = chain;
+          continue;
+        }
+        bool first = true;
+        while (w0 < w1) {  // private tables: segment by segment
+          const int64_t sidx = S.nE ? w0 / S.seg : 0;
           const int64_t sbase = sidx * S.seg;
           const int64_t q1 = (S.seg < w1 - sbase) ? S.seg : w1 - sbase;
+          const bool from_dir = first && have_dir;
+          if (from_dir) {
+            const double wE = dir_decode<T>(C, S, de, xs, E, u0);
+            if (priv_cls != ci || priv_seg != sidx) priv_wE = wE;
+          } else if (w0 == sbase) {
+            for (int i = 0; i < S.gt; ++i) u0[i] = i;  // a segment starts with the first combination
+          }
           if (priv_cls != ci || priv_seg != sidx) {
-            int32_t E[ST_MAX_RANK];
-            priv_wE = unrank_earlier<T>(P, C, sidx, xs, E);
+            if (!from_dir) priv_wE = unrank_earlier<T>(P, C, sidx, xs, E, ws);
             __syncwarp();
             for (int uu = lane; uu < S.Rt; uu += 32) priv[uu] = xrel_pow<T>(xs, E, S.nE, S.mu, uu);
             __syncwarp();
             priv_cls = ci;
             priv_seg = sidx;
           }
-          total += walk_range_staged<T, NST>(P, S, priv, priv, nullptr, priv_wE, Acls + sbase, w0 - sbase, q1, lane, ring);
+          total += walk_range<T, U>(P, S, priv, priv, nullptr, priv_wE, Acls + sbase, w0 - sbase, q1, lane,
+                                    (from_dir || w0 == sbase) ? u0 : nullptr, bufA, bufB, false, nullptr, ws);
           w0 = sbase + q1;
+          first = false;
         }
-        pos = pend;
-      } else {
-        // ---- shared table: the CTA builds T once per segment
+      }
+    } else {
+      // ---- mode B: chunks of nwarps tiles per CTA; the CTA rebuilds T once per segment
+      const int64_t ch0 = k0 / nwarps, ch1 = (k1 + nwarps - 1) / nwarps;
+      const int64_t chunk = tile * nwarps;
+      int64_t jc = ((int64_t)blockIdx.x - (tile_base / nwarps) % gridDim.x + gridDim.x) % gridDim.x;
+      for (; ch0 + jc < ch1; jc += gridDim.x) {
+        int64_t pos = (ch0 + jc) * chunk;
+        int64_t pend = pos + chunk;
+        if (pos < lo) pos = lo;
+        if (pend > hi) pend = hi;
         while (pos < pend) {
           const int64_t sidx = pos / S.seg;
           const int64_t sbase = sidx * S.seg;
@@ -217,7 +404,15 @@ __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a)
           if (ctl->cur_cls != ci || ctl->cur_seg != sidx) {  // CTA-uniform
             __syncthreads();  // everybody is done with the previous tables
             if (threadIdx.x == 0) {
-              ctl->wE = unrank_earlier<T>(P, C, sidx, xs, ctl->E);
+              // the earlier runs of this segment: from the directory entry of a tile that starts inside the
+              // segment when there is one (cheap), else by unranking the segment index
+              const int64_t tk0 = (sbase + tile - 1) / tile;
+              if (a.dir != nullptr && tk0 * tile < sbase + S.seg && tk0 * tile < csize) {
+                ws.de = a.dir[cls_s[ci].tile_base + tk0];
+                ctl->wE = dir_decode<T>(C, S, ws.de, xs, ctl->E, ws.u0);
+              } else {
+                ctl->wE = unrank_earlier<T>(P, C, sidx, xs, ctl->E, ws);
+              }
               ctl->cur_cls = ci;
               ctl->cur_seg = sidx;
             }
@@ -228,37 +423,65 @@ __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a)
               blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
             }
             __syncthreads();
-            {  // T[q] over the tau-combinations of range(Rt); each thread fills a contiguous slice
-              const int64_t per = (S.tbl_n + kTailThreads - 1) / kTailThreads;
-              const int64_t q = (int64_t)threadIdx.x * per;
-              build_table_slice<T>(P, S, xr, tbl, q, (q + per < S.tbl_n) ? q + per : S.tbl_n);
-            }
-            __syncthreads();
+            build_shared_table<T>(P, S, xr, tbl);
           }
-          // warps split the piece [q0, q1) evenly (multiples of 32 components)
-          const int64_t len = q1 - q0;
-          int64_t per = (len + nwarps - 1) / nwarps;
-          per = (per + 31) / 32 * 32;
-          const int64_t w0 = q0 + (int64_t)warp * per;
-          const int64_t w1 = (w0 + per < q1) ? w0 + per : q1;
-          if (w0 < w1) total += walk_range_staged<T, NST>(P, S, tbl, xr, blen, ctl->wE, Acls + sbase, w0, w1, lane, ring);
+          // warp w takes tile w of the chunk, clipped to this segment's piece [q0, q1): it starts either at a
+          // tile start (directory) or at the start of the segment (first combination)
+          {
+            const int64_t tk = (ch0 + jc) * nwarps + warp;  // tile index inside the class
+            int64_t w0 = tk * tile - sbase, w1 = w0 + tile;
+            const bool at_tile = w0 >= q0;
+            if (w0 < q0) w0 = q0;
+            if (w1 > q1) w1 = q1;
+            if (w0 < w1) {
+              int32_t* u0 = ws.u0;
+              const int32_t* ui = nullptr;
+              if (w0 == 0) {
+                for (int i = 0; i < S.gt; ++i) u0[i] = i;
+                ui = u0;
+              } else if (at_tile && a.dir != nullptr) {
+                __syncwarp();
+                ws.de = a.dir[cls_s[ci].tile_base + tk];
+                __syncwarp();
+                dir_decode<T>(C, S, ws.de, xs, ws.E, u0);
+                ui = u0;
+              }
+              total += walk_range<T, U>(P, S, tbl, xr, blen, ctl->wE, Acls + sbase, w0, w1, lane, ui, bufA, bufB, false, nullptr, ws);
+            }
+          }
           pos = sbase + q1;
         }
       }
-      coord = C.offset + pos;
     }
-    // one partial per ITEM (not per CTA): the final sum does not depend on which CTA processed which item
-    __syncthreads();
-    block_store_partial(total, ctl->red, a.partials + item);
+    tile_base += k1 - k0;
   }
-  // self-cleaning counters: the last CTA to finish resets them for the next launch on this stream
+
+  // one partial per warp of the grid, added in index order by the last CTA to finish (deterministic; saves the
+  // second launch).  The ticket counter is self-resetting.
+  total = warp_sum(total);
+  if (lane == 0) a.partials[gw] = total;
+  __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    const unsigned long long ticket = atomicAdd(a.counter + 1, 1ULL);
-    if (ticket == gridDim.x - 1) {
+    const unsigned long long ticket = atomicAdd(a.counter, 1ULL);
+    const bool last = ticket == gridDim.x - 1;
+    if (last) {
       a.counter[0] = 0ULL;
-      a.counter[1] = 0ULL;
       __threadfence();
+    }
+    ctl->last = last ? 1 : 0;
+  }
+  __syncthreads();
+  if (a.out != nullptr && ctl->last) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < W; i += kTailThreads) s += __ldcg(a.partials + i);
+    s = warp_sum(s);
+    if (lane == 0) ctl->red[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < nwarps ? ctl->red[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) *a.out = (T)t;
     }
   }
 }
@@ -266,19 +489,26 @@ __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a)
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
-static int g_variant = 0;
+static const size_t kClsInfoBytes = sizeof(ClsInfo);
+int g_variant = 0;
+static int g_use_dir = 1;  // tuning knob "vec_use_dir": 0 unranks every tile start in the kernel
 int g_force_tau = 0;  // test hook: force the tail length (0 = cost model)
+int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
 struct StratKey {
-  int dev, rank, esize, nst;
-  int64_t dim;
-  bool operator<(const StratKey& o) const {
-    return std::tie(dev, rank, esize, nst, dim) < std::tie(o.dev, o.rank, o.esize, o.nst, o.dim);
-  }
+  int dev, rank, esize;
+  int64_t dim, tile;
+  bool operator<(const StratKey& o) const { return std::tie(dev, rank, esize, dim, tile) < std::tie(o.dev, o.rank, o.esize, o.dim, o.tile); }
 };
 struct StratEntry {
   TailStrategy* d_strat;
+  DirEntry* d_dir;        // tile directory (nullptr when disabled)
+  int64_t* d_tile_base;   // [ncls + 1]
+  DirEntry* d_sdir;       // per-component directory of the small classes
+  int64_t* d_sbase;       // [ncls + 1]
+  int32_t cdesc_smem;
   int32_t tbl_cap;
+  int32_t binom_smem;
   size_t smem_bytes;
   bool supported;
 };
@@ -291,17 +521,22 @@ static double dbinom(const HostPlan* hp, int64_t n, int k) {
 }
 
 // Choose tau per class with a small cost model (estimated warp-instructions per component):
-//   streaming      0.2 (mode A: LDG + LDS + FMA)  /  0.3 + 0.03 nE (mode B: relabel + pow on the fly)
-//   per block      ~30-40 warp-uniform instructions for the head odometer
+//   streaming      ~0.1 (one LDG.128, VEC table loads and FMAs per 16-byte vector)
+//   per block      ~50 warp-uniform instructions (odometer step + one predicated pass over the batch)
 //   table builds   ~0.5 per entry, amortised over a segment (multi-run classes) or over a CTA's share of the
 //                  class (single-run classes, table built once per CTA)
 // Pure host function (also used by the CPU emulation harness in tests/emu).
-bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, int nst, std::vector<TailStrategy>& st, int32_t* tbl_cap, size_t* smem_bytes) {
+bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, std::vector<TailStrategy>& st, int32_t* tbl_cap,
+                           int32_t* binom_smem, int32_t* cdesc_smem, size_t* smem_bytes) {
   const int rank = hp->rank;
   const int64_t dim = hp->dim;
   const size_t smem_budget = 224 * 1024;
-  // everything but the table: xr, xs, blen, the cp.async rings, control block, alignment slack
-  const size_t fixed = (size_t)2 * dim * esize + (size_t)dim * 4 + (size_t)nwarps * nst * kStageBytes + sizeof(TailCtrl) + 128;
+  const size_t binom_bytes = (size_t)hp->binom_rows * (rank + 1) * sizeof(int64_t);
+  *binom_smem = binom_bytes <= (size_t)kBinomSmemMax ? (int32_t)(hp->binom_rows * (rank + 1)) : 0;
+  *cdesc_smem = (size_t)hp->ncls * sizeof(ClassDesc) <= 24 * 1024 ? 1 : 0;
+  // everything but the table: xr, xs, blen, the binomial table, class records, per-warp scratch, control block, slack
+  const size_t fixed = (size_t)2 * dim * esize + (size_t)dim * 4 + (size_t)*binom_smem * sizeof(int64_t) + (size_t)hp->ncls * kClsInfoBytes +
+                       (*cdesc_smem ? (size_t)hp->ncls * sizeof(ClassDesc) : 0) + (size_t)nwarps * sizeof(WarpScratch) + sizeof(TailCtrl) + 128;
   if (fixed + 32 * esize > smem_budget) return false;  // x itself does not fit shared memory
   const int64_t cap = (int64_t)((smem_budget - fixed) / esize);
   if (cap < (int64_t)nwarps * dim) return false;  // the per-warp private tables (which alias the table) must fit
@@ -311,7 +546,8 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, int nst, s
     const ClassDesc& C = hp->h_cls[c];
     TailStrategy& S = st[c];
     memset(&S, 0, sizeof(S));
-    if (C.nvals == 0 || C.size == 0) { S.tau = 1; S.gt = 1; S.Rt = 1; S.mu = 1; S.tbl_n = 1; S.seg = 1; continue; }
+    if (C.nvals == 0 || C.size == 0) { S.tau = 0; S.gt = 1; S.Rt = 1; S.mu = 1; S.tbl_n = 1; S.seg = 1; continue; }
+    if (C.size <= g_small_class && g_variant != 2) { S.tau = 0; S.gt = 1; S.Rt = 1; S.mu = 1; S.tbl_n = 1; S.seg = C.size; continue; }
     const int t = C.nruns - 1;
     S.gt = C.run_len[t];
     S.nE = C.nvals - S.gt;
@@ -321,58 +557,109 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, int nst, s
     double best = 1e300;
     int best_tau = 1;
     for (int tau = 1; tau <= S.gt; ++tau) {
+      int64_t nA = 0, nB = 0;
+      table_scratch(hp->h_binom, rank, S.Rt, tau, &nA, &nB);
       const double tn = dbinom(hp, S.Rt, tau);
-      if (tau > 1 && tn > (double)cap) break;
+      if (tau > 1 && tn + (double)nA + (double)nB > (double)cap) break;
       const double nheads = dbinom(hp, S.Rt - tau, S.gt - tau);
       const double avg_block = (double)S.seg / (nheads > 0 ? nheads : 1);
       double cost;
       if (tau == 1) {
-        cost = 0.2 + 40.0 / avg_block + (S.nE ? (400.0 + 0.5 * S.Rt) / (double)S.seg : 0.0);
+        cost = 0.1 + 150.0 / avg_block + (S.nE ? (400.0 + 0.5 * S.Rt) / (double)S.seg : 0.0);
       } else {
-        const double amort = (S.nE == 0) ? std::max(1.0, (double)C.size / 296.0) : (double)S.seg;
-        cost = 0.2 + 30.0 / avg_block + (0.5 * tn + 2000.0) / amort;
+        // level-by-level build: ~0.3 warp-instructions per entry plus the barriers, once per class (single-run
+        // classes) or per segment and CTA (mode B: a chunk sees about two segments)
+        const double amort = (S.nE == 0) ? std::max(1.0, (double)C.size / 148.0) : 0.5 * (double)S.seg;
+        cost = 0.1 + 150.0 / avg_block + (0.3 * (tn + (double)nA + (double)nB) + 3000.0) / amort;
       }
       if (cost < best) { best = cost; best_tau = tau; }
     }
     if (g_force_tau > 0) best_tau = std::min(g_force_tau, (int)S.gt);
-    if (best_tau > 1 && dbinom(hp, S.Rt, best_tau) > (double)cap) best_tau = 1;
+    int64_t nA = 0, nB = 0;
+    table_scratch(hp->h_binom, rank, S.Rt, best_tau, &nA, &nB);
+    if (best_tau > 1 && dbinom(hp, S.Rt, best_tau) + (double)nA + (double)nB > (double)cap) { best_tau = 1; nA = nB = 0; }
     S.tau = best_tau;
     S.hn = S.gt - S.tau;
     S.tbl_n = hp->h_binom[(int64_t)S.Rt * (rank + 1) + S.tau];
-    if (S.tau > 1) tbl_max = std::max(tbl_max, S.tbl_n);
+    if (S.tau > 1) tbl_max = std::max(tbl_max, S.tbl_n + nA + nB);
   }
   *tbl_cap = (int32_t)((tbl_max + 31) / 32 * 32);
   {
     size_t off = ((size_t)*tbl_cap * esize + 15) / 16 * 16;
     off = (off + 2 * (size_t)dim * esize + 15) / 16 * 16;
     off = (off + (size_t)dim * 4 + 15) / 16 * 16;
-    off += (size_t)nwarps * nst * kStageBytes;
+    off += (size_t)*binom_smem * sizeof(int64_t);
+    off += (size_t)hp->ncls * kClsInfoBytes;
+    off += *cdesc_smem ? (size_t)hp->ncls * sizeof(ClassDesc) : 0;
+    off = (off + 15) / 16 * 16;
+    off += (size_t)nwarps * sizeof(WarpScratch);
     *smem_bytes = off + sizeof(TailCtrl);
   }
   return true;
 }
 
-static int get_strategy(int rank, int64_t dim, int esize, int nst, StratEntry* out) {
+static const int64_t kMaxDirTiles = (int64_t)1 << 23;  // 256 MB of directory at most
+
+static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, StratEntry* out) {
   const HostPlan* hp = get_host_plan(rank, dim);
   if (!hp) return ST_ERR_INVALID;
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_smu);
-  StratKey key{dev, rank, esize, nst, dim};
+  StratKey key{dev, rank, esize, dim, tile};
   auto it = g_strats.find(key);
   if (it != g_strats.end()) { *out = it->second; return ST_OK; }
   StratEntry e;
   e.d_strat = nullptr;
+  e.d_dir = nullptr;
+  e.d_tile_base = nullptr;
+  e.d_sdir = nullptr;
+  e.d_sbase = nullptr;
+  e.cdesc_smem = 0;
   e.tbl_cap = 32;
+  e.binom_smem = 0;
   e.smem_bytes = 0;
   std::vector<TailStrategy> st;
-  e.supported = compute_tail_strategy(hp, esize, kTailThreads / 32, nst, st, &e.tbl_cap, &e.smem_bytes);
+  e.supported = compute_tail_strategy(hp, esize, kTailThreads / 32, st, &e.tbl_cap, &e.binom_smem, &e.cdesc_smem, &e.smem_bytes);
   if (e.supported) {
     rc = check_cuda(cudaMalloc(&e.d_strat, sizeof(TailStrategy) * hp->ncls), "cudaMalloc(strategy)");
     if (rc) return rc;
     rc = check_cuda(cudaMemcpy(e.d_strat, st.data(), sizeof(TailStrategy) * hp->ncls, cudaMemcpyHostToDevice), "cudaMemcpy(strategy)");
     if (rc) return rc;
+    // tile directory: built once per (device, rank, dim, tile size) by the GPU enumerator
+    std::vector<int64_t> tb(hp->ncls + 1, 0);
+    for (int c = 0; c < hp->ncls; ++c) tb[c + 1] = tb[c] + (hp->h_cls[c].size + tile - 1) / tile;
+    const int64_t ntiles = tb[hp->ncls];
+    if (g_use_dir && dim <= 65535 && ntiles > 0 && ntiles <= kMaxDirTiles) {
+      PlanView P;
+      rc = get_device_plan(rank, dim, &P);
+      if (rc) return rc;
+      rc = check_cuda(cudaMalloc(&e.d_tile_base, sizeof(int64_t) * (hp->ncls + 1)), "cudaMalloc(tile_base)");
+      if (rc) return rc;
+      rc = check_cuda(cudaMemcpy(e.d_tile_base, tb.data(), sizeof(int64_t) * (hp->ncls + 1), cudaMemcpyHostToDevice), "cudaMemcpy(tile_base)");
+      if (rc) return rc;
+      rc = check_cuda(cudaMalloc(&e.d_dir, sizeof(DirEntry) * ntiles), "cudaMalloc(tile directory)");
+      if (rc) return rc;
+      vec_dir_kernel<<<(unsigned)((ntiles + 127) / 128), 128>>>(P, tile, e.d_tile_base, ntiles, e.d_dir);
+      count_launch();
+      // small classes: one entry per component ("tile" of one component)
+      std::vector<int64_t> sb(hp->ncls + 1, 0);
+      for (int c = 0; c < hp->ncls; ++c) sb[c + 1] = sb[c] + (st[c].tau == 0 ? hp->h_cls[c].size : 0);
+      const int64_t nsmall = sb[hp->ncls];
+      if (nsmall > 0) {
+        rc = check_cuda(cudaMalloc(&e.d_sbase, sizeof(int64_t) * (hp->ncls + 1)), "cudaMalloc(sbase)");
+        if (rc) return rc;
+        rc = check_cuda(cudaMemcpy(e.d_sbase, sb.data(), sizeof(int64_t) * (hp->ncls + 1), cudaMemcpyHostToDevice), "cudaMemcpy(sbase)");
+        if (rc) return rc;
+        rc = check_cuda(cudaMalloc(&e.d_sdir, sizeof(DirEntry) * nsmall), "cudaMalloc(small-class directory)");
+        if (rc) return rc;
+        vec_dir_kernel<<<(unsigned)((nsmall + 127) / 128), 128>>>(P, 1, e.d_sbase, nsmall, e.d_sdir);
+        count_launch();
+      }
+      rc = check_cuda(cudaDeviceSynchronize(), "vec_dir_kernel");
+      if (rc) return rc;
+    }
   }
   g_strats[key] = e;
   *out = e;
@@ -411,50 +698,45 @@ static int get_counter(cudaStream_t stream, unsigned long long** out) {
   return ST_OK;
 }
 
-template <typename T, int NST>
-static int launch_tail_t(VecArgs<T>& a, const StratEntry& se, int64_t len, int* grid_out, cudaStream_t stream) {
+template <typename T, int U>
+static int launch_tail_u(VecArgs<T>& a, const StratEntry& se, int64_t len, int* grid_out, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(vec_tail_kernel<T, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
+    int rc = check_cuda(cudaFuncSetAttribute(vec_tail_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
                         "cudaFuncSetAttribute");
     if (rc) return rc;
     attr_set = true;
   }
-  // One resident CTA per SM claims work items dynamically; the item size gives every CTA about
-  // `g_items_per_cta` items: large enough to amortise the per-warp unrank, small enough to balance the tail.
-  const int64_t quantum = 32 * (kTailThreads / 32);
+  // One resident CTA per SM; tiles are dealt round-robin to the warps of the grid (see the kernel).
+  const int nwarps = kTailThreads / 32;
+  const int64_t tile = a.tile_elems;
+  const int64_t ntiles = (len + tile - 1) / tile;
   int64_t grid = std::min<int64_t>((int64_t)sm_count(), kMaxCtas);
-  grid = std::max<int64_t>(1, std::min<int64_t>(grid, (len + quantum - 1) / quantum));
-  int64_t nitems = std::min<int64_t>(grid * g_items_per_cta, kMaxPartials);
-  int64_t item = (len + nitems - 1) / nitems;
-  item = (item + quantum - 1) / quantum * quantum;
-  a.item_elems = item;
-  a.n_items = (len + item - 1) / item;
-  grid = std::min<int64_t>(grid, a.n_items);
+  grid = std::min<int64_t>(grid, kMaxPartials / nwarps);
+  grid = std::max<int64_t>(1, std::min<int64_t>(grid, (ntiles + nwarps - 1) / nwarps));
   {
     int rc = get_counter(stream, &a.counter);
     if (rc) return rc;
   }
-  vec_tail_kernel<T, NST><<<(int)grid, kTailThreads, se.smem_bytes, stream>>>(a);
-  *grid_out = (int)a.n_items;  // number of partials written
+  vec_tail_kernel<T, U><<<(int)grid, kTailThreads, se.smem_bytes, stream>>>(a);
+  *grid_out = (int)grid * nwarps;  // number of partials written
   return ST_OK;
 }
 
 template <typename T>
-static int launch_tail(VecArgs<T>& a, const StratEntry& se, int nst, int64_t len, int* grid_out, cudaStream_t stream) {
-  switch (nst) {
-    case 2: return launch_tail_t<T, 2>(a, se, len, grid_out, stream);
-    case 3: return launch_tail_t<T, 3>(a, se, len, grid_out, stream);
-    case 6: return launch_tail_t<T, 6>(a, se, len, grid_out, stream);
-    case 8: return launch_tail_t<T, 8>(a, se, len, grid_out, stream);
-    default: return launch_tail_t<T, 4>(a, se, len, grid_out, stream);
+static int launch_tail(VecArgs<T>& a, const StratEntry& se, int64_t len, int* grid_out, cudaStream_t stream) {
+  switch (g_batch_slots) {
+    case 2: return launch_tail_u<T, 2>(a, se, len, grid_out, stream);
+    default: return launch_tail_u<T, 4>(a, se, len, grid_out, stream);
   }
 }
 
-// Launch the main pass over [begin, end): writes `*grid_out` fp64 partials to `partials`.
+// Launch the main pass over [begin, end): writes `*grid_out` fp64 partials to `partials`.  With `d_out` the
+// tail kernel also reduces them (`*fused` = true); otherwise (or on the generic path) the caller finalizes.
 template <typename T>
 static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, int64_t begin, int64_t end, const T* d_x,
-                        double* partials, int* grid_out, cudaStream_t stream) {
+                        double* partials, int* grid_out, T* d_out, bool* fused, cudaStream_t stream) {
+  if (fused) *fused = false;
   if (layout != ST_LAYOUT_PERMCLS && layout != ST_LAYOUT_FLAT) { set_error("unknown layout %d", layout); return ST_ERR_INVALID; }
   PlanView P;
   int rc = get_device_plan(rank, dim, &P);
@@ -463,6 +745,7 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   if (begin < 0 || end < begin || end > total) { set_error("range [%lld, %lld) outside [0, %lld]", (long long)begin, (long long)end, (long long)total); return ST_ERR_INVALID; }
   if (begin % ST_CLASS_ALIGN) { set_error("begin must be a multiple of %d", ST_CLASS_ALIGN); return ST_ERR_INVALID; }
   if (!partials || (end > begin && (!d_packed || (dim > 0 && !d_x)))) { set_error("null pointer"); return ST_ERR_INVALID; }
+  if (end > begin && ((uintptr_t)d_packed % 16)) { set_error("the packed buffer must be 16-byte aligned"); return ST_ERR_INVALID; }
   VecArgs<T> a;
   a.P = P;
   a.strat = nullptr;
@@ -471,41 +754,40 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   a.begin = begin;
   a.end = end;
   a.partials = partials;
-  a.n_items = 1;
-  a.item_elems = end - begin;
+  a.out = nullptr;
+  a.tile_elems = 0;
+  a.dir = nullptr;
+  a.tile_base = nullptr;
+  a.sdir = nullptr;
+  a.sbase = nullptr;
+  a.cdesc_smem = 0;
   a.tbl_cap = 0;
+  a.binom_smem = 0;
   a.counter = nullptr;
   *grid_out = 1;
   if (end == begin) return check_cuda(cudaMemsetAsync(partials, 0, sizeof(double), stream), "cudaMemsetAsync");
   StratEntry se;
   se.supported = false;
-  int nst = 6;
   if (layout == ST_LAYOUT_PERMCLS && rank > 0 && g_variant != 1) {
-    // the tables come first: take the tail lengths the cost model picks with the smallest ring, then the deepest
-    // ring (up to g_ring_stages; 4 stages = 3 KB in flight per warp) that still leaves room for those tables
-    StratEntry base;
-    rc = get_strategy(rank, dim, (int)sizeof(T), 2, &base);
+    a.tile_elems = std::max<int64_t>(ST_CLASS_ALIGN, (g_tile_bytes / (int64_t)sizeof(T)) / ST_CLASS_ALIGN * ST_CLASS_ALIGN);
+    rc = get_strategy(rank, dim, (int)sizeof(T), a.tile_elems, &se);
     if (rc) return rc;
-    se = base;
-    nst = 2;
-    if (base.supported) {
-      const int cand[4] = {8, 6, 4, 3};
-      for (int i = 0; i < 4; ++i) {
-        if (cand[i] > g_ring_stages) continue;
-        StratEntry e2;
-        rc = get_strategy(rank, dim, (int)sizeof(T), cand[i], &e2);
-        if (rc) return rc;
-        if (e2.supported && e2.tbl_cap == base.tbl_cap) { se = e2; nst = cand[i]; break; }
-      }
-    }
     if (!se.supported && g_variant == 2) { set_error("tail-table kernel unavailable for dim %lld", (long long)dim); return ST_ERR_UNSUPPORTED; }
   }
   if (se.supported) {
     a.strat = se.d_strat;
     a.tbl_cap = se.tbl_cap;
-    rc = launch_tail<T>(a, se, nst, end - begin, grid_out, stream);
+    a.binom_smem = se.binom_smem;
+    a.dir = se.d_dir;
+    a.tile_base = se.d_tile_base;
+    a.sdir = se.d_sdir;
+    a.sbase = se.d_sbase;
+    a.cdesc_smem = se.cdesc_smem;
+    a.out = d_out;
+    rc = launch_tail<T>(a, se, end - begin, grid_out, stream);
     if (rc) return rc;
     count_launch();
+    if (fused) *fused = d_out != nullptr;
     return check_cuda(cudaGetLastError(), "vec_tail_kernel");
   }
   const int64_t n = end - begin;
@@ -532,8 +814,10 @@ static int contract_vec(int layout, int rank, int64_t dim, const T* d_packed, in
   if (!d_out || !d_ws) { set_error("null pointer"); return ST_ERR_INVALID; }
   double* partials = reinterpret_cast<double*>(d_ws);
   int grid = 1;
-  int rc = vec_partials<T>(layout, rank, dim, d_packed, begin, end, d_x, partials, &grid, stream);
+  bool fused = false;
+  int rc = vec_partials<T>(layout, rank, dim, d_packed, begin, end, d_x, partials, &grid, d_out, &fused, stream);
   if (rc) return rc;
+  if (fused) return ST_OK;
   return vec_finalize<T>(partials, grid, d_out, stream);
 }
 
@@ -625,7 +909,7 @@ static int contract_vec_host(int layout, int rank, int64_t dim, const T* h_packe
     if (rc) return rc;
     int grid = 1;
     rc = vec_partials<T>(layout, rank, dim, reinterpret_cast<const T*>(st->d_buf[b]), begin, end, reinterpret_cast<const T*>(st->d_x),
-                         st->d_ws + c * kMaxPartials, &grid, st->s_comp);
+                         st->d_ws + c * kMaxPartials, &grid, nullptr, nullptr, st->s_comp);
     if (rc) return rc;
     rc = check_cuda(cudaEventRecord(st->computed[b], st->s_comp), "cudaEventRecord");
     if (rc) return rc;
@@ -651,8 +935,20 @@ int64_t st_contract_vec_workspace_bytes(void) { return (int64_t)sizeof(double) *
 int st_set_tuning(const char* key, int64_t value) {
   if (!key) { set_error("null key"); return ST_ERR_INVALID; }
   const std::string k(key);
-  if (k == "vec_ring_stages" && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8)) { g_ring_stages = (int)value; return ST_OK; }
-  if (k == "vec_items_per_cta" && value >= 1 && value <= 64) { g_items_per_cta = (int)value; return ST_OK; }
+  if (k == "vec_small_class" && value >= 0) {
+    g_small_class = value;
+    std::lock_guard<std::mutex> lk(g_smu);
+    g_strats.clear();
+    return ST_OK;
+  }
+  if (k == "vec_use_dir" && (value == 0 || value == 1)) {
+    g_use_dir = (int)value;
+    std::lock_guard<std::mutex> lk(g_smu);
+    g_strats.clear();  // rebuilt on next use (old device tables are leaked: test hook)
+    return ST_OK;
+  }
+  if (k == "vec_batch_slots" && (value == 2 || value == 4)) { g_batch_slots = (int)value; return ST_OK; }
+  if (k == "vec_tile_bytes" && value >= 1024 && value <= (1 << 28)) { g_tile_bytes = (int)value; return ST_OK; }
   if (k == "vec_force_tau" && value >= 0 && value <= ST_MAX_RANK) {
     g_force_tau = (int)value;
     std::lock_guard<std::mutex> lk(g_smu);
@@ -666,6 +962,8 @@ int st_set_tuning(const char* key, int64_t value) {
 int st_set_vec_variant(int variant) {
   if (variant < 0 || variant > 2) { set_error("variant must be 0, 1 or 2"); return ST_ERR_INVALID; }
   g_variant = variant;
+  std::lock_guard<std::mutex> lk(g_smu);
+  g_strats.clear();  // strategies depend on the variant (old device tables are leaked: test hook)
   return ST_OK;
 }
 

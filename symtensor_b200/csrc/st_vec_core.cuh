@@ -19,15 +19,6 @@ struct TailStrategy {
   int64_t seg;   // C(Rt, g_t): components per fixed assignment of the earlier runs
 };
 
-template <typename T>
-ST_HD T ld_stream(const T* p) {
-#ifdef __CUDA_ARCH__
-  return __ldcs(p);
-#else
-  return *p;
-#endif
-}
-
 // ------------------------------------------------------------------------------------------------------
 // tail-table kernel
 // ------------------------------------------------------------------------------------------------------
@@ -40,24 +31,43 @@ ST_HD T ld_stream(const T* p) {
 //   shared  (tau >= 2)  T and xr live once per CTA and are rebuilt (with __syncthreads) when E changes;
 //   private (tau == 1)  T == xr, one copy per warp, rebuilt by the warp itself when it enters a new segment --
 //                       used when segments are too short to amortise a CTA-wide rebuild.
-// Shared memory: [T: tbl_cap x T][xr: dim x T][xs: dim x T (copy of x)][private xr: nwarps x dim x T][ctrl]
 struct TailCtrl {
   double red[32];
   double wE;               // gamma * prod over earlier runs x[v]^m
   int32_t E[ST_MAX_RANK];  // values of the earlier runs, ascending
   int32_t cur_cls;
   int64_t cur_seg;
-  long long item;          // work item broadcast (dynamic scheduling)
+  long long item[2];       // work item broadcast (dynamic scheduling), double-buffered
+  int32_t last;            // this CTA is the last one to finish (fused finalize)
+};
+
+// Warp-uniform small arrays of the walk.  On the device one copy per warp lives in SHARED memory: as thread-local
+// arrays they would be indexed dynamically, i.e. sit in local memory, 32 identical copies per warp, and with
+// most of the L1 carved out for the tail table every access would go to L2 (measured: a single unrank took
+// tens of microseconds).  All lanes of a converged warp write the same values; on the host (tests/emu) it is a
+// plain local.
+struct alignas(16) DirEntry {  // tile directory entry, see dir_decode
+  uint16_t v[ST_MAX_RANK];
+};
+
+struct WarpScratch {
+  DirEntry de;
+  double pref[ST_MAX_RANK + 1];
+  int64_t dig[ST_MAX_RANK];
+  int32_t u[ST_MAX_RANK];
+  int32_t E[ST_MAX_RANK];
+  int32_t u0[ST_MAX_RANK];
+  int32_t vals[ST_MAX_RANK];
 };
 
 // earlier runs of segment `sidx`: values (ascending, in E) and the weight gamma * prod x[v]^m
 template <typename T>
 ST_HD double unrank_earlier(const PlanView& P, const ClassDesc& C, int64_t sidx, const T* __restrict__ xs,
-                                                 int32_t* E) {
+                                                 int32_t* E, WarpScratch& ws) {
   double w = (double)C.gamma;
   if (C.nruns <= 1) return w;
-  int32_t vals[ST_MAX_RANK];
-  int64_t dig[ST_MAX_RANK];
+  int32_t* vals = ws.vals;
+  int64_t* dig = ws.dig;
   int nused = 0;
   for (int j = C.nruns - 2; j >= 0; --j) { const int64_t q = sidx / C.radix[j]; dig[j] = sidx - q * C.radix[j]; sidx = q; }
   for (int j = 0; j < C.nruns - 1; ++j) {
@@ -90,188 +100,11 @@ ST_HD T xrel_pow(const T* __restrict__ xs, const int32_t* E, int nE, int mu, int
   return p;
 }
 
-// ------------------------------------------------------------------------------------------------------
-// walk_range: one warp's walk over segment positions [q0, q1) of one segment.
-//
-// Memory and index arithmetic are DECOUPLED.  On the device the components are streamed through a per-warp
-// shared-memory ring with cp.async (16-byte copies, NST stages of 1 KB, NST-1 in flight while one is
-// consumed) in fixed stages that ignore block boundaries; the walk is handed one 32-wide SLOT of consecutive
-// components at a time and multiplies it against the "pieces" (block ∩ range) that overlap it:
-//     weight(idx) = hw * tbl[toff + idx]   for idx in [pb, pe)
-// A warp-uniform odometer produces the pieces: the common step -- increment the last head value -- costs a
-// handful of instructions (fast path); carries take the general path over the local arrays u[] / pref[].
-// All hot state is in scalar locals (registers); only u[] and pref[] are indexed dynamically.
-// `tbl` is the tail table (T for tau >= 2, xr for tau == 1), `xr` the head-factor table, `blen` the optional
-// table  blen[u] = C(Rt-1-u, tau)  of block lengths (nullptr: computed from the binomial table).
-// STAGED = false reads the components directly (CPU emulation in tests/emu, which replays this code lane by
-// lane; on the device it serves as the reference path for tiny ranges).
-// ------------------------------------------------------------------------------------------------------
 #ifdef __CUDA_ARCH__
 #define ST_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 #else
 #define ST_ASSUME_SHARED(p)
 #endif
-#ifdef __CUDACC__
-__device__ __forceinline__ void st_cp_async16(uint32_t saddr, const void* g) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
-}
-__device__ __forceinline__ void st_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void st_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#endif
-
-template <typename T, int NST, bool STAGED>
-ST_HD double walk_range(const PlanView& P, const TailStrategy& S, const T* __restrict__ tbl, const T* __restrict__ xr,
-                        const int32_t* __restrict__ blen, double wE, const T* __restrict__ Aseg, int64_t q0, int64_t q1, int lane,
-                        T* ring, const int32_t* u_init) {
-  ST_ASSUME_SHARED(tbl);
-  ST_ASSUME_SHARED(xr);
-  const int64_t* __restrict__ bt = P.binom;
-  const int rk = P.rank;
-  const int gt = S.gt, hn = S.hn, tau = S.tau, Rt = S.Rt;
-  const int tbl_n = (int)S.tbl_n;
-  const int n = (int)(q1 - q0);
-  int32_t u[ST_MAX_RANK];        // head combination (relabelled values), warp-uniform; slow path only
-  double pref[ST_MAX_RANK + 1];  // pref[i] = wE * prod_{j<i} xr[u[j]];                 slow path only
-  if (u_init) { for (int i = 0; i < gt; ++i) u[i] = u_init[i]; }
-  else comb_unrank(bt, rk, q0, Rt, gt, u);
-  const int tq = (int)comb_rank(bt, rk, u + hn, Rt, tau);  // table index of the first tail
-  pref[0] = wE;
-  for (int i = 0; i < hn; ++i) pref[i + 1] = pref[i] * (double)xr[u[i]];
-  int u_last = hn ? u[hn - 1] : -1;           // == u[hn-1]
-  double pref_prev = hn ? pref[hn - 1] : wE;  // == pref[hn-1]
-  double hw = pref[hn];
-  int pb = 0;                                  // current piece [pb, pe), positions relative to q0
-  int pe = (tbl_n - tq < n) ? tbl_n - tq : n;
-  int toff = tq;
-  T s = T(0);          // per-lane partial of the current piece
-  double total = 0.0;  // per-lane running total
-
-  // next block: lexicographic successor of the head combination
-  auto advance = [&]() {
-    pb = pe;
-    if (hn == 0) { pe = n; return; }  // defensive: a segment with hn == 0 is a single block
-    if (u_last + 1 <= Rt - tau - 1) {
-      ++u_last;  // fast path: no carry
-    } else {
-      u[hn - 1] = u_last;
-      int j = hn - 1;
-      while (j >= 0 && u[j] + 1 > Rt - (gt - j)) --j;
-      if (j < 0) { pe = n; return; }  // defensive: cannot happen inside a segment
-      ++u[j];
-      for (int k = j + 1; k < hn; ++k) u[k] = u[k - 1] + 1;
-      for (int k = j; k < hn - 1; ++k) pref[k + 1] = pref[k] * (double)xr[u[k]];
-      u_last = u[hn - 1];
-      pref_prev = pref[hn - 1];
-    }
-    hw = pref_prev * (double)xr[u_last];
-    // first tail of the new head is (b+1, b+2, ..), b = u_last: block length C(Rt-1-b, tau), at the table's end
-    const int bl = tau == 1 ? Rt - 1 - u_last : (blen ? blen[u_last] : (int)binom_at(bt, rk, Rt - 1 - u_last, tau));
-    toff = tbl_n - bl - pb;
-    pe = (bl < n - pb) ? pb + bl : n;
-  };
-  // consume the slot [base, slot_end): this lane holds component base + lane in v (0 beyond slot_end)
-  auto slot = [&](int base, int slot_end, T v) {
-    const int idx = base + lane;
-    while (true) {
-      const bool in = (idx >= pb) & (idx < pe);
-      const T tv = tbl[toff + (in ? idx : pb)];
-      s += (in ? v : T(0)) * tv;
-      if (pe >= slot_end) break;  // the piece covers the rest of the slot
-      total += hw * (double)s;
-      s = T(0);
-      advance();
-    }
-  };
-
-  const T* __restrict__ ap = Aseg + q0;
-  bool staged = false;
-#ifdef __CUDA_ARCH__
-  staged = STAGED;
-  if (STAGED) {
-    constexpr int VEC = 16 / (int)sizeof(T);  // components per 16-byte vector
-    constexpr int STAGE_E = 2 * 32 * VEC;     // a stage is 1 KB: two 16-byte vectors per lane
-    // consume one stage [base, slot_end) held at shared address `sp`
-    auto vslot = [&](const T* __restrict__ sp, int base, int slot_end) {
-      if (pb <= base && pe >= base + STAGE_E && slot_end == base + STAGE_E) {
-        // warp-uniform fast path: one piece covers the whole stage; each lane multiplies two 16-byte vectors
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int off = h * 32 * VEC + lane * VEC;
-          const float4 raw = *reinterpret_cast<const float4*>(sp + off);
-          const T* __restrict__ tp = tbl + (toff + base + off);
-          if (sizeof(T) == 8) {
-            s += (T)__hiloint2double(__float_as_int(raw.y), __float_as_int(raw.x)) * tp[0];
-            s += (T)__hiloint2double(__float_as_int(raw.w), __float_as_int(raw.z)) * tp[VEC - 1];
-          } else {
-            s += (T)raw.x * tp[0];
-            s += (T)raw.y * tp[1 % VEC];
-            s += (T)raw.z * tp[2 % VEC];
-            s += (T)raw.w * tp[3 % VEC];
-          }
-        }
-        return;
-      }
-      // general path, piece-major: lanes stride the components of each piece that overlaps the stage
-      while (true) {
-        const int lo = pb > base ? pb : base, hi = pe < slot_end ? pe : slot_end;
-        const T* __restrict__ tp = tbl + toff;
-        for (int idx = lo + lane; idx < hi; idx += 32) s += sp[idx - base] * tp[idx];
-        if (pe >= slot_end) break;
-        total += hw * (double)s;
-        s = T(0);
-        advance();
-      }
-    };
-    int a0 = (int)(((16u - (unsigned)((uintptr_t)ap & 15u)) & 15u) / sizeof(T));  // components before 16-byte alignment
-    if (a0 > n) a0 = n;
-    if (a0 > 0) slot(0, a0, lane < a0 ? ld_stream(ap + lane) : T(0));
-    const int nb = (n - a0) / VEC * VEC;  // body: whole 16-byte vectors
-    const int nchunks = (nb + STAGE_E - 1) / STAGE_E;
-    const int body_end = a0 + nb;
-    const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring) + lane * 16;
-    const char* __restrict__ gp = reinterpret_cast<const char*>(ap + a0 + lane * VEC);  // this lane's next vector to fetch
-    int e_next = lane * VEC;                                                             // its component index in the body
-    auto fetch = [&](int stage) {
-      if (e_next < nb) st_cp_async16(ring_s + stage * 1024, gp);
-      if (e_next + 32 * VEC < nb) st_cp_async16(ring_s + stage * 1024 + 512, gp + 512);
-      st_cp_async_commit();
-      gp += 1024;
-      e_next += STAGE_E;
-    };
-#pragma unroll
-    for (int c = 0; c < NST - 1; ++c) fetch(c);
-    int st = 0;           // stage holding chunk c
-    int st_in = NST - 1;  // stage receiving chunk c + NST - 1
-    int cbase = a0;
-    for (int c = 0; c < nchunks; ++c) {
-      fetch(st_in);
-      st_cp_async_wait<NST - 1>();
-      __syncwarp();
-      const int cend = (cbase + STAGE_E < body_end) ? cbase + STAGE_E : body_end;
-      vslot(ring + st * STAGE_E, cbase, cend);
-      __syncwarp();  // the stage is overwritten by the copy issued in the next iteration
-      st = (st + 1 == NST) ? 0 : st + 1;
-      st_in = (st_in + 1 == NST) ? 0 : st_in + 1;
-      cbase += STAGE_E;
-    }
-    if (body_end < n) slot(body_end, n, body_end + lane < n ? ld_stream(ap + body_end + lane) : T(0));
-  }
-#endif
-  if (!staged) {
-    for (int base = 0; base < n; base += 32) {
-      const int idx = base + lane;
-      slot(base, (base + 32 < n) ? base + 32 : n, idx < n ? ap[idx] : T(0));
-    }
-  }
-  return total + hw * (double)s;
-}
-
-template <typename T>
-ST_HD double walk_range_direct(const PlanView& P, const TailStrategy& S, const T* tbl, const T* xr, const int32_t* blen, double wE,
-                               const T* Aseg, int64_t q0, int64_t q1, int lane) {
-  return walk_range<T, 2, false>(P, S, tbl, xr, blen, wE, Aseg, q0, q1, lane, nullptr, nullptr);
-}
 
 #ifdef __CUDACC__
 // Warp-cooperative inverse of comb_rank: every lane tests one candidate value per step (ballot), so a
@@ -300,7 +133,282 @@ __device__ __forceinline__ void comb_unrank_warp(const int64_t* __restrict__ tbl
 }
 #endif
 
+// one 16-byte vector of components (streaming load: every component is read exactly once)
+template <typename T>
+ST_HD void ld_vec16(const T* __restrict__ p, T* v) {
+#ifdef __CUDA_ARCH__
+  if (sizeof(T) == 8) {
+    const double2 r = __ldcs(reinterpret_cast<const double2*>(p));
+    v[0] = (T)r.x;
+    v[1] = (T)r.y;
+  } else {
+    const float4 r = __ldcs(reinterpret_cast<const float4*>(p));
+    v[0] = (T)r.x;
+    v[1] = (T)r.y;
+    v[2 % (16 / (int)sizeof(T))] = (T)r.z;
+    v[3 % (16 / (int)sizeof(T))] = (T)r.w;
+  }
+#else
+  for (int k = 0; k < 16 / (int)sizeof(T); ++k) v[k] = p[k];
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------
+// walk_range: one warp's walk over segment positions [q0, q1) of one segment (q1 - q0 < 2^30).
+//
+// Memory and index arithmetic are DECOUPLED.  The components are fetched in BATCHES of U slots (a slot is one
+// 16-byte vector per lane: 512 contiguous bytes per warp), all U loads of a batch issued back to back into
+// registers; two batches are kept (one being consumed, the next in flight) so a warp always has loads
+// outstanding.  Batches start at the 16-byte boundary at or below the range start and ignore block boundaries.  The odometer hands out "pieces" (block ∩ range, positions relative to q0):
+//     weight(idx) = hw * tbl[toff + idx]   for idx in [pb, pe)
+// A batch inside one piece takes the fast path (per 16-byte vector: one LDG.128, VEC table loads, VEC FMAs);
+// otherwise the batch is consumed piece by piece with per-element predicates.  The warp-uniform odometer's
+// common step -- increment the last head value -- costs a handful of instructions; carries take the general
+// path over the local arrays u[] / pref[].  `tbl` is the tail table (T for tau >= 2, xr for tau == 1), `xr`
+// the head-factor table, `blen` the optional table blen[u] = C(Rt-1-u, tau) of block lengths (nullptr:
+// computed from the binomial table).  `u_init` is the last run's combination at q0 when the caller knows it (tile
+// directory, start of a segment); otherwise it is unranked here, after the first two batches have been requested.
+// The same code runs on the host (tests/emu replays it lane by lane).
+// ------------------------------------------------------------------------------------------------------
+template <typename T, int U>
+ST_HD double walk_range(const PlanView& P, const TailStrategy& S, const T* __restrict__ tbl, const T* __restrict__ xr,
+                        const int32_t* __restrict__ blen, double wE, const T* __restrict__ Aseg, int64_t q0, int64_t q1, int lane,
+                        const int32_t* u_init, T (&bufA)[U][16 / sizeof(T)], T (&bufB)[U][16 / sizeof(T)], bool preloaded,
+                        const T* __restrict__ next_ap, WarpScratch& ws) {
+  ST_ASSUME_SHARED(tbl);
+  ST_ASSUME_SHARED(xr);
+  constexpr int VEC = 16 / (int)sizeof(T);  // components per 16-byte vector
+  constexpr int SLOT = 32 * VEC;            // components per slot
+  constexpr int BATCH = U * SLOT;
+  const int64_t* __restrict__ bt = P.binom;
+  const int rk = P.rank;
+  const int gt = S.gt, hn = S.hn, tau = S.tau, Rt = S.Rt;
+  const int tbl_n = (int)S.tbl_n;
+  const int n = (int)(q1 - q0);
+  const T* __restrict__ ap = Aseg + q0;
+  // components between the 16-byte boundary at or below `ap` and `ap` (they belong to whoever owns them: masked out)
+  const int a_pre = (int)(((uintptr_t)ap & 15u) / sizeof(T));
+  const T* __restrict__ lp = ap - a_pre + lane * VEC;  // this lane's vector of slot 0 of the batch at position -a_pre
+  int pos = -a_pre;                                    // position (relative to q0) of the current batch
+  // bufA / bufB: two batches in registers, one being consumed, one in flight.  They belong to the caller so that
+  // the stream can continue ACROSS ranges: with `next_ap` (16-byte aligned start of the caller's next range, at
+  // least two whole batches long; only legal when this range has an even number of batches) the first two
+  // batches of the next range are requested as soon as the buffers free up, and the next call passes
+  // `preloaded`.
+  // fetch the batch at position p (whole vectors while they end inside the range, single components up to n,
+  // zeros beyond: only the last batch of a range is partial)
+  auto load = [&](T (&buf)[U][VEC], int p) {
+    const T* __restrict__ bp = lp + (p + a_pre);
+    if (p + BATCH <= n) {
+#pragma unroll
+      for (int s = 0; s < U; ++s) ld_vec16(bp + s * SLOT, buf[s]);
+    } else {
+#pragma unroll
+      for (int s = 0; s < U; ++s) {
+        const int i0 = p + s * SLOT + lane * VEC;
+        if (i0 + VEC <= n) {
+          ld_vec16(bp + s * SLOT, buf[s]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) buf[s][k] = (i0 + k < n && i0 + k >= 0) ? bp[s * SLOT + k] : T(0);
+        }
+      }
+    }
+  };
+  if (!preloaded) {
+    load(bufA, pos);
+    if (pos + BATCH < n) load(bufB, pos + BATCH);
+  }
+  int nx = 0;  // batches of the next range requested so far
+  auto load_next = [&](T (&buf)[U][VEC]) {
+    const T* __restrict__ bp = next_ap + nx * BATCH + lane * VEC;
+#pragma unroll
+    for (int s = 0; s < U; ++s) ld_vec16(bp + s * SLOT, buf[s]);
+    ++nx;
+  };
+
+  // ---- odometer state at q0
+  int32_t* u = ws.u;       // head combination (relabelled values), warp-uniform; slow path only
+  double* pref = ws.pref;  // pref[i] = wE * prod_{j<i} xr[u[j]];                 slow path only
+  if (u_init) {
+    for (int i = 0; i < gt; ++i) u[i] = u_init[i];  // from the tile directory / the start of a segment
+  } else {
+#ifdef __CUDA_ARCH__
+    comb_unrank_warp(bt, rk, q0, Rt, gt, u, lane);
+#else
+    comb_unrank(bt, rk, q0, Rt, gt, u);
+#endif
+  }
+  const int tq = (int)comb_rank(bt, rk, u + hn, Rt, tau);  // table index of the first tail
+  pref[0] = wE;
+  for (int i = 0; i < hn; ++i) pref[i + 1] = pref[i] * (double)xr[u[i]];
+  int u_last = hn ? u[hn - 1] : -1;           // == u[hn-1]
+  double pref_prev = hn ? pref[hn - 1] : wE;  // == pref[hn-1]
+  double hw = pref[hn];
+  int pb = 0;                                  // current piece [pb, pe), positions relative to q0
+  int pe = (tbl_n - tq < n) ? tbl_n - tq : n;
+  int toff = tq;
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);  // per-lane partials of the current piece (independent FMA chains)
+  double total = 0.0;                            // per-lane running total
+
+  // next block: lexicographic successor of the head combination
+  auto advance = [&]() {
+    pb = pe;
+    if (hn == 0) { pe = n; return; }  // defensive: a segment with hn == 0 is a single block
+    if (u_last + 1 <= Rt - tau - 1) {
+      ++u_last;  // fast path: no carry
+    } else {
+      u[hn - 1] = u_last;
+      int j = hn - 1;
+      while (j >= 0 && u[j] + 1 > Rt - (gt - j)) --j;
+      if (j < 0) { pe = n; return; }  // defensive: cannot happen inside a segment
+      ++u[j];
+      for (int k = j + 1; k < hn; ++k) u[k] = u[k - 1] + 1;
+      for (int k = j; k < hn - 1; ++k) pref[k + 1] = pref[k] * (double)xr[u[k]];
+      u_last = u[hn - 1];
+      pref_prev = pref[hn - 1];
+    }
+    hw = pref_prev * (double)xr[u_last];
+    // first tail of the new head is (b+1, b+2, ..), b = u_last: block length C(Rt-1-b, tau), at the table's end
+    const int bl = tau == 1 ? Rt - 1 - u_last : (blen ? blen[u_last] : (int)binom_at(bt, rk, Rt - 1 - u_last, tau));
+    toff = tbl_n - bl - pb;
+    pe = (bl < n - pb) ? pb + bl : n;
+  };
+  auto flush = [&]() {
+    total += hw * (((double)s0 + (double)s1) + ((double)s2 + (double)s3));
+    s0 = T(0);
+    s1 = T(0);
+    s2 = T(0);
+    s3 = T(0);
+  };
+  // slot s of a batch, entirely inside the current piece: no predicates
+  auto slot_full = [&](const T (&v)[VEC], const T* __restrict__ tp, int s) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const T t = tp[k];
+      switch ((s * VEC + k) & 3) {
+        case 0: s0 += v[k] * t; break;
+        case 1: s1 += v[k] * t; break;
+        case 2: s2 += v[k] * t; break;
+        default: s3 += v[k] * t; break;
+      }
+    }
+  };
+
+  // consume the batch at `pos`, valid up to bend = min(pos + BATCH, n); invariant on entry: pb <= max(pos, 0) < pe
+  auto consume = [&](T (&cur)[U][VEC]) {
+    const int bend = (pos + BATCH < n) ? pos + BATCH : n;
+    if (pb <= pos && pe >= pos + BATCH) {
+      // one piece covers the whole batch
+      const T* __restrict__ tp = tbl + (toff + pos + lane * VEC);
+#pragma unroll
+      for (int s = 0; s < U; ++s) slot_full(cur[s], tp + s * SLOT, s);
+      if (pe == bend) {
+        flush();
+        if (pe < n) advance();
+      }
+      return;
+    }
+    while (true) {
+      // the part of the current piece inside this batch: slots it covers entirely take the plain path, the
+      // (at most two) slots holding its ends are predicated per component
+#pragma unroll
+      for (int s = 0; s < U; ++s) {
+        const int sb = pos + s * SLOT;
+        if (pe > sb && pb < sb + SLOT) {  // the piece overlaps this slot (warp-uniform)
+          if (pb <= sb && pe >= sb + SLOT) {
+            slot_full(cur[s], tbl + (toff + sb + lane * VEC), s);
+          } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+              const int idx = sb + lane * VEC + k;
+              const bool in = (idx >= pb) & (idx < pe);
+              const T tv = tbl[toff + (in ? idx : pb)];
+              s0 += (in ? cur[s][k] : T(0)) * tv;
+            }
+          }
+        }
+      }
+      if (pe > bend) break;  // the piece continues in the next batch
+      flush();
+      if (pe >= n) break;    // end of the range
+      advance();
+      if (pb >= bend) break; // the next piece starts with the next batch
+    }
+  };
+
+  while (true) {
+    // tight run: while the current piece covers the two batches in registers and the two batches after them are
+    // whole, stream with no per-batch bookkeeping (per 16-byte vector: one LDG.128, VEC table loads, VEC FMAs)
+    if (pb <= pos && pos + 2 * BATCH <= pe && pos + 4 * BATCH <= n) {
+      const T* __restrict__ tp = tbl + (toff + pos + lane * VEC);
+      const T* __restrict__ gp = lp + (pos + a_pre) + 2 * BATCH;  // this lane's vector of the batch after next
+      int run = (pe - pos) / (2 * BATCH);
+      const int run_n = (n - pos - 2 * BATCH) / (2 * BATCH);
+      if (run_n < run) run = run_n;
+      pos += run * (2 * BATCH);
+      for (; run > 0; --run) {
+#pragma unroll
+        for (int s = 0; s < U; ++s) slot_full(bufA[s], tp + s * SLOT, s);
+#pragma unroll
+        for (int s = 0; s < U; ++s) ld_vec16(gp + s * SLOT, bufA[s]);
+#pragma unroll
+        for (int s = 0; s < U; ++s) slot_full(bufB[s], tp + BATCH + s * SLOT, s);
+#pragma unroll
+        for (int s = 0; s < U; ++s) ld_vec16(gp + BATCH + s * SLOT, bufB[s]);
+        tp += 2 * BATCH;
+        gp += 2 * BATCH;
+      }
+      if (pe == pos) {  // the piece ended exactly here (pos < n: two more batches were loaded)
+        flush();
+        advance();
+      }
+    }
+    consume(bufA);
+    pos += BATCH;
+    if (pos + BATCH < n) load(bufA, pos + BATCH);
+    else if (next_ap != nullptr && nx < 2) load_next(bufA);
+    if (pos >= n) break;
+    consume(bufB);
+    pos += BATCH;
+    if (pos + BATCH < n) load(bufB, pos + BATCH);
+    else if (next_ap != nullptr && nx < 2) load_next(bufB);
+    if (pos >= n) break;
+  }
+  return total + hw * (((double)s0 + (double)s1) + ((double)s2 + (double)s3));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tile directory: the distinct values (class order, absolute) of the component at the start of every tile,
+// 16 x uint16 per tile, written once per (rank, dim, tile size) by the GPU index enumerator (st_vec.cu) so that
+// starting a tile costs one 32-byte load instead of a combinatorial unrank.
+// ------------------------------------------------------------------------------------------------------
+// entry -> earlier-run values E (ascending), their weight factor, and the last run's relabelled combination
+template <typename T>
+ST_HD double dir_decode(const ClassDesc& C, const TailStrategy& S, const DirEntry& d, const T* __restrict__ xs, int32_t* E, int32_t* u) {
+  double w = (double)C.gamma;
+  int nE = 0;
+  for (int j = 0; j < C.nruns - 1; ++j) {
+    for (int i = 0; i < C.run_len[j]; ++i) {
+      const int32_t v = d.v[C.run_start[j] + i];
+      const double xv = (double)xs[v];
+      for (int m = 0; m < C.run_mult[j]; ++m) w *= xv;
+      int e = nE++;
+      while (e > 0 && E[e - 1] > v) { E[e] = E[e - 1]; --e; }
+      E[e] = v;
+    }
+  }
+  for (int i = 0; i < S.gt; ++i) {
+    const int32_t v = d.v[S.nE + i];
+    int32_t below = 0;
+    for (int e = 0; e < nE; ++e) below += (E[e] < v);
+    u[i] = v - below;
+  }
+  return w;
+}
+
 // T[q] = prod of xr over the q-th tau-combination of range(Rt), for q in [q, qe): contiguous slice of one thread
+// (serial reference form; the kernel uses build_table_level below)
 template <typename T>
 ST_HD void build_table_slice(const PlanView& P, const TailStrategy& S, const T* __restrict__ xr, T* __restrict__ tbl,
                              int64_t q, int64_t qe) {
@@ -317,6 +425,45 @@ ST_HD void build_table_slice(const PlanView& P, const TailStrategy& S, const T* 
     ++cmb[j];
     for (int k = j + 1; k < S.tau; ++k) cmb[k] = cmb[k - 1] + 1;
   }
+}
+
+// Level-by-level table build.  The t-combinations of range(Rt) in lexicographic order are grouped by their
+// first value c0, and the group of c0 is xr[c0] times the SUFFIX of the (t-1)-table that holds the
+// combinations whose first value exceeds c0 (a contiguous run: lexicographic order again):
+//     T_t[C(Rt,t) - C(Rt-c0,t) + i] = xr[c0] * T_{t-1}[C(Rt,t-1) - C(Rt-1-c0,t-1) + i],  0 <= i < C(Rt-1-c0,t-1)
+// with T_1 = xr.  One level is a set of independent, coalesced scaled copies: thread `tid` of `nthreads` takes
+// the groups warp by warp.  The caller separates levels with a barrier.  src/dst must not overlap.
+template <typename T>
+ST_HD void build_table_level(const int64_t* __restrict__ bt, int rk, int Rt, int t, const T* __restrict__ xr, const T* __restrict__ src,
+                             T* __restrict__ dst, int tid, int nthreads) {
+  const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+  const int64_t nt = binom_at(bt, rk, Rt, t), nt1 = binom_at(bt, rk, Rt, t - 1);
+  for (int c0 = warp; c0 + t <= Rt; c0 += nw) {
+    const int64_t go = nt - binom_at(bt, rk, Rt - c0, t);
+    const int64_t len = binom_at(bt, rk, Rt - 1 - c0, t - 1);
+    const int64_t so = nt1 - len;
+    const T xv = xr[c0];
+    for (int64_t i = lane; i < len; i += 32) dst[go + i] = xv * src[so + i];
+  }
+}
+
+// Scratch (beyond the C(Rt, tau) entries of the table itself) of the level-by-level build: levels t < tau
+// alternate between two buffers behind the table, A (tau - t odd) and B (tau - t even).
+ST_HD void table_scratch(const int64_t* bt, int rk, int Rt, int tau, int64_t* nA, int64_t* nB) {
+  *nA = 0;
+  *nB = 0;
+  for (int t = 2; t < tau; ++t) {
+    const int64_t c = binom_at(bt, rk, Rt, t);
+    if ((tau - t) & 1) { if (c > *nA) *nA = c; }
+    else { if (c > *nB) *nB = c; }
+  }
+}
+
+// source / destination of level t inside the buffer `tbl` (table first, then scratch A, then scratch B)
+template <typename T>
+ST_HD T* table_level_buffer(T* tbl, int64_t tbl_n, int64_t nA, int tau, int t) {
+  if (t == tau) return tbl;
+  return ((tau - t) & 1) ? tbl + tbl_n : tbl + tbl_n + nA;
 }
 
 }  // namespace st

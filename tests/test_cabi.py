@@ -168,12 +168,12 @@ def test_tail_kernel_index_walk_emulated_on_cpu(emu_lib):
             buf[o:o + s] = data[c]
         return buf
 
-    def emu(rank, dim, buf, x, begin=0, end=None, nwarps=4, grid=3, item=64, tau=0):
+    def emu(rank, dim, buf, x, begin=0, end=None, nwarps=4, grid=3, item=64, tau=0, use_dir=1, small=0):
         end = len(buf) if end is None else end
         out = ctypes.c_double()
         taus = (ctypes.c_int32 * comb.class_table(rank, dim).ncls)()
         rc = emu_lib.emu_contract_vec_f64(rank, i64(dim), ctypes.c_void_p(buf[begin:].ctypes.data), i64(begin), i64(end),
-                                          ctypes.c_void_p(x.ctypes.data), nwarps, grid, i64(item), tau, ctypes.byref(out), taus)
+                                          ctypes.c_void_p(x.ctypes.data), nwarps, grid, i64(item), tau, use_dir, i64(small), ctypes.byref(out), taus)
         assert rc == 0
         return out.value
 
@@ -183,9 +183,20 @@ def test_tail_kernel_index_walk_emulated_on_cpu(emu_lib):
         ref = po.contract_all_indices_with_vector(data, rank, dim, x)
         buf = pack(data, rank, dim)
         for tau in (0, 1, 2, 3):
-            for nw, grid, item in [(4, 3, 64), (16, 5, 32768)]:
-                assert abs(emu(rank, dim, buf, x, nwarps=nw, grid=grid, item=item, tau=tau) - ref) <= 1e-12 * abs(ref)
+            for nw, grid, item in [(4, 3, 64), (16, 5, 2048), (2, 7, 32), (1, 2, 1024)]:
+                for use_dir in (0, 1):
+                    got = emu(rank, dim, buf, x, nwarps=nw, grid=grid, item=item, tau=tau, use_dir=use_dir)
+                    assert abs(got - ref) <= 1e-12 * abs(ref), (rank, dim, tau, nw, grid, item, use_dir)
+        for small in (100, 10 ** 9):  # some / all classes through the per-component phase
+            assert abs(emu(rank, dim, buf, x, small=small) - ref) <= 1e-12 * abs(ref)
         tot = len(buf)
         cut = (tot // 3) // 32 * 32
-        s = sum(emu(rank, dim, buf, x, begin=b, end=e) for b, e in [(0, cut), (cut, 2 * cut), (2 * cut, tot)])
+        s = sum(emu(rank, dim, buf, x, begin=b, end=e, small=sm) for sm, (b, e) in zip((0, 50, 0), [(0, cut), (cut, 2 * cut), (2 * cut, tot)]))
         assert abs(s - ref) <= 1e-12 * abs(ref)
+        # fp32 instantiation (4 components per 16-byte vector)
+        buf32, x32 = buf.astype(np.float32), x.astype(np.float32)
+        out = ctypes.c_double()
+        for tau in (0, 2):
+            rc = emu_lib.emu_contract_vec_f32(rank, i64(dim), ctypes.c_void_p(buf32.ctypes.data), i64(0), i64(len(buf32)),
+                                              ctypes.c_void_p(x32.ctypes.data), 4, 3, i64(4096), tau, 1, i64(0), ctypes.byref(out), None)
+            assert rc == 0 and abs(out.value - ref) <= 1e-5 * abs(ref)

@@ -29,6 +29,8 @@ def abs_terms(data, rank, dim, x):
 
 @pytest.fixture(autouse=True)
 def _reset_variant():
+    """variant 0 = production (small classes per component, the rest through the tail tables), 1 = generic
+    per-component kernel, 2 = every class through the tail tables (so small test tensors exercise them)."""
     yield
     lib.st_set_vec_variant(0)
 
@@ -62,7 +64,7 @@ def test_config1_matches_the_reference_run(goldens):
     data = {cls: rng.uniform(0.5, 1.5, io.permclass_size(cls, 50)) for cls in io.perm_classes(4)}
     x = rng.uniform(0.5, 1.5, 50) / np.sqrt(50)
     A = st.PermClsTorchSymmetricTensor(rank=4, dim=50, data=data, device=DEV)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         check(lib.st_set_vec_variant(variant))
         got = float(st.contract_all_indices_with_vector(A, x))
         assert abs(got - c["result"]) <= RTOL64 * abs(c["result"])
@@ -75,7 +77,7 @@ def test_against_packed_oracle_fp64(rank, dim, dist):
     ref = po.contract_all_indices_with_vector(data, rank, dim, x)
     scale = abs_terms(data, rank, dim, x)
     A = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=data, device=DEV)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         check(lib.st_set_vec_variant(variant))
         assert abs(float(st.contract_all_indices_with_vector(A, x)) - ref) <= RTOL64 * scale
 
@@ -88,7 +90,7 @@ def test_fp32_against_fp64_oracle(rank, dim):
     ref = po.contract_all_indices_with_vector({k: v.astype(np.float64) for k, v in data.items()}, rank, dim, x.astype(np.float64))
     A = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=data, device=DEV)
     assert A.dtype == np.float32
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         check(lib.st_set_vec_variant(variant))
         res = st.contract_all_indices_with_vector(A, x)
         assert res.dtype == np.float32
@@ -166,7 +168,7 @@ def test_range_partials_sum_to_the_whole(rank, dim):
     A = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=data, device=DEV)
     xd = torch.as_tensor(x, device=DEV)
     total = A.packed.numel()
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         check(lib.st_set_vec_variant(variant))
         for nshards in (2, 3, 8):
             cuts = [min(total, (total * i // nshards + 31) // 32 * 32) for i in range(nshards)] + [total]

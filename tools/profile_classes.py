@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-class timing of the vector-contraction kernel (uses the [begin, end) range interface to run one class at
-a time).  python tools/profile_classes.py RANK DIM {f32|f64} [threads] [items_per_cta]"""
+a time).  python tools/profile_classes.py RANK DIM {f32|f64} [tile_bytes]"""
 import os
 import sys
 
@@ -17,9 +17,7 @@ def main():
     rank, dim = int(sys.argv[1]), int(sys.argv[2])
     tdt = torch.float32 if sys.argv[3] == "f32" else torch.float64
     if len(sys.argv) > 4:
-        check(lib.st_set_tuning(b"vec_ring_stages", c_i64(int(sys.argv[4]))))
-    if len(sys.argv) > 5:
-        check(lib.st_set_tuning(b"vec_items_per_cta", c_i64(int(sys.argv[5]))))
+        check(lib.st_set_tuning(b"vec_tile_bytes", c_i64(int(sys.argv[4]))))
     t = comb.class_table(rank, dim)
     buf = torch.rand(t.total, dtype=tdt, device=DEV) + 0.5
     x = (torch.rand(dim, dtype=tdt, device=DEV) + 0.5) / dim ** 0.5

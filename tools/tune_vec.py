@@ -2,7 +2,7 @@
 """Sweep the tuning knobs of the vector-contraction kernel on a B200 (run under gpurun).
 
     python tools/tune_vec.py [--quick]
-Prints one line per (workload, threads, items_per_cta): ms per launch and achieved GB/s of algorithmic bytes.
+Prints one line per (workload, threads, tile_bytes): ms per launch and achieved GB/s of algorithmic bytes.
 """
 import itertools
 import os
@@ -48,11 +48,10 @@ def main():
         workloads = workloads[:2]
     for rank, dim, tdt in workloads:
         for variant in ([0] if quick else [0]):
-            for threads, ipc in itertools.product([3, 6, 8], [4, 8, 16]):
-                check(lib.st_set_tuning(b"vec_ring_stages", c_i64(threads)))
-                check(lib.st_set_tuning(b"vec_items_per_cta", c_i64(ipc)))
+            for ipc in [4096, 8192, 16384, 32768, 65536]:
+                check(lib.st_set_tuning(b"vec_tile_bytes", c_i64(ipc)))
                 ms, gbs, val = bench(rank, dim, tdt)
-                print(f"r{rank} d{dim} {str(tdt)[6:]} stages={threads} items/cta={ipc}: {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s  val={val:.6g}", flush=True)
+                print(f"r{rank} d{dim} {str(tdt)[6:]} tile_bytes={ipc}: {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s  val={val:.6g}", flush=True)
 
 
 if __name__ == "__main__":
