@@ -123,6 +123,64 @@ int st_contract_vec_host_f64(int layout, int rank, int64_t dim, const double* h_
 int st_contract_vec_host_f32(int layout, int rank, int64_t dim, const float* h_packed, int64_t total,
                              const float* h_x, float* h_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Layout converters: permcls <-> flat re-ordering of the packed components (the step either side of the
+ * ops; replaces the Python gathers of PermClsSymmetricTensor._validate_data / todense,
+ * symtensor/permcls_symtensor.py:599-618, 883-887, and FlatSymmetricTensor.__init__,
+ * symtensor/flat_symtensor.py:100-110).  d_flat has C(dim+rank-1, rank) elements; d_permcls is the
+ * ST_LAYOUT_PERMCLS buffer (padding is written as zeros); [begin, end) is a range of permcls coordinates
+ * and d_permcls points at coordinate `begin`.
+ * ------------------------------------------------------------------------------------------------ */
+int st_permcls_to_flat_f64(int rank, int64_t dim, const double* d_permcls, double* d_flat, void* stream);
+int st_permcls_to_flat_f32(int rank, int64_t dim, const float* d_permcls, float* d_flat, void* stream);
+int st_flat_to_permcls_f64(int rank, int64_t dim, const double* d_flat, double* d_permcls, int64_t begin, int64_t end, void* stream);
+int st_flat_to_permcls_f32(int rank, int64_t dim, const float* d_flat, float* d_permcls, int64_t begin, int64_t end, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * multiply.outer, symmetrized  (symtensor/symalg.py:294-316 via symmetrized_op :206-283):
+ *     C_K = C(ra+rb, ra)^-1 * sum over position subsets S, |S| = ra, of A[K_S] * B[K_S^c]
+ * Operands in ST_LAYOUT_FLAT (rank ra / rb, same dim); the output is the ST_LAYOUT_PERMCLS buffer of rank
+ * ra + rb, coordinates [begin, end) (d_out points at `begin`): output ranges shard over GPUs with no
+ * collective.  st_outer_vec_* is the fused outer -> contract_all_indices_with_vector: it returns
+ * sum_K gamma_K C_K prod x[K] over the range without ever storing the rank-(ra+rb) tensor.
+ * ------------------------------------------------------------------------------------------------ */
+int st_outer_f64(int ra, int rb, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out, int64_t begin,
+                 int64_t end, void* stream);
+int st_outer_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin,
+                 int64_t end, void* stream);
+int64_t st_outer_vec_workspace_bytes(void);
+int st_outer_vec_f64(int ra, int rb, int64_t dim, const double* d_a_flat, const double* d_b_flat, const double* d_x,
+                     double* d_out, void* d_workspace, int64_t begin, int64_t end, void* stream);
+int st_outer_vec_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, const float* d_x, float* d_out,
+                     void* d_workspace, int64_t begin, int64_t end, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * tensordot, symmetrized, k contracted index pairs  (symtensor/symalg.py:427-459):
+ *     C_K = C(n, ra-k)^-1 sum_S sum_{J in [d]^k} A[K_S, J] B[J, K_S^c],   n = ra + rb - 2k
+ * computed as a pair-packed Gram matrix G = Aexp . Bexp^T (rows: packed free indices, columns: packed
+ * contracted tuples weighted by their multiplicity) followed by the gather of the C(n, ra-k) splits.
+ * Operands ST_LAYOUT_FLAT; output ST_LAYOUT_PERMCLS of rank n over [begin, end) (rank 0: one component,
+ * the reference returns dim 1).  d_workspace: st_tensordot_workspace_bytes() bytes.
+ * ------------------------------------------------------------------------------------------------ */
+int st_tensordot_workspace_bytes(int ra, int rb, int k, int64_t dim, int elem_size, int64_t* out_bytes);
+int st_tensordot_f64(int ra, int rb, int k, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out,
+                     int64_t begin, int64_t end, void* d_workspace, void* stream);
+int st_tensordot_f32(int ra, int rb, int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out,
+                     int64_t begin, int64_t end, void* d_workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * contract_all_indices_with_matrix  (symtensor/symalg.py:475-496):
+ *     C[j1..jr] = sum A[i1..ir] W[i1,j1] ... W[ir,jr]      (W is dim x dim, row-major, contracted on axis 0)
+ * as the partially-symmetric mode chain T_{k+1}[j1..j_{k+1}; I] = sum_a W[a, j_{k+1}] T_k[j1..jk; sort(a, I)];
+ * every intermediate is stored packed x packed.  Input and output ST_LAYOUT_FLAT of the same rank / dim.
+ * d_workspace: st_contract_mat_workspace_bytes() bytes (two ping-pong intermediates).
+ * ------------------------------------------------------------------------------------------------ */
+int st_contract_mat_workspace_bytes(int rank, int64_t dim, int elem_size, int64_t* out_bytes);
+int st_contract_mat_f64(int rank, int64_t dim, const double* d_a_flat, const double* d_W, double* d_out_flat, void* d_workspace,
+                        void* stream);
+int st_contract_mat_f32(int rank, int64_t dim, const float* d_a_flat, const float* d_W, float* d_out_flat, void* d_workspace,
+                        void* stream);
+
 /* kernel variant selection for benchmarking / tests: 0 = auto, 1 = generic per-element enumerator,
  * 2 = tail-table segmented kernel.  Process-wide. */
 int st_set_vec_variant(int variant);

@@ -43,6 +43,21 @@ SIGNATURES = {
     "st_contract_vec_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "st_contract_vec_host_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "st_contract_vec_host_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp]),
+    "st_permcls_to_flat_f64": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp]),
+    "st_permcls_to_flat_f32": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp]),
+    "st_flat_to_permcls_f64": (c_int, [c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_flat_to_permcls_f32": (c_int, [c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_outer_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_outer_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_outer_vec_workspace_bytes": (c_i64, []),
+    "st_outer_vec_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_outer_vec_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_tensordot_workspace_bytes": (c_int, [c_int, c_int, c_int, c_i64, c_int, c_i64p]),
+    "st_tensordot_f64": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "st_tensordot_f32": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "st_contract_mat_workspace_bytes": (c_int, [c_int, c_i64, c_int, c_i64p]),
+    "st_contract_mat_f64": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "st_contract_mat_f32": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "st_set_vec_variant": (c_int, [c_int]),
     "st_set_tuning": (c_int, [ctypes.c_char_p, c_i64]),
     "st_launch_count": (c_i64, []),

@@ -1,0 +1,567 @@
+// Packed-space implementations of the three tensor-valued ops of the hot path and the layout converters
+// they use.  Every op works on packed components only -- the reference's defaults densify to d^r and average
+// r! transposes (symtensor/symalg.py:206-283, 294-316, 427-459, 475-496); here the formulas of SURVEY.md A.3
+// are evaluated directly:
+//
+//   multiply.outer   C_K = C(n,ra)^-1  sum_{S subset of positions, |S| = ra}  A[K_S] B[K_S^c]          (n = ra + rb)
+//   tensordot        C_K = C(n,ra-k)^-1 sum_S sum_{J in [d]^k} A[K_S, J] B[J, K_S^c]                  (n = ra + rb - 2k)
+//                        = C(n,ra-k)^-1 sum_S G[rank(K_S)][rank(K_S^c)],   G = Aexp . Bexp^T  (pair-packed Gram matrix,
+//                          rows = packed free indices, columns = packed contracted tuples weighted by multiplicity)
+//   contract_all_indices_with_matrix   the partially-symmetric mode chain
+//                        T_{k+1}[j_1..j_{k+1}; I''] = sum_a W[a, j_{k+1}] T_k[j_1..j_k; sort(a, I'')],  T_0 = A, T_r = C
+//                    every T_k is stored packed x packed (flat order in both index groups); the "unpack" of the
+//                    contracted mode is a gather into the shared-memory tile of the step's GEMM.
+//
+// Operands and intermediates use the FLAT order (combinations_with_replacement, symtensor/flat_symtensor.py:
+// 39-50): the position of a sorted sub-multi-index is a sum of r binomials, so gathering A[K_S] needs no sort
+// (a subsequence of a sorted sequence is sorted) and no class lookup.  Results are written in the caller's
+// layout (permcls ranges [begin, end) for sharding over GPUs).
+#include <algorithm>
+#include <vector>
+
+#include "st_common.cuh"
+
+namespace st {
+
+// flat position of the sorted r-tuple s (r <= plan rank), using the plan's binomial table
+ST_HD int64_t flat_rank_r(const PlanView& P, const int32_t* s, int r) {
+  int64_t pos = binom_at(P.binom, P.rank, P.dim + r - 1, r) - 1;
+  for (int k = 0; k < r; ++k) pos -= binom_at(P.binom, P.rank, P.dim - 1 + k - s[r - 1 - k], k + 1);
+  return pos;
+}
+
+ST_HD void flat_unrank_r(const PlanView& P, int64_t pos, int r, int32_t* s) {
+  comb_unrank(P.binom, P.rank, pos, P.dim + r - 1, r, s);
+  for (int k = 0; k < r; ++k) s[k] -= k;
+}
+
+// packed coordinate of the permcls layout -> sorted multi-index (false for alignment padding)
+ST_HD bool permcls_coord_sorted(const PlanView& P, int64_t c, int32_t* K) {
+  const int ci = class_of_coord(P, c);
+  const ClassDesc& C = P.cls[ci];
+  const int64_t pos = c - C.offset;
+  if (pos >= C.size) return false;
+  int32_t vals[ST_MAX_RANK];
+  permcls_unrank_vals(P, C, pos, vals);
+  int n = 0;
+  for (int v = 0; v < C.nvals; ++v)
+    for (int m = 0; m < C.mult[v]; ++m) {
+      const int32_t x = vals[v];
+      int u = n++;
+      while (u > 0 && K[u - 1] > x) { K[u] = K[u - 1]; --u; }
+      K[u] = x;
+    }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// layout converters (also the "pack / unpack" step either side of the ops: permcls <-> flat re-ordering)
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void permcls_to_flat_kernel(PlanView P, const T* __restrict__ in, T* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P.flat_size; i += (int64_t)gridDim.x * blockDim.x) {
+    int32_t s[ST_MAX_RANK], vals[ST_MAX_RANK];
+    flat_unrank_sorted(P, i, s);
+    const int c = classify_index(P, s, vals);
+    out[i] = in[P.cls[c].offset + permcls_rank_vals(P, P.cls[c], vals)];
+  }
+}
+
+template <typename T>
+__global__ void flat_to_permcls_kernel(PlanView P, const T* __restrict__ in, T* __restrict__ out, int64_t begin, int64_t end) {
+  for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
+    int32_t K[ST_MAX_RANK];
+    out[c - begin] = permcls_coord_sorted(P, c, K) ? in[flat_rank_sorted(P, K)] : T(0);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// symmetrized outer product: one thread per packed output component, C(n, ra) gathered products
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) outer_kernel(PlanView P, int ra, int rb, const T* __restrict__ af, const T* __restrict__ bf,
+                                                    T* __restrict__ out, int64_t begin, int64_t end, double inv_count) {
+  const int n = ra + rb;
+  for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
+    int32_t K[ST_MAX_RANK];
+    if (!permcls_coord_sorted(P, c, K)) { out[c - begin] = T(0); continue; }
+    double acc = 0.0;
+    // all position subsets of size ra, as bit masks in increasing order (Gosper's hack)
+    for (uint32_t mask = (1u << ra) - 1u; mask < (1u << n);) {
+      int32_t sa[ST_MAX_RANK], sb[ST_MAX_RANK];
+      int ia = 0, ib = 0;
+      for (int p = 0; p < n; ++p) {
+        if ((mask >> p) & 1u) sa[ia++] = K[p]; else sb[ib++] = K[p];
+      }
+      acc += (double)af[flat_rank_r(P, sa, ra)] * (double)bf[flat_rank_r(P, sb, rb)];
+      if (ra == 0) break;
+      const uint32_t lo = mask & (0u - mask), hi = mask + lo;
+      mask = (((mask ^ hi) >> 2) / lo) | hi;
+    }
+    out[c - begin] = (T)(acc * inv_count);
+  }
+}
+
+// fused outer -> contract_all_indices_with_vector: sum_K gamma_K C_K prod x[K], the rank-n tensor is never stored
+template <typename T>
+__global__ void __launch_bounds__(256) outer_vec_kernel(PlanView P, int ra, int rb, const T* __restrict__ af, const T* __restrict__ bf,
+                                                        const T* __restrict__ x, double* __restrict__ partials, int64_t begin, int64_t end,
+                                                        double inv_count) {
+  __shared__ double red[32];
+  const int n = ra + rb;
+  double total = 0.0;
+  for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
+    int32_t K[ST_MAX_RANK];
+    if (!permcls_coord_sorted(P, c, K)) continue;
+    double acc = 0.0;
+    for (uint32_t mask = (1u << ra) - 1u; mask < (1u << n);) {
+      int32_t sa[ST_MAX_RANK], sb[ST_MAX_RANK];
+      int ia = 0, ib = 0;
+      for (int p = 0; p < n; ++p) {
+        if ((mask >> p) & 1u) sa[ia++] = K[p]; else sb[ib++] = K[p];
+      }
+      acc += (double)af[flat_rank_r(P, sa, ra)] * (double)bf[flat_rank_r(P, sb, rb)];
+      if (ra == 0) break;
+      const uint32_t lo = mask & (0u - mask), hi = mask + lo;
+      mask = (((mask ^ hi) >> 2) / lo) | hi;
+    }
+    double w = (double)P.cls[class_of_coord(P, c)].gamma;
+    for (int p = 0; p < n; ++p) w *= (double)x[K[p]];
+    total += acc * inv_count * w;
+  }
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = total;
+  __syncthreads();
+  if (warp == 0) {
+    double s = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) partials[blockIdx.x] = s;
+  }
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* out64, float* out32) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += partials[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) {
+      if (out64) *out64 = t;
+      if (out32) *out32 = (float)t;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tensordot: expansion of an operand to [packed free indices] x [packed contracted tuples]
+//   exp[p][J] = w(J) * flat[rank(sort(F_p, J))],  w(J) = multiplicity of the sorted k-tuple J (A side) or 1 (B side)
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void expand_kernel(PlanView P, int rfree, int k, const T* __restrict__ flat, T* __restrict__ ex, int64_t nfree, int64_t ncon,
+                              int weighted) {
+  const int64_t total = nfree * ncon;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / ncon, j = i - p * ncon;
+    int32_t f[ST_MAX_RANK], J[ST_MAX_RANK], m[ST_MAX_RANK];
+    flat_unrank_r(P, p, rfree, f);
+    flat_unrank_r(P, j, k, J);
+    // merge the two sorted tuples
+    int a = 0, b = 0, o = 0;
+    while (a < rfree || b < k) m[o++] = (b >= k || (a < rfree && f[a] <= J[b])) ? f[a++] : J[b++];
+    double w = 1.0;
+    if (weighted) {  // k! / prod(count!) distinct orderings of J
+      int rep = 0;
+      for (int q = 0; q < k; ++q) {
+        rep = (q > 0 && J[q] == J[q - 1]) ? rep + 1 : 1;
+        w *= (double)(q + 1) / (double)rep;
+      }
+    }
+    ex[i] = (T)(w * (double)flat[flat_rank_r(P, m, rfree + k)]);
+  }
+}
+
+// C[M x N] = A[M x K] . B[N x K]^T  (row-major, any sizes): 64 x 64 tile per CTA, 4 x 4 outputs per thread
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_nt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int64_t M, int64_t N,
+                                                      int64_t K) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ T As[TK][TM + 4];
+  __shared__ T Bs[TK][TN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  for (int64_t k0 = 0; k0 < K; k0 += TK) {
+    for (int e = threadIdx.x; e < TM * TK; e += 256) {
+      const int r = e / TK, kk = e % TK;
+      As[kk][r] = (m0 + r < M && k0 + kk < K) ? A[(m0 + r) * K + k0 + kk] : T(0);
+      Bs[kk][r] = (n0 + r < N && k0 + kk < K) ? B[(n0 + r) * K + k0 + kk] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) C[m * N + n] = acc[i][j];
+    }
+}
+
+// epilogue: C_K = inv_count * sum_S G[rank(K_S)][rank(K_S^c)], written in the permcls layout of rank n
+template <typename T>
+__global__ void __launch_bounds__(256) gram_gather_kernel(PlanView P, int na, int nb, const T* __restrict__ G, int64_t ncols, T* __restrict__ out,
+                                                          int64_t begin, int64_t end, double inv_count) {
+  const int n = na + nb;
+  for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
+    int32_t K[ST_MAX_RANK];
+    if (!permcls_coord_sorted(P, c, K)) { out[c - begin] = T(0); continue; }
+    double acc = 0.0;
+    for (uint32_t mask = (1u << na) - 1u; mask < (1u << n);) {
+      int32_t sa[ST_MAX_RANK], sb[ST_MAX_RANK];
+      int ia = 0, ib = 0;
+      for (int p = 0; p < n; ++p) {
+        if ((mask >> p) & 1u) sa[ia++] = K[p]; else sb[ib++] = K[p];
+      }
+      acc += (double)G[flat_rank_r(P, sa, na) * ncols + flat_rank_r(P, sb, nb)];
+      if (na == 0) break;
+      const uint32_t lo = mask & (0u - mask), hi = mask + lo;
+      mask = (((mask ^ hi) >> 2) / lo) | hi;
+    }
+    out[c - begin] = (T)(acc * inv_count);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// matrix contraction: one step of the mode chain
+//   Tn[(J, j)][I] = sum_a W[a][j] Tk[J][sort(a, I)]     J: sorted k-tuple, j >= max(J), I: sorted m-tuple (m = r-k-1)
+// CTA: one J, a tile of TI rows I and TJ columns j; the A-operand tile S[i][a] is GATHERED from the packed
+// row Tk[J][.] (the contracted mode is unpacked in shared memory only), W streams through shared memory.
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) mat_step_kernel(PlanView P, int k, int m, const T* __restrict__ Tk, const T* __restrict__ W,
+                                                       T* __restrict__ Tn, int64_t nJ, int64_t nI, int64_t nI1) {
+  constexpr int TI = 64, TJ = 64, TK = 16;
+  __shared__ T Ss[TK][TI + 4];
+  __shared__ T Ws[TK][TJ + 4];
+  __shared__ int32_t Is[TI][ST_MAX_RANK];  // the sorted m-tuples of the tile's rows
+  __shared__ int32_t Js[ST_MAX_RANK];
+  const int64_t d = P.dim;
+  const int64_t tilesI = (nI + TI - 1) / TI;
+  const int64_t jidx = blockIdx.x / tilesI, i0 = (blockIdx.x % tilesI) * TI;
+  const int64_t j0 = (int64_t)blockIdx.y * TJ;
+  if (threadIdx.x == 0) flat_unrank_r(P, jidx, k, Js);
+  for (int r = threadIdx.x; r < TI; r += 256)
+    if (i0 + r < nI) flat_unrank_r(P, i0 + r, m, Is[r]);
+  __syncthreads();
+  const int jlast = k ? Js[k - 1] : 0;
+  if (j0 + TJ <= jlast) return;  // every column of this tile is below max(J): not a sorted (k+1)-tuple
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const T* __restrict__ row = Tk + jidx * nI1;
+  T acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+  for (int64_t a0 = 0; a0 < d; a0 += TK) {
+    for (int e = threadIdx.x; e < TI * TK; e += 256) {
+      const int r = e % TI, aa = e / TI;
+      const int64_t a = a0 + aa;
+      T v = T(0);
+      if (i0 + r < nI && a < d) {
+        // flat rank of sort(a, I): walk the merged tuple from its largest element down
+        int64_t pos = binom_at(P.binom, P.rank, d + m, m + 1) - 1;
+        int q = m - 1;
+        bool placed = false;
+        for (int t = 0; t <= m; ++t) {
+          int32_t z;
+          if (!placed && (q < 0 || Is[r][q] <= a)) { z = (int32_t)a; placed = true; }
+          else z = Is[r][q--];
+          pos -= binom_at(P.binom, P.rank, d - 1 + t - z, t + 1);
+        }
+        v = row[pos];
+      }
+      Ss[aa][r] = v;
+    }
+    for (int e = threadIdx.x; e < TJ * TK; e += 256) {
+      const int c = e % TJ, aa = e / TJ;
+      Ws[aa][c] = (a0 + aa < d && j0 + c < d) ? W[(a0 + aa) * d + j0 + c] : T(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      T a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Ss[kk][ty * 4 + i]; b[i] = Ws[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  // store: row of the output = flat rank of the sorted (k+1)-tuple (J, j)
+  int32_t Jn[ST_MAX_RANK];
+  for (int q = 0; q < k; ++q) Jn[q] = Js[q];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t jj = j0 + tx * 4 + j;
+    if (jj >= d || jj < jlast) continue;
+    Jn[k] = (int32_t)jj;
+    const int64_t orow = flat_rank_r(P, Jn, k + 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t ii = i0 + ty * 4 + i;
+      if (ii < nI) Tn[orow * nI + ii] = acc[i][j];
+    }
+  }
+}
+
+static int grid_1d(int64_t n, int threads) {
+  int64_t g = (n + threads - 1) / threads;
+  const int64_t cap = 148 * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static int64_t flat_size_host(const HostPlan* hp, int r) {
+  return r == 0 ? 1 : hp->h_binom[(hp->dim + r - 1) * (hp->rank + 1) + r];
+}
+
+static double binom_double(int n, int k) {
+  double v = 1.0;
+  for (int i = 1; i <= k; ++i) v = v * (double)(n - k + i) / (double)i;
+  return v;
+}
+
+template <typename T>
+static int permcls_to_flat(int rank, int64_t dim, const T* d_in, T* d_out, cudaStream_t stream) {
+  PlanView P;
+  int rc = get_device_plan(rank, dim, &P);
+  if (rc) return rc;
+  if (get_host_plan(rank, dim)->flat_overflow) { set_error("flat size does not fit int64"); return ST_ERR_OVERFLOW; }
+  if (!d_in || !d_out) { set_error("null pointer"); return ST_ERR_INVALID; }
+  permcls_to_flat_kernel<T><<<grid_1d(P.flat_size, 256), 256, 0, stream>>>(P, d_in, d_out);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "permcls_to_flat_kernel");
+}
+
+template <typename T>
+static int flat_to_permcls(int rank, int64_t dim, const T* d_in, T* d_out, int64_t begin, int64_t end, cudaStream_t stream) {
+  PlanView P;
+  int rc = get_device_plan(rank, dim, &P);
+  if (rc) return rc;
+  if (begin < 0 || end < begin || end > P.total) { set_error("range [%lld, %lld) outside [0, %lld]", (long long)begin, (long long)end, (long long)P.total); return ST_ERR_INVALID; }
+  if (end == begin) return ST_OK;
+  if (!d_in || !d_out) { set_error("null pointer"); return ST_ERR_INVALID; }
+  flat_to_permcls_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(P, d_in, d_out, begin, end);
+  count_launch();
+  return check_cuda(cudaGetLastError(), "flat_to_permcls_kernel");
+}
+
+template <typename T>
+static int outer(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_b_flat, T* d_out, int64_t begin, int64_t end, cudaStream_t stream) {
+  if (ra < 0 || rb < 0 || ra + rb > ST_MAX_RANK) { set_error("ranks %d + %d exceed %d", ra, rb, ST_MAX_RANK); return ST_ERR_INVALID; }
+  PlanView P;
+  int rc = get_device_plan(ra + rb, dim, &P);
+  if (rc) return rc;
+  if (begin < 0 || end < begin || end > P.total) { set_error("range [%lld, %lld) outside [0, %lld]", (long long)begin, (long long)end, (long long)P.total); return ST_ERR_INVALID; }
+  if (end == begin) return ST_OK;
+  if (!d_a_flat || !d_b_flat || !d_out) { set_error("null pointer"); return ST_ERR_INVALID; }
+  outer_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_out, begin, end,
+                                                                  1.0 / binom_double(ra + rb, ra));
+  count_launch();
+  return check_cuda(cudaGetLastError(), "outer_kernel");
+}
+
+static const int kOuterVecCtas = 148 * 8;
+
+template <typename T>
+static int outer_vec(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_b_flat, const T* d_x, T* d_out, double* d_ws, int64_t begin,
+                     int64_t end, cudaStream_t stream) {
+  if (ra < 0 || rb < 0 || ra + rb > ST_MAX_RANK) { set_error("ranks %d + %d exceed %d", ra, rb, ST_MAX_RANK); return ST_ERR_INVALID; }
+  PlanView P;
+  int rc = get_device_plan(ra + rb, dim, &P);
+  if (rc) return rc;
+  if (begin < 0 || end < begin || end > P.total) { set_error("range outside the packed tensor"); return ST_ERR_INVALID; }
+  if (!d_a_flat || !d_b_flat || !d_out || !d_ws || (dim > 0 && !d_x)) { set_error("null pointer"); return ST_ERR_INVALID; }
+  const int grid = std::min(grid_1d(std::max<int64_t>(end - begin, 1), 256), kOuterVecCtas);
+  outer_vec_kernel<T><<<grid, 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_x, d_ws, begin, end, 1.0 / binom_double(ra + rb, ra));
+  if (sizeof(T) == 8) sum_partials_kernel<<<1, 256, 0, stream>>>(d_ws, grid, reinterpret_cast<double*>(d_out), nullptr);
+  else sum_partials_kernel<<<1, 256, 0, stream>>>(d_ws, grid, nullptr, reinterpret_cast<float*>(d_out));
+  count_launch(2);
+  return check_cuda(cudaGetLastError(), "outer_vec_kernel");
+}
+
+struct TdotShape {
+  int na, nb, n, R;
+  int64_t M, N, K;
+};
+
+static int tdot_shape(int ra, int rb, int k, int64_t dim, TdotShape* s) {
+  if (ra < 0 || rb < 0 || k < 0 || k > ra || k > rb) { set_error("cannot contract %d axes of rank-%d and rank-%d tensors", k, ra, rb); return ST_ERR_INVALID; }
+  s->na = ra - k;
+  s->nb = rb - k;
+  s->n = s->na + s->nb;
+  s->R = std::max(std::max(ra, rb), s->n);
+  if (s->R > ST_MAX_RANK) { set_error("rank %d exceeds %d", s->R, ST_MAX_RANK); return ST_ERR_INVALID; }
+  const HostPlan* hp = get_host_plan(s->R, dim);
+  if (!hp) return ST_ERR_INVALID;
+  s->M = flat_size_host(hp, s->na);
+  s->N = flat_size_host(hp, s->nb);
+  s->K = flat_size_host(hp, k);
+  return ST_OK;
+}
+
+template <typename T>
+static int tensordot(int ra, int rb, int k, int64_t dim, const T* d_a_flat, const T* d_b_flat, T* d_out, int64_t begin, int64_t end,
+                     void* d_ws, cudaStream_t stream) {
+  TdotShape s;
+  int rc = tdot_shape(ra, rb, k, dim, &s);
+  if (rc) return rc;
+  if (k == 0) return outer<T>(ra, rb, dim, d_a_flat, d_b_flat, d_out, begin, end, stream);
+  PlanView P, Pn;
+  rc = get_device_plan(s.R, dim, &P);  // operand gathers: binomials up to the largest rank involved
+  if (rc) return rc;
+  rc = get_device_plan(s.n, s.n ? dim : 1, &Pn);  // the output's permcls layout (rank 0: one component, dim 1)
+  if (rc) return rc;
+  if (begin < 0 || end < begin || end > Pn.total) { set_error("range outside the packed output"); return ST_ERR_INVALID; }
+  if (end == begin) return ST_OK;
+  if (!d_a_flat || !d_b_flat || !d_out || !d_ws) { set_error("null pointer"); return ST_ERR_INVALID; }
+  T* aex = reinterpret_cast<T*>(d_ws);
+  T* bex = aex + s.M * s.K;
+  T* G = bex + s.N * s.K;
+  expand_kernel<T><<<grid_1d(s.M * s.K, 256), 256, 0, stream>>>(P, s.na, k, d_a_flat, aex, s.M, s.K, 1);
+  expand_kernel<T><<<grid_1d(s.N * s.K, 256), 256, 0, stream>>>(P, s.nb, k, d_b_flat, bex, s.N, s.K, 0);
+  const dim3 grid((unsigned)((s.N + 63) / 64), (unsigned)((s.M + 63) / 64));
+  if (grid.y > 65535) { set_error("Gram matrix with %lld rows needs the tiled (non-materialising) kernel", (long long)s.M); return ST_ERR_UNSUPPORTED; }
+  gemm_nt_kernel<T><<<grid, 256, 0, stream>>>(aex, bex, G, s.M, s.N, s.K);
+  // the gather runs on the plan of the output rank; sub-tuple ranks only need binomials up to rank n there
+  gram_gather_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(Pn, s.na, s.nb, G, s.N, d_out, begin, end,
+                                                                        1.0 / binom_double(s.n, s.na));
+  count_launch(4);
+  return check_cuda(cudaGetLastError(), "tensordot kernels");
+}
+
+template <typename T>
+static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, T* d_out_flat, void* d_ws, cudaStream_t stream) {
+  if (rank < 0 || rank > ST_MAX_RANK) { set_error("rank %d outside [0, %d]", rank, ST_MAX_RANK); return ST_ERR_INVALID; }
+  PlanView P;
+  int rc = get_device_plan(rank, dim, &P);
+  if (rc) return rc;
+  const HostPlan* hp = get_host_plan(rank, dim);
+  if (!d_a_flat || !d_out_flat || (rank > 0 && (!d_W || !d_ws))) { set_error("null pointer"); return ST_ERR_INVALID; }
+  if (rank == 0 || dim == 0) return check_cuda(cudaMemcpyAsync(d_out_flat, d_a_flat, sizeof(T) * (size_t)P.flat_size, cudaMemcpyDeviceToDevice, stream), "cudaMemcpyAsync");
+  int64_t maxT = 0;
+  for (int k = 0; k <= rank; ++k) maxT = std::max(maxT, flat_size_host(hp, k) * flat_size_host(hp, rank - k));
+  T* buf[2] = {reinterpret_cast<T*>(d_ws), reinterpret_cast<T*>(d_ws) + maxT};
+  const T* src = d_a_flat;
+  for (int k = 0; k < rank; ++k) {
+    const int m = rank - k - 1;
+    const int64_t nJ = flat_size_host(hp, k), nI = flat_size_host(hp, m), nI1 = flat_size_host(hp, m + 1);
+    T* dst = (k == rank - 1) ? d_out_flat : buf[k & 1];
+    const int64_t tilesI = (nI + 63) / 64;
+    const int64_t gx = nJ * tilesI;
+    if (gx > 2147483647LL) { set_error("mode-chain step %d needs %lld CTAs", k, (long long)gx); return ST_ERR_UNSUPPORTED; }
+    const dim3 grid((unsigned)gx, (unsigned)((dim + 63) / 64));
+    mat_step_kernel<T><<<grid, 256, 0, stream>>>(P, k, m, src, d_W, dst, nJ, nI, nI1);
+    count_launch();
+    src = dst;
+  }
+  return check_cuda(cudaGetLastError(), "mat_step_kernel");
+}
+
+}  // namespace st
+
+using namespace st;
+
+extern "C" {
+
+int st_permcls_to_flat_f64(int rank, int64_t dim, const double* d_permcls, double* d_flat, void* stream) {
+  return permcls_to_flat<double>(rank, dim, d_permcls, d_flat, (cudaStream_t)stream);
+}
+int st_permcls_to_flat_f32(int rank, int64_t dim, const float* d_permcls, float* d_flat, void* stream) {
+  return permcls_to_flat<float>(rank, dim, d_permcls, d_flat, (cudaStream_t)stream);
+}
+int st_flat_to_permcls_f64(int rank, int64_t dim, const double* d_flat, double* d_permcls, int64_t begin, int64_t end, void* stream) {
+  return flat_to_permcls<double>(rank, dim, d_flat, d_permcls, begin, end, (cudaStream_t)stream);
+}
+int st_flat_to_permcls_f32(int rank, int64_t dim, const float* d_flat, float* d_permcls, int64_t begin, int64_t end, void* stream) {
+  return flat_to_permcls<float>(rank, dim, d_flat, d_permcls, begin, end, (cudaStream_t)stream);
+}
+
+int st_outer_f64(int ra, int rb, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out, int64_t begin, int64_t end,
+                 void* stream) {
+  return outer<double>(ra, rb, dim, d_a_flat, d_b_flat, d_out, begin, end, (cudaStream_t)stream);
+}
+int st_outer_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin, int64_t end,
+                 void* stream) {
+  return outer<float>(ra, rb, dim, d_a_flat, d_b_flat, d_out, begin, end, (cudaStream_t)stream);
+}
+
+int64_t st_outer_vec_workspace_bytes(void) { return (int64_t)sizeof(double) * kOuterVecCtas; }
+int st_outer_vec_f64(int ra, int rb, int64_t dim, const double* d_a_flat, const double* d_b_flat, const double* d_x, double* d_out,
+                     void* d_workspace, int64_t begin, int64_t end, void* stream) {
+  return outer_vec<double>(ra, rb, dim, d_a_flat, d_b_flat, d_x, d_out, reinterpret_cast<double*>(d_workspace), begin, end, (cudaStream_t)stream);
+}
+int st_outer_vec_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, const float* d_x, float* d_out,
+                     void* d_workspace, int64_t begin, int64_t end, void* stream) {
+  return outer_vec<float>(ra, rb, dim, d_a_flat, d_b_flat, d_x, d_out, reinterpret_cast<double*>(d_workspace), begin, end, (cudaStream_t)stream);
+}
+
+int st_tensordot_workspace_bytes(int ra, int rb, int k, int64_t dim, int elem_size, int64_t* out_bytes) {
+  TdotShape s;
+  int rc = tdot_shape(ra, rb, k, dim, &s);
+  if (rc) return rc;
+  if (!out_bytes) { set_error("null pointer"); return ST_ERR_INVALID; }
+  const __int128 elems = k == 0 ? 0 : (__int128)s.M * s.K + (__int128)s.N * s.K + (__int128)s.M * s.N;
+  if (elems * elem_size > (__int128)INT64_MAX) { set_error("workspace does not fit int64"); return ST_ERR_OVERFLOW; }
+  *out_bytes = (int64_t)elems * elem_size;
+  return ST_OK;
+}
+int st_tensordot_f64(int ra, int rb, int k, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out, int64_t begin,
+                     int64_t end, void* d_workspace, void* stream) {
+  return tensordot<double>(ra, rb, k, dim, d_a_flat, d_b_flat, d_out, begin, end, d_workspace, (cudaStream_t)stream);
+}
+int st_tensordot_f32(int ra, int rb, int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin,
+                     int64_t end, void* d_workspace, void* stream) {
+  return tensordot<float>(ra, rb, k, dim, d_a_flat, d_b_flat, d_out, begin, end, d_workspace, (cudaStream_t)stream);
+}
+
+int st_contract_mat_workspace_bytes(int rank, int64_t dim, int elem_size, int64_t* out_bytes) {
+  const HostPlan* hp = get_host_plan(rank, dim);
+  if (!hp) return ST_ERR_INVALID;
+  if (!out_bytes) { set_error("null pointer"); return ST_ERR_INVALID; }
+  __int128 maxT = 0;
+  for (int k = 0; k <= rank; ++k) maxT = std::max(maxT, (__int128)flat_size_host(hp, k) * flat_size_host(hp, rank - k));
+  if (maxT * 2 * elem_size > (__int128)INT64_MAX) { set_error("workspace does not fit int64"); return ST_ERR_OVERFLOW; }
+  *out_bytes = (int64_t)(maxT * 2 * elem_size);
+  return ST_OK;
+}
+int st_contract_mat_f64(int rank, int64_t dim, const double* d_a_flat, const double* d_W, double* d_out_flat, void* d_workspace, void* stream) {
+  return contract_mat<double>(rank, dim, d_a_flat, d_W, d_out_flat, d_workspace, (cudaStream_t)stream);
+}
+int st_contract_mat_f32(int rank, int64_t dim, const float* d_a_flat, const float* d_W, float* d_out_flat, void* d_workspace, void* stream) {
+  return contract_mat<float>(rank, dim, d_a_flat, d_W, d_out_flat, d_workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -5,6 +5,8 @@ error behaviour, then makes ONE call into the C-ABI with raw device pointers on 
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -83,3 +85,217 @@ def _contract_all_indices_with_vector(symtensor, x):
 
 for _cls in (CudaPermClsSymmetricTensor, CudaFlatSymmetricTensor):
     _cls.implements(symalg.contract_all_indices_with_vector)(_contract_all_indices_with_vector)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# tensor-valued ops: multiply.outer, tensordot, contract_all_indices_with_matrix
+# ------------------------------------------------------------------------------------------------------------
+_SYM = (CudaPermClsSymmetricTensor, CudaFlatSymmetricTensor)
+
+
+def _fn(name: str, tdt: torch.dtype):
+    return getattr(lib, f"{name}_{'f64' if tdt == torch.float64 else 'f32'}")
+
+
+def _need_device(t):
+    if t._host:
+        raise RuntimeError("symtensor_b200: this op needs the tensor on a CUDA device (use .to('cuda')); there is no CPU "
+                           "fallback")
+
+
+def _flat_buffer(t, tdt: torch.dtype) -> torch.Tensor:
+    """The components of ``t`` in the flat order (combinations_with_replacement), on its device, as ``tdt``."""
+    _need_device(t)
+    buf = t._buf if t._buf.dtype == tdt else t._buf.to(tdt)
+    if isinstance(t, CudaFlatSymmetricTensor):
+        return buf.contiguous()
+    out = torch.empty(max(1, t.indep_size), dtype=tdt, device=t.device)
+    with torch.cuda.device(t.device):
+        check(_fn("st_permcls_to_flat", tdt)(t.rank, c_i64(t.dim), buf.data_ptr(), out.data_ptr(), _stream_ptr(t.device)))
+    return out
+
+
+def _wrap_flat_result(cls, rank: int, dim: int, flat: torch.Tensor):
+    """A tensor of class ``cls`` from components in the flat order."""
+    if issubclass(cls, CudaFlatSymmetricTensor):
+        return cls.from_packed(rank, dim, flat)
+    total = comb_total(rank, dim)
+    out = torch.empty(total, dtype=flat.dtype, device=flat.device)
+    with torch.cuda.device(flat.device):
+        check(_fn("st_flat_to_permcls", flat.dtype)(rank, c_i64(dim), flat.data_ptr(), out.data_ptr(), c_i64(0), c_i64(total),
+                                                    _stream_ptr(flat.device)))
+    return cls.from_packed(rank, dim, out)
+
+
+def comb_total(rank: int, dim: int) -> int:
+    from . import combinatorics as comb
+    return comb.class_table(rank, dim).total
+
+
+def _as_symtensor_operand(x, like):
+    """ndarray / torch operands of tensordot and outer: vectors and scalars are symmetric tensors already; a
+    higher-rank dense array must be symmetric (it is packed through the class constructor, which checks)."""
+    if isinstance(x, _SYM):
+        return x
+    arr = x if isinstance(x, torch.Tensor) else np.asarray(x)
+    nd = arr.ndim
+    if nd == 0:
+        return type(like)(rank=0, dim=1, data={(): arr} if isinstance(like, CudaPermClsSymmetricTensor) else arr, device=like.device)
+    if isinstance(like, CudaPermClsSymmetricTensor):
+        return CudaPermClsSymmetricTensor(data=arr, device=like.device) if nd > 1 else \
+            CudaPermClsSymmetricTensor(rank=1, dim=arr.shape[0], data={(1,): arr}, device=like.device)
+    return CudaFlatSymmetricTensor(nd, arr.shape[0], arr, device=like.device)
+
+
+def _result_dtype(a, b) -> torch.dtype:
+    res = np.result_type(a.dtype, b.dtype)
+    if res not in _NP2TORCH:
+        raise TypeError(f"unsupported result dtype {res}")
+    return _NP2TORCH[res]
+
+
+def outer_device(a, b, out_rank_buf: torch.Tensor, begin: int, end: int, tdt: torch.dtype, af=None, bf=None):
+    """Raw launch: coordinates [begin, end) of the permcls buffer of a (x)_s b into ``out_rank_buf`` (which starts at
+    coordinate ``begin``) -- the output range is the sharding axis for multi-GPU runs."""
+    af = _flat_buffer(a, tdt) if af is None else af
+    bf = _flat_buffer(b, tdt) if bf is None else bf
+    with torch.cuda.device(af.device):
+        check(_fn("st_outer", tdt)(a.rank, b.rank, c_i64(a.dim), af.data_ptr(), bf.data_ptr(), out_rank_buf.data_ptr(),
+                                   c_i64(begin), c_i64(end), _stream_ptr(af.device)))
+
+
+def _outer(ufunc, a, b, **kwargs):
+    """symtensor/symalg.py:294-316 for ``multiply``: C_K = mean over the C(n, ra) position splits of A[K_S] B[K_S^c]."""
+    if ufunc is not symalg.multiply:
+        return NotImplemented  # add.outer / subtract.outer: "next" row of the scope table
+    like = a if isinstance(a, _SYM) else b
+    ranka, rankb = np.ndim(a) if not isinstance(a, _SYM) else a.rank, np.ndim(b) if not isinstance(b, _SYM) else b.rank
+    dima = a.dim if isinstance(a, _SYM) else (*np.shape(a), 1)[0]
+    dimb = b.dim if isinstance(b, _SYM) else (*np.shape(b), 1)[0]
+    if ranka != 0 and rankb != 0 and dima != dimb:
+        return NotImplemented
+    symargs = tuple(x for x in (a, b) if isinstance(x, _SYM))
+    cls = symalg.result_array(*symargs)
+    a, b = _as_symtensor_operand(a, like), _as_symtensor_operand(b, like)
+    out = kwargs.pop("out", None)
+    tdt = _result_dtype(a, b) if out is None else out.torch_dtype
+    n = a.rank + b.rank
+    dim = a.dim if a.rank else b.dim
+    if a.rank == 0 or b.rank == 0:  # scalar times tensor
+        s, t = (a, b) if a.rank == 0 else (b, a)
+        res = cls.from_packed(t.rank, t.dim, (t._buf.to(tdt) * s._buf.to(tdt).reshape(-1)[0]))
+        if out is not None:
+            out._buf.copy_(res._buf)
+            return out
+        return res
+    if issubclass(cls, CudaFlatSymmetricTensor):
+        tmp = torch.empty(comb_total(n, dim), dtype=tdt, device=a.device)
+        outer_device(a, b, tmp, 0, tmp.numel(), tdt)
+        res_p = CudaPermClsSymmetricTensor.from_packed(n, dim, tmp)
+        res = cls.from_packed(n, dim, _flat_buffer(res_p, tdt))
+    else:
+        buf = out._buf if (out is not None and isinstance(out, CudaPermClsSymmetricTensor)) else \
+            torch.empty(comb_total(n, dim), dtype=tdt, device=a.device)
+        outer_device(a, b, buf, 0, buf.numel(), tdt)
+        res = out if buf is getattr(out, "_buf", None) else cls.from_packed(n, dim, buf)
+    if out is not None and res is not out:
+        out._buf.copy_(res._buf)
+        return out
+    return res
+
+
+def _normalize_axes(axes, ra: int, rb: int) -> int:
+    """Only the NUMBER of contracted axes matters for symmetric operands (symtensor/testing/api.py:546-552)."""
+    if isinstance(axes, (int, np.integer)):
+        k = int(axes)
+    else:
+        ax_a, ax_b = axes
+        ax_a = [ax_a] if isinstance(ax_a, (int, np.integer)) else list(ax_a)
+        ax_b = [ax_b] if isinstance(ax_b, (int, np.integer)) else list(ax_b)
+        if len(ax_a) != len(ax_b):
+            raise ValueError("shape-mismatch for sum")
+        k = len(ax_a)
+    if k < 0 or k > ra or k > rb:
+        raise ValueError(f"cannot contract {k} axes of tensors with ranks {ra} and {rb}")
+    return k
+
+
+def _tensordot(a, b, axes=2):
+    """symtensor/symalg.py:427-459: Sym(sum over `axes` contracted index pairs)."""
+    like = a if isinstance(a, _SYM) else b
+    cls = symalg.result_array(*(x for x in (a, b) if isinstance(x, _SYM)))
+    a, b = _as_symtensor_operand(a, like), _as_symtensor_operand(b, like)
+    k = _normalize_axes(axes, a.rank, b.rank)
+    if a.rank and b.rank and a.dim != b.dim:
+        raise ValueError(f"shape-mismatch for sum: dimensions {a.dim} and {b.dim}")
+    if k == 0:
+        return _outer(symalg.multiply, a, b)
+    tdt = _result_dtype(a, b)
+    dim = a.dim
+    n = a.rank + b.rank - 2 * k
+    out_dim = dim if n else 1
+    af, bf = _flat_buffer(a, tdt), _flat_buffer(b, tdt)
+    nbytes = c_i64(0)
+    check(lib.st_tensordot_workspace_bytes(a.rank, b.rank, k, c_i64(dim), af.element_size(), ctypes.byref(nbytes)))
+    if nbytes.value > 64 << 30:
+        raise NotImplementedError(f"symtensor_b200.tensordot: the pair-packed Gram matrix needs {nbytes.value / 2 ** 30:.0f} GiB; "
+                                  "sizes beyond one GPU need the tiled kernel (not in this build)")
+    total = comb_total(n, out_dim)
+    with torch.cuda.device(af.device):
+        ws = torch.empty(max(1, nbytes.value // af.element_size()), dtype=tdt, device=af.device)
+        buf = torch.empty(total, dtype=tdt, device=af.device)
+        check(_fn("st_tensordot", tdt)(a.rank, b.rank, k, c_i64(dim), af.data_ptr(), bf.data_ptr(), buf.data_ptr(), c_i64(0),
+                                       c_i64(total), ws.data_ptr(), _stream_ptr(af.device)))
+    res = CudaPermClsSymmetricTensor.from_packed(n, out_dim, buf)
+    if issubclass(cls, CudaFlatSymmetricTensor):
+        return cls.from_packed(n, out_dim, _flat_buffer(res, tdt))
+    return res if cls is CudaPermClsSymmetricTensor else cls.from_packed(n, out_dim, buf)
+
+
+def _contract_all_indices_with_matrix(symtensor, W):
+    """symtensor/symalg.py:475-496: C[j1..jr] = sum A[i1..ir] W[i1,j1]...W[ir,jr] (W contracted on its first axis)."""
+    if not isinstance(symtensor, _SYM):
+        return NotImplemented
+    cls = type(symtensor)
+    Wt = W if isinstance(W, torch.Tensor) else torch.as_tensor(np.asarray(W))
+    d = symtensor.dim
+    if symtensor.rank > 0 and tuple(Wt.shape) != (d, d):
+        raise ValueError(f"W must have shape {(d, d)} to contract a tensor of dimension {d}; received {tuple(Wt.shape)}")
+    wd = _TORCH2NP.get(Wt.dtype, np.dtype("float64"))
+    tdt = _promote(symtensor.dtype, np.empty(0, dtype=wd if wd.kind == "f" else symtensor.dtype))
+    af = _flat_buffer(symtensor, tdt)
+    nbytes = c_i64(0)
+    check(lib.st_contract_mat_workspace_bytes(symtensor.rank, c_i64(d), af.element_size(), ctypes.byref(nbytes)))
+    with torch.cuda.device(af.device):
+        Wd = Wt.to(device=af.device, dtype=tdt).contiguous()
+        ws = torch.empty(max(1, nbytes.value // af.element_size()), dtype=tdt, device=af.device)
+        outf = torch.empty_like(af)
+        check(_fn("st_contract_mat", tdt)(symtensor.rank, c_i64(d), af.data_ptr(), Wd.data_ptr(), outf.data_ptr(), ws.data_ptr(),
+                                          _stream_ptr(af.device)))
+    return _wrap_flat_result(cls, symtensor.rank, d, outf)
+
+
+def outer_then_contract_vec(a, b, x):
+    """Fused ``contract_all_indices_with_vector(multiply.outer(a, b), x)``: the rank-(ra+rb) tensor is never stored
+    (BASELINE config 5's pipeline in one pass).  Returns a rank-0 tensor of the operands' class."""
+    like = a
+    cls = symalg.result_array(a, b)
+    tdt = _promote(np.result_type(a.dtype, b.dtype), x)
+    if len(x) != a.dim or a.dim != b.dim:
+        raise ValueError("Dimensions of tensors and vector must match")
+    af, bf = _flat_buffer(a, tdt), _flat_buffer(b, tdt)
+    n = a.rank + b.rank
+    total = comb_total(n, a.dim)
+    with torch.cuda.device(af.device):
+        xd = (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(device=af.device, dtype=tdt).contiguous()
+        out = torch.zeros(32 if cls.layout == 0 else 1, dtype=tdt, device=af.device)
+        ws = torch.empty(int(lib.st_outer_vec_workspace_bytes()) // 8, dtype=torch.float64, device=af.device)
+        check(_fn("st_outer_vec", tdt)(a.rank, b.rank, c_i64(a.dim), af.data_ptr(), bf.data_ptr(), xd.data_ptr(), out.data_ptr(),
+                                       ws.data_ptr(), c_i64(0), c_i64(total), _stream_ptr(af.device)))
+    return cls.from_packed(0, 1, out)
+
+
+for _cls in _SYM:
+    _cls.implements(symalg.tensordot)(_tensordot)
+    _cls.implements(symalg.contract_all_indices_with_matrix)(_contract_all_indices_with_matrix)
+    _cls.implements_ufunc.outer(symalg.multiply)(_outer)

@@ -1,0 +1,237 @@
+"""multiply.outer, tensordot and contract_all_indices_with_matrix on the GPU, through the reference-facing API
+(symtensor_b200.symalg, registered with ``@Cls.implements`` like a reference backend mixin) and the C-ABI, against:
+the unmodified reference's outputs (tests/golden), the packed oracle on seeded inputs at sizes the reference cannot
+reach, and the algebraic identities of SURVEY.md 8c.  Index maps (layout converters) are checked bit-exactly.
+
+Tolerances (north-star): 1e-12 relative (fp64) / 1e-5 relative (fp32) of the sum of |terms| per component; fp32
+parity is taken against the fp64 oracle on the up-cast inputs (the reference's own fp32 path raises)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import index_oracle as io
+from oracle import packed_oracle as po
+
+import symtensor_b200 as st
+from symtensor_b200 import combinatorics as comb
+from symtensor_b200 import ops
+from symtensor_b200._cabi import c_i64, check, lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RTOL64, RTOL32 = 1e-12, 1e-5
+
+
+def rand_packed(rank, dim, rng, dist="pos", dtype=np.float64):
+    out = {}
+    for c in io.perm_classes(rank):
+        n = io.permclass_size(c, dim)
+        out[c] = (rng.uniform(0.5, 1.5, n) if dist == "pos" else rng.standard_normal(n)).astype(dtype)
+    return out
+
+
+def absd(d):
+    return {k: np.abs(np.asarray(v, dtype=np.float64)) for k, v in d.items()}
+
+
+def assert_classes_close(T, ref, scale, rtol):
+    """T: GPU tensor; ref / scale: {class: array} (scale = same op on |inputs|, the per-component sum of |terms|)."""
+    got = T.to_numpy_dict()
+    for c, r in ref.items():
+        if io.permclass_size(c, T.dim) == 0 and T.rank:
+            continue
+        g = np.asarray(got[c], dtype=np.float64).reshape(np.shape(r))
+        s = np.maximum(np.asarray(scale[c], dtype=np.float64), 1e-300)
+        assert np.all(np.abs(g - np.asarray(r, dtype=np.float64)) <= rtol * s), (c, np.max(np.abs(g - r) / s))
+
+
+def full(data, rank, dim):
+    return {k: np.broadcast_to(np.asarray(v, dtype=np.float64), (io.permclass_size(k, dim),)) if rank else np.asarray(v)
+            for k, v in data.items()}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def test_layout_converters_are_bit_exact():
+    """permcls <-> flat re-ordering (the reference's σindex_iter / combinations_with_replacement orders)."""
+    for rank, dim in [(1, 7), (2, 9), (3, 6), (4, 11), (5, 5), (6, 7), (8, 5)]:
+        rng = np.random.default_rng(rank * 100 + dim)
+        data = rand_packed(rank, dim, rng, "normal")
+        A = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=data, device=DEV)
+        flat = ops._flat_buffer(A, torch.float64)
+        assert np.array_equal(flat.cpu().numpy(), po.permcls_to_flat(data, rank, dim))
+        B = ops._wrap_flat_result(st.PermClsTorchSymmetricTensor, rank, dim, flat)
+        assert torch.equal(B.packed, A.packed)  # values and zero padding
+
+
+def test_outer_reference_goldens(goldens):
+    for c in goldens.cases("outer"):
+        A, B, ref = goldens.packed(c["tag"] + ".A"), goldens.packed(c["tag"] + ".B"), goldens.packed(c["tag"] + ".out")
+        ra, rb, d = c["ra"], c["rb"], c["dim"]
+        TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=d, data=dict(A), device=DEV)
+        TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=d, data=dict(B), device=DEV)
+        C = st.multiply.outer(TA, TB)
+        assert isinstance(C, st.PermClsTorchSymmetricTensor) and C.rank == ra + rb and C.dim == d
+        scale = po.outer(absd(full(A, ra, d)), ra, absd(full(B, rb, d)), rb, d)
+        assert_classes_close(C, ref, scale, 1e-11)  # the reference's own (ra+rb)! symmetrization noise
+        assert_classes_close(C, po.outer(full(A, ra, d), ra, full(B, rb, d), rb, d), scale, RTOL64)
+    # e0 (x)_s e1: off-diagonal 0.5, diagonal 0 (symtensor/testing/api.py:497-512)
+    e0 = st.PermClsTorchSymmetricTensor(rank=1, dim=2, data={(1,): np.array([1.0, 0.0])}, device=DEV)
+    e1 = st.PermClsTorchSymmetricTensor(rank=1, dim=2, data={(1,): np.array([0.0, 1.0])}, device=DEV)
+    C = st.multiply.outer(e0, e1)
+    assert np.allclose(C["ij"].cpu().numpy(), [0.5]) and np.allclose(C["ii"].cpu().numpy(), [0.0, 0.0])
+    # different dimensions: TypeError like the reference (NotImplemented from every provider)
+    with pytest.raises(TypeError):
+        st.multiply.outer(e0, st.PermClsTorchSymmetricTensor(rank=1, dim=3, data=1.0, device=DEV))
+
+
+@pytest.mark.parametrize("ra,rb,dim,dist", [(2, 2, 12, "pos"), (3, 2, 9, "normal"), (4, 4, 5, "pos"), (1, 5, 6, "pos"), (3, 3, 10, "normal")])
+def test_outer_against_packed_oracle(ra, rb, dim, dist):
+    rng = np.random.default_rng(ra * 10 + rb + dim)
+    A, B = rand_packed(ra, dim, rng, dist), rand_packed(rb, dim, rng, dist)
+    TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=A, device=DEV)
+    TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=B, device=DEV)
+    C = st.multiply.outer(TA, TB)
+    ref, scale = po.outer(A, ra, B, rb, dim), po.outer(absd(A), ra, absd(B), rb, dim)
+    assert_classes_close(C, ref, scale, RTOL64)
+    # fp32 against the fp64 oracle on the up-cast inputs
+    C32 = st.multiply.outer(TA.astype(np.float32), TB.astype(np.float32))
+    assert C32.dtype == np.float32
+    A32, B32 = {k: v.astype(np.float32).astype(np.float64) for k, v in A.items()}, {k: v.astype(np.float32).astype(np.float64) for k, v in B.items()}
+    assert_classes_close(C32, po.outer(A32, ra, B32, rb, dim), scale, RTOL32)
+    # identity (A (x)_s B) . x^n = (A . x^ra)(B . x^rb), and the fused outer -> vector kernel
+    x = rng.uniform(0.5, 1.5, dim) / np.sqrt(dim)
+    lhs = float(st.contract_all_indices_with_vector(C, x))
+    rhs = po.contract_all_indices_with_vector(A, ra, dim, x) * po.contract_all_indices_with_vector(B, rb, dim, x)
+    s = po.contract_all_indices_with_vector(absd(A), ra, dim, np.abs(x)) * po.contract_all_indices_with_vector(absd(B), rb, dim, np.abs(x))
+    assert abs(lhs - rhs) <= 1e-11 * s
+    fused = float(ops.outer_then_contract_vec(TA, TB, x))
+    assert abs(fused - rhs) <= 1e-11 * s
+
+
+def test_outer_output_ranges_shard(goldens):
+    """[begin, end) output ranges (the multi-GPU partition of multiply.outer): the pieces concatenate to the whole."""
+    ra, rb, dim = 3, 3, 8
+    rng = np.random.default_rng(5)
+    TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=rand_packed(ra, dim, rng), device=DEV)
+    TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=rand_packed(rb, dim, rng), device=DEV)
+    whole = st.multiply.outer(TA, TB).packed
+    total = whole.numel()
+    cuts = [min(total, (total * i // 3 + 31) // 32 * 32) for i in range(3)] + [total]
+    for b, e in zip(cuts[:-1], cuts[1:]):
+        part = torch.empty(e - b, dtype=torch.float64, device=DEV)
+        ops.outer_device(TA, TB, part, b, e, torch.float64)
+        assert torch.equal(part, whole[b:e])
+
+
+def test_tensordot_reference_goldens(goldens):
+    for c in goldens.cases("tensordot"):
+        A, B, ref = goldens.packed(c["tag"] + ".A"), goldens.packed(c["tag"] + ".B"), goldens.packed(c["tag"] + ".out")
+        ra, rb, d, k = c["ra"], c["rb"], c["dim"], c["k"]
+        TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=d, data=dict(A), device=DEV)
+        TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=d, data=dict(B), device=DEV)
+        C = st.tensordot(TA, TB, axes=k)
+        assert isinstance(C, st.PermClsTorchSymmetricTensor) and C.rank == c["out_rank"] and C.dim == c["out_dim"]
+        scale, _ = po.tensordot(absd(full(A, ra, d)), ra, absd(full(B, rb, d)), rb, d, k)
+        if C.rank == 0:
+            assert abs(float(C) - float(ref[()])) <= 1e-11 * float(scale[()])
+            continue
+        assert_classes_close(C, ref, scale, 1e-11)
+
+
+@pytest.mark.parametrize("ra,rb,k,dim", [(3, 3, 1, 11), (3, 3, 2, 9), (4, 2, 1, 8), (3, 1, 1, 17), (4, 3, 2, 6), (2, 2, 2, 13), (3, 2, 1, 40)])
+def test_tensordot_against_packed_oracle(ra, rb, k, dim):
+    rng = np.random.default_rng(ra + 7 * rb + 31 * k + dim)
+    A, B = rand_packed(ra, dim, rng, "normal"), rand_packed(rb, dim, rng, "normal")
+    TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=A, device=DEV)
+    TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=B, device=DEV)
+    ref, n = po.tensordot(A, ra, B, rb, dim, k)
+    scale, _ = po.tensordot(absd(A), ra, absd(B), rb, dim, k)
+    for axes in (k, (list(range(k)), list(range(k)))):  # NumPy-style axis tuples: only their number matters
+        C = st.tensordot(TA, TB, axes=axes)
+        assert C.rank == n
+        if n == 0:
+            assert abs(float(C) - float(ref[()])) <= RTOL64 * float(scale[()])
+        else:
+            assert_classes_close(C, ref, scale, RTOL64)
+    C32 = st.tensordot(TA.astype(np.float32), TB.astype(np.float32), axes=k)
+    A32, B32 = {q: v.astype(np.float32).astype(np.float64) for q, v in A.items()}, {q: v.astype(np.float32).astype(np.float64) for q, v in B.items()}
+    ref32, _ = po.tensordot(A32, ra, B32, rb, dim, k)
+    if n == 0:
+        assert abs(float(C32) - float(ref32[()])) <= RTOL32 * float(scale[()])
+    else:
+        assert_classes_close(C32, ref32, scale, RTOL32)
+
+
+def test_tensordot_identities():
+    """tensordot(A, B, 0) == multiply.outer(A, B) (symtensor/testing/api.py:521-522); r-fold tensordot with a
+    vector == contract_all_indices_with_vector."""
+    rng = np.random.default_rng(11)
+    d = 7
+    A, B = rand_packed(3, d, rng), rand_packed(2, d, rng)
+    TA = st.PermClsTorchSymmetricTensor(rank=3, dim=d, data=A, device=DEV)
+    TB = st.PermClsTorchSymmetricTensor(rank=2, dim=d, data=B, device=DEV)
+    assert torch.equal(st.tensordot(TA, TB, axes=0).packed, st.multiply.outer(TA, TB).packed)
+    x = rng.uniform(0.5, 1.5, d)
+    t = TA
+    for _ in range(3):
+        t = st.tensordot(t, x, axes=1)
+    assert t.rank == 0
+    ref = po.contract_all_indices_with_vector(A, 3, d, x)
+    assert abs(float(t) - ref) <= 1e-12 * abs(ref)
+    assert abs(float(st.contract_all_indices_with_vector(TA, x)) - ref) <= 1e-12 * abs(ref)
+
+
+def test_matrix_reference_goldens(goldens):
+    for c in goldens.cases("mat"):
+        A, W, ref = goldens.packed(c["tag"] + ".A"), goldens.ops[c["tag"] + ".W"], goldens.packed(c["tag"] + ".out")
+        r, d = c["rank"], c["dim"]
+        TA = st.PermClsTorchSymmetricTensor(rank=r, dim=d, data=dict(A), device=DEV)
+        C = st.contract_all_indices_with_matrix(TA, W)
+        assert isinstance(C, st.PermClsTorchSymmetricTensor) and C.rank == r and C.dim == d
+        scale = po.contract_all_indices_with_matrix(absd(full(A, r, d)), r, d, np.abs(W))
+        assert_classes_close(C, ref, scale, 1e-11)
+
+
+@pytest.mark.parametrize("rank,dim", [(2, 33), (3, 20), (4, 12), (5, 7), (6, 6), (3, 70), (4, 66)])
+def test_matrix_against_packed_oracle(rank, dim):
+    rng = np.random.default_rng(rank * 1000 + dim)
+    A = rand_packed(rank, dim, rng, "normal")
+    W = rng.standard_normal((dim, dim)) / np.sqrt(dim)
+    TA = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=A, device=DEV)
+    C = st.contract_all_indices_with_matrix(TA, W)
+    ref = po.contract_all_indices_with_matrix(A, rank, dim, W)
+    scale = po.contract_all_indices_with_matrix(absd(A), rank, dim, np.abs(W))
+    assert_classes_close(C, ref, scale, RTOL64)
+    C32 = st.contract_all_indices_with_matrix(TA.astype(np.float32), W.astype(np.float32))
+    assert C32.dtype == np.float32
+    A32 = {q: v.astype(np.float32).astype(np.float64) for q, v in A.items()}
+    ref32 = po.contract_all_indices_with_matrix(A32, rank, dim, W.astype(np.float32).astype(np.float64))
+    assert_classes_close(C32, ref32, scale, RTOL32)
+    # the flat format goes through the same kernels
+    F = st.FlatSymmetricTensor(rank, dim, po.permcls_to_flat(A, rank, dim), device=DEV)
+    CF = st.contract_all_indices_with_matrix(F, W)
+    assert isinstance(CF, st.FlatSymmetricTensor)
+    assert np.allclose(CF.packed.cpu().numpy(), po.permcls_to_flat(ref, rank, dim), rtol=0, atol=1e-9 * max(np.max(v) for v in scale.values()))
+    with pytest.raises(ValueError):
+        st.contract_all_indices_with_matrix(TA, np.ones((dim + 1, dim)))
+
+
+def test_matrix_identity_at_config4_shape():
+    """BASELINE config 4's shape family (rank 6): vec(mat(A, W), y) == vec(A, W y), beyond the dense oracle's reach
+    (rank 6 dim 24: 475,020 packed components, dense would be 1.9e8)."""
+    rank, dim = 6, 24
+    rng = np.random.default_rng(4)
+    t = comb.class_table(rank, dim)
+    buf = torch.rand(t.total, dtype=torch.float64, device=DEV) + 0.5
+    for c, s, o in zip(t.classes, t.sizes, t.offsets):
+        buf[o + s:t.offsets[t.index(c) + 1]] = 0
+    A = st.PermClsTorchSymmetricTensor.from_packed(rank, dim, buf)
+    W = rng.uniform(0.5, 1.5, (dim, dim)) / dim
+    y = rng.uniform(0.5, 1.5, dim)
+    C = st.contract_all_indices_with_matrix(A, W)
+    lhs = float(st.contract_all_indices_with_vector(C, y))
+    rhs = float(st.contract_all_indices_with_vector(A, W @ y))
+    assert abs(lhs - rhs) <= 1e-11 * abs(rhs)
+    # W = identity returns the tensor itself, bit for bit (index maps of the whole chain)
+    I = st.contract_all_indices_with_matrix(A, np.eye(dim))
+    assert torch.equal(I.packed, A.packed)
