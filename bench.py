@@ -193,8 +193,8 @@ def run_gpu(args):
     n_comps = sum(table.sizes)
     total = table.total
     # contiguous 32-aligned slices of the packed coordinate range, balanced by bytes
-    cuts = [min(total, (total * i // world + 31) // 32 * 32) for i in range(world)] + [total]
-    begin, end = cuts[rank], cuts[rank + 1]
+    from symtensor_b200 import sharding
+    begin, end = sharding.my_range(total, rank, world)
 
     # synthetic shard, generated on the device from a per-rank seed (values U[0.5, 1.5)); alignment padding zeroed
     g = torch.Generator(device=dev)
@@ -220,9 +220,8 @@ def run_gpu(args):
     ws = torch.empty(int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
 
     def step():
-        ops.contract_vec_device(desc, x, out, ws, begin, end, packed=shard)
-        if world > 1:
-            dist.all_reduce(out)
+        # local streaming kernel over this rank's slice, then (N > 1) the all-reduce of one fp64
+        sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, out, ws)
 
     def timed(nsteps):
         if world > 1:
@@ -254,8 +253,7 @@ def run_gpu(args):
     strong = None
     if world > 1:
         t200 = comb.class_table(RANK, DIM)
-        c2 = [min(t200.total, (t200.total * i // world + 31) // 32 * 32) for i in range(world)] + [t200.total]
-        b2, e2_ = c2[rank], c2[rank + 1]
+        b2, e2_ = sharding.my_range(t200.total, rank, world)
         sh2 = shard[:e2_ - b2]
         x2 = x[:DIM].contiguous()
         d2 = _Desc()
@@ -263,8 +261,7 @@ def run_gpu(args):
         d2._buf = sh2
 
         def step2():
-            ops.contract_vec_device(d2, x2, out, ws, b2, e2_, packed=sh2)
-            dist.all_reduce(out)
+            sharding.contract_vec_sharded(RANK, DIM, sh2, x2, b2, e2_, out, ws)
         for _ in range(5):
             step2()
         dist.barrier()
@@ -300,6 +297,36 @@ def run_gpu(args):
                "d2h_bytes_per_step": 8, "ms_per_step": dt * 1e3,
                "api": "symtensor_b200.contract_all_indices_with_vector(host-resident PermClsTorchSymmetricTensor, x)"}
         del Ah
+    else:
+        # N > 1: every rank streams ITS slice from pinned host memory, runs the kernel, all-reduces, reads the scalar back
+        sh_host = shard.cpu().pin_memory()
+        sh_dev = torch.empty_like(shard)
+        x_pin = x_host.pin_memory()
+        x_dev = torch.empty_like(x)
+        n_e2e = max(3, min(10, args.steps))
+
+        def e2e_step():
+            sh_dev.copy_(sh_host, non_blocking=True)
+            x_dev.copy_(x_pin, non_blocking=True)
+            sharding.contract_vec_sharded(RANK, dim, sh_dev, x_dev, begin, end, out, ws)
+            return float(out.cpu()[0])
+        for _ in range(2):
+            e2e_step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            r_e2e = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt[0])
+        assert abs(r_e2e - result) <= 1e-12 * abs(result), (r_e2e, result)
+        e2e = {"value": n_comps / dt, "unit": "packed components/s", "h2d_bytes_per_step": int((end - begin) * 8 + dim * 8),
+               "d2h_bytes_per_step": 8, "ms_per_step": dt * 1e3,
+               "api": "symtensor_b200.sharding.contract_vec_sharded(pinned host slice per rank -> device, x) + scalar read-back; "
+                      "bytes are per rank"}
+    if world == 1:
         # ---- CPU baselines on this box's host cores (reported, not a target)
         v, dt_cpu, n_cpu = cpu_reference_arm(1, 0)
         cpu_baseline = {"value": v, "unit": "packed components/s", "cores": os.cpu_count(), "kind": "port",
@@ -337,11 +364,7 @@ def run_gpu(args):
             "clocks": clocks.summary(),
             "gpu_launches": int(launches),
         }
-        if e2e is not None:
-            line["e2e"] = e2e
-        else:
-            line["e2e"] = {"value": None, "unit": "packed components/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                           "note": "end-to-end host-buffer path is measured at N=1"}
+        line["e2e"] = e2e
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
             line["cpu_packed_oracle"] = cpu_packed

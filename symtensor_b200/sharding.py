@@ -1,0 +1,60 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, ``torch.distributed``).
+
+The path shards without any data-path collective:
+
+* ``contract_all_indices_with_vector``: the packed coordinate range is cut into ``world`` contiguous 32-aligned
+  slices balanced by bytes; every rank holds only its slice, ``x`` is replicated, and the ONLY collective is the
+  sum all-reduce of one scalar (NCCL over NVLink on GPUs, gloo in the CPU tests);
+* ``multiply.outer`` / ``tensordot`` / fused outer->vector: the OUTPUT packed range is cut the same way, the (small)
+  operands are replicated, the tensor result stays sharded -- no collective (a scalar all-reduce if a vector
+  contraction follows).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+ALIGN = 32  # ST_CLASS_ALIGN: shard boundaries keep 16-byte vector loads aligned
+
+
+def shard_bounds(total: int, world: int, align: int = ALIGN) -> List[int]:
+    """``world + 1`` cut points of ``[0, total)``: contiguous slices, starts aligned, sizes balanced."""
+    if world < 1:
+        raise ValueError("world must be >= 1")
+    cuts = [min(total, (total * i // world + align - 1) // align * align) for i in range(world)]
+    return cuts + [total]
+
+
+def my_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    cuts = shard_bounds(total, world)
+    return cuts[rank], cuts[rank + 1]
+
+
+def all_reduce_sum(value: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum of the per-rank partial results (in place); a no-op outside a process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(value, op=dist.ReduceOp.SUM, group=group)
+    return value
+
+
+def contract_vec_sharded(rank_: int, dim: int, shard: torch.Tensor, x: torch.Tensor, begin: int, end: int, out: torch.Tensor,
+                         ws: Optional[torch.Tensor] = None, group=None, partial_fn: Optional[Callable] = None) -> torch.Tensor:
+    """Vector contraction of a range-sharded permcls tensor: local streaming kernel over ``[begin, end)`` (``shard``
+    starts at coordinate ``begin``), then the scalar all-reduce.  ``partial_fn(shard, x, begin, end) -> float`` replaces
+    the CUDA launch in the CPU (gloo) tests of the host logic."""
+    if partial_fn is not None:
+        out.fill_(partial_fn(shard, x, begin, end))
+    else:
+        from . import ops
+
+        class _Desc:
+            layout = 0
+        d = _Desc()
+        d.rank, d.dim, d._buf = rank_, dim, shard
+        if ws is None:
+            from ._cabi import lib
+            ws = torch.empty(int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=shard.device)
+        ops.contract_vec_device(d, x, out, ws, begin, end, packed=shard)
+    return all_reduce_sum(out, group)
