@@ -187,6 +187,10 @@ int st_set_vec_variant(int variant);
 /* tuning hooks (process-wide; defaults are the tuned values): "vec_tile_bytes" in [1024, 2^28],
  * "vec_force_tau" in [0, ST_MAX_RANK] (0 = cost model). */
 int st_set_tuning(const char* key, int64_t value);
+/* debug: with st_set_tuning("vec_timeline", 1) the vector-contraction kernel stamps %globaltimer at its phase
+ * boundaries ([cta][16] stamps, then one finish stamp per warp of the grid); this copies the first n stamps of
+ * the last launch to the host.  Profiling aid (tools/vec_timeline.py), not part of the reference-facing surface. */
+int st_debug_vec_timeline(unsigned long long* h_out, int64_t n);
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 int64_t st_launch_count(void);
 

@@ -17,6 +17,8 @@
 //    cross-check used by the tests).
 // Both write one fp64 partial per CTA; vec_finalize_kernel adds them in a fixed order (deterministic).
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
@@ -29,6 +31,11 @@ namespace st {
 
 static const int kMaxCtas = 148 * 8;
 static const int kMaxPartials = 4096;   // fp64 partial sums per launch (one per warp of the grid / per CTA)
+// vec_ring_kernel's workspace: [0] the launch's sum, [1, 1 + warps) per-warp sums (small classes), then one slot per
+// tile of the whole tensor (kTilePartOff + directory index); the tile size grows so that the tiles fit
+static const int kTilePartOff = kMaxPartials + 8;
+static const int64_t kWsSlots = (int64_t)1 << 19;  // 4 MB of fp64 slots
+static const int kMaxCounters = 2 + 256;  // ticket pair + one tile counter per class
 static const int kTailThreads = 512;    // 16 warps per CTA, one CTA per SM (the tail table fills shared memory)
 static int g_batch_slots = 4;           // 16-byte vectors per lane and batch; two batches in flight (tuning knob)
 static const int kBinomSmemMax = 40 * 1024;  // the binomial table is copied to shared memory when it is at most this big
@@ -53,6 +60,22 @@ struct VecArgs {
   int32_t tbl_cap;     // table entries that fit the dynamic shared memory
   int32_t binom_smem;  // entries of the binomial table to copy to shared memory (0: use the global copy)
   int32_t cdesc_smem;  // copy the class descriptors to shared memory
+  double* sum_out;     // vec_ring_kernel: where the launch's sum goes (fp64)
+  int32_t dynamic;     // vec_ring_kernel: deal the tiles of mode-A classes dynamically (per-class counters behind `counter`)
+  unsigned long long* tl;  // debug timeline (nullptr: off): [cta][16] phase stamps, then [warp of the grid] finish stamps
+  int32_t priv_cap;    // vec_ring_kernel: entries of the per-warp xr tables (nwarps * dim, or 0)
+  int32_t ring_slots;  // vec_ring_kernel: slots per warp (R)
+  int32_t ring_elems;  // vec_ring_kernel: components per slot (Bel; Bel * sizeof(T) is a multiple of 16)
+};
+
+// The launch's class records and tile schedule as kernel parameters (rank <= 8: at most 22 classes): computed on
+// the host in microseconds, they would cost every CTA several microseconds of serial 64-bit divisions.
+static const int kMaxSchedCls = 24;
+struct RingSched {
+  int32_t n;  // 0: not provided (too many classes) -- the kernel builds them itself
+  int32_t pad_;
+  ClsInfo cls[kMaxSchedCls];
+  ClsRun run[kMaxSchedCls];
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -131,15 +154,6 @@ __global__ void __launch_bounds__(256) vec_generic_kernel(VecArgs<T> a) {
   block_store_partial(acc, red, a.partials + blockIdx.x);
 }
 
-// Per-class record kept in shared memory (everything the scheduling loop needs, so that it never waits on a
-// global load).
-struct ClsInfo {
-  int64_t offset, size;
-  int64_t tile_base;  // tiles of the classes before this one (whole tensor): index into the tile directory
-  int64_t sbase;      // components of the SMALL classes before this one: index into the per-component directory
-  TailStrategy S;
-};
-
 // GPU index enumerator, bulk form: the values of the component at the start of every tile
 __global__ void vec_dir_kernel(PlanView P, int64_t tile, const int64_t* __restrict__ tile_base, int64_t ntiles, DirEntry* __restrict__ dir) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -163,13 +177,13 @@ __global__ void vec_dir_kernel(PlanView P, int64_t tile, const int64_t* __restri
 
 // CTA-wide build of the shared tail table (xr must be in place and visible); ends with a barrier
 template <typename T>
-__device__ __forceinline__ void build_shared_table(const PlanView& P, const TailStrategy& S, const T* xr, T* tbl) {
+__device__ __forceinline__ void build_shared_table(const PlanView& P, const TailStrategy& S, const T* xr, T* tbl, int nthreads = kTailThreads) {
   int64_t nA, nB;
   table_scratch(P.binom, P.rank, S.Rt, S.tau, &nA, &nB);
   for (int t = 2; t <= S.tau; ++t) {
     const T* src = t == 2 ? xr : table_level_buffer<T>(tbl, S.tbl_n, nA, S.tau, t - 1);
     T* dst = table_level_buffer<T>(tbl, S.tbl_n, nA, S.tau, t);
-    build_table_level<T>(P.binom, P.rank, S.Rt, t, xr, src, dst, threadIdx.x, kTailThreads);
+    build_table_level<T>(P.binom, P.rank, S.Rt, t, xr, src, dst, threadIdx.x, nthreads);
     __syncthreads();
   }
 }
@@ -189,7 +203,7 @@ __device__ __forceinline__ void build_shared_table(const PlanView& P, const Tail
 //                [ClsInfo x ncls][ctrl]
 template <typename T, int U>
 __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   PlanView P = a.P;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int nwarps = kTailThreads / 32;
@@ -487,18 +501,424 @@ __global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// ring kernel (production path): per-warp TMA rings
+// ------------------------------------------------------------------------------------------------------
+// Same schedule and tables as the tail-table walk described above, but the components never pass through
+// registers on their way in: every warp owns a RING of R slots of B bytes in shared memory and keeps it full
+// with 1-D bulk copies (cp.async.bulk, SASS UBLKCP) that complete on an mbarrier per slot.  The copies are
+// issued by the warp itself -- a slot is refilled the moment its sub-chunk has been consumed -- so there is no
+// producer warp, no "empty" barrier, and the bytes in flight per SM (NW x R x B, ~48-96 KB) do not depend on
+// how fast the arithmetic runs: the index arithmetic (odometer steps, table rebuilds, class changes) overlaps
+// with the memory stream instead of stalling it.  A warp's stream is the concatenation of its tiles, so the
+// ring also prefetches ACROSS tiles and classes (the first copies are issued before the tables are built).
+template <typename T>
+__global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant__ VecArgs<T> a, const __grid_constant__ RingSched sched) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  PlanView P = a.P;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nthreads = blockDim.x, nwarps = blockDim.x >> 5;
+  const int G = gridDim.x;
+  const RingLayout L = ring_layout((int)sizeof(T), P.dim, a.tbl_cap, a.priv_cap, a.binom_smem, P.ncls, a.cdesc_smem, nwarps, a.ring_slots, a.ring_elems);
+  T* tbl = reinterpret_cast<T*>(smem_raw);
+  T* priv = reinterpret_cast<T*>(smem_raw + L.priv) + (size_t)warp * P.dim;  // this warp's private xr table (classes with earlier runs)
+  T* xr = reinterpret_cast<T*>(smem_raw + L.xr);
+  T* xs = xr + P.dim;
+  int32_t* blen = reinterpret_cast<int32_t*>(smem_raw + L.blen);
+  int64_t* binom_s = reinterpret_cast<int64_t*>(smem_raw + L.binom);
+  ClsInfo* cls_s = reinterpret_cast<ClsInfo*>(smem_raw + L.cls);
+  ClassDesc* cdesc_s = reinterpret_cast<ClassDesc*>(smem_raw + L.cdesc);
+  WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw + L.ws)[warp];
+  TailCtrl* ctl = reinterpret_cast<TailCtrl*>(smem_raw + L.ctl);
+  ClsRun* run = reinterpret_cast<ClsRun*>(smem_raw + L.run);
+  const int64_t tile = a.tile_elems;
+  auto stamp = [&](int slot) {
+    if (a.tl != nullptr && threadIdx.x == 0) {
+      unsigned long long ts;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+      a.tl[(size_t)blockIdx.x * 16 + slot] = ts;
+    }
+  };
+  stamp(0);
+
+  // ---- 1. class records and the launch's tile schedule (from the kernel parameters when the host could put them
+  // there), barriers; the stream starts at once
+  if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
+  const uint32_t bar0 = smem_u32(smem_raw + L.bar) + 8u * (uint32_t)(warp * a.ring_slots);
+  if (lane == 0) for (int r = 0; r < a.ring_slots; ++r) mbar_init(bar0 + 8u * r, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  if (sched.n > 0) {
+    for (int c = threadIdx.x; c < P.ncls; c += nthreads) {
+      cls_s[c] = sched.cls[c];
+      run[c] = sched.run[c];
+    }
+    __syncthreads();
+  } else {
+    for (int c = threadIdx.x; c < P.ncls; c += nthreads) {
+      cls_s[c].offset = a.P.cls[c].offset;
+      cls_s[c].size = a.P.cls[c].size;
+      cls_s[c].tile_base = a.tile_base ? a.tile_base[c] : 0;
+      cls_s[c].sbase = a.sbase ? a.sbase[c] : 0;
+      cls_s[c].S = a.strat[c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) make_runs(cls_s, P.ncls, a.begin, a.end, tile, nwarps, G, run);
+    __syncthreads();
+  }
+  RingSrc<T> src;
+  src.ring = reinterpret_cast<T*>(smem_raw + L.ring) + (size_t)warp * a.ring_slots * a.ring_elems;
+  src.bar0 = bar0;
+  src.R = a.ring_slots;
+  src.Bel = a.ring_elems;
+  src.lane = lane;
+  src.run = run;
+  src.cls = cls_s;
+  src.A = a.A;
+  src.dir = a.dir;
+  src.ctr = a.dynamic ? a.counter + 2 : nullptr;
+  src.QD = a.ring_slots + 2;
+  src.queue = reinterpret_cast<TileQ*>(smem_raw + L.queue) + (size_t)warp * (a.ring_slots + 2);
+  src.begin = a.begin;
+  src.tile = tile;
+  src.ncls = P.ncls;
+  src.NW = nwarps;
+  src.G = G;
+  src.warp = warp;
+  src.cta = blockIdx.x;
+  // x is requested now and stored after the stream has started (its latency overlaps the first claims and copies)
+  const T x_pre = (int64_t)threadIdx.x < P.dim ? a.x[threadIdx.x] : T(0);
+  stamp(1);
+  src.start();
+  stamp(2);
+
+  // ---- 2. x, binomials, class descriptors
+  if ((int64_t)threadIdx.x < P.dim) xs[threadIdx.x] = x_pre;
+  for (int i = threadIdx.x + nthreads; i < P.dim; i += nthreads) xs[i] = a.x[i];
+  if (a.binom_smem) {
+    for (int i = threadIdx.x; i < a.binom_smem; i += nthreads) binom_s[i] = a.P.binom[i];
+    P.binom = binom_s;
+  }
+  if (a.cdesc_smem) {
+    const int nw32 = (int)(sizeof(ClassDesc) / 4) * P.ncls;
+    for (int i = threadIdx.x; i < nw32; i += nthreads) reinterpret_cast<int32_t*>(cdesc_s)[i] = reinterpret_cast<const int32_t*>(a.P.cls)[i];
+    P.cls = cdesc_s;
+  }
+  __syncthreads();
+  // the first class with a class-wide table (no earlier runs): its table is built now and stays for the whole launch
+  // (the classes with per-warp tables do not touch it), so no warp ever waits for another at a class change
+  for (int ci = 0; ci < P.ncls; ++ci) {
+    const TailStrategy& S = cls_s[ci].S;
+    if (run[ci].mode != 1 || S.tau < 2 || S.nE != 0) continue;
+    if (threadIdx.x == 0) {
+      ctl->wE = unrank_earlier<T>(P, P.cls[ci], 0, xs, ctl->E, ws);
+      ctl->cur_cls = ci;
+      ctl->cur_seg = 0;
+    }
+    for (int uu = threadIdx.x; uu < S.Rt; uu += nthreads) {
+      xr[uu] = xrel_pow<T>(xs, ctl->E, 0, S.mu, uu);
+      blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
+    }
+    __syncthreads();
+    if (!S.direct) {
+      build_shared_table<T>(P, S, xr, tbl, nthreads);
+    } else if (S.k0 < S.Rt - 1) {
+      build_pair_suffix<T>(S.Rt, S.k0, xr, tbl, threadIdx.x, nthreads);
+      __syncthreads();
+    }
+    break;
+  }
+  stamp(3);
+  int priv_cls = -1;  // (class, segment) the private table was built for -- warp-uniform
+  int64_t priv_seg = -1;
+  double priv_wE = 0.0;
+  const int64_t W = (int64_t)G * nwarps;                   // warps of the grid
+  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // this warp
+  double total = 0.0;
+
+  // ---- 3. SMALL classes (tau == 0 in the strategy): one component per thread from the per-component directory
+  {
+    int64_t sm_base = 0;
+    const int64_t nthr = W * 32, tid = gw * 32 + lane;
+    for (int ci = 0; ci < P.ncls; ++ci) {
+      if (cls_s[ci].S.tau != 0) continue;
+      const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
+      const int64_t lo = (a.begin > coff ? a.begin : coff) - coff;
+      const int64_t hi = (a.end < coff + csize ? a.end : coff + csize) - coff;
+      if (lo >= hi) continue;
+      const ClassDesc& C = P.cls[ci];
+      const T* Acls = a.A + (coff - a.begin);
+      const int nvals = C.nvals;
+      const double gamma = (double)C.gamma;
+      for (int64_t p = lo + (tid - sm_base % nthr + nthr) % nthr; p < hi; p += nthr) {
+        const double v = (double)__ldcs(Acls + p);
+        double w = gamma;
+        if (a.sdir != nullptr) {
+          const uint4* q = reinterpret_cast<const uint4*>(a.sdir + (cls_s[ci].sbase + p));
+          const uint4 e0 = __ldg(q), e1 = __ldg(q + 1);
+          const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+          for (int k = 0; k < ST_MAX_RANK; ++k) {
+            if (k < nvals) {
+              const int val = (int)((words[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+              const double xv = (double)xs[val];
+              const int m = C.mult[k];
+              for (int mm = 0; mm < m; ++mm) w *= xv;
+            }
+          }
+        } else {
+          int32_t vals[ST_MAX_RANK];
+          permcls_unrank_vals(P, C, p, vals);
+          for (int k = 0; k < nvals; ++k) {
+            const double xv = (double)xs[vals[k]];
+            for (int m = 0; m < C.mult[k]; ++m) w *= xv;
+          }
+        }
+        total += v * w;
+      }
+      sm_base += hi - lo;
+    }
+  }
+
+  stamp(4);
+  // ---- 4. tail-table classes, in stream order.  Every tile's sum goes to its own slot of the workspace (the deal
+  // may be dynamic: the final reduction must not depend on who walked which tile).
+  double* tile_part = a.partials + kTilePartOff;
+  auto store_tile = [&](int64_t slot, double v) {
+    v = warp_sum(v);
+    if (lane == 0) tile_part[slot] = v;
+  };
+  for (int ci = 0; ci < P.ncls; ++ci) {
+    const ClsRun rr = run[ci];
+    if (!rr.mode) continue;
+    if (ci < 8) stamp(5 + ci);
+    const TailStrategy S = cls_s[ci].S;
+    const ClassDesc& C = P.cls[ci];
+    const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
+    const T* Acls = a.A + (coff - a.begin);
+    const int64_t lo = rr.lo, hi = rr.hi, k0 = rr.k0, k1 = rr.k1, ch0 = rr.ch0, ch1 = rr.ch1;
+    const int64_t dbase = cls_s[ci].tile_base;
+    if (rr.mode == 1) {
+      // ---- mode A: tiles are per warp; tables are per class (no earlier runs) or per warp (tau == 1 / direct)
+      const bool shared_tbl = S.tau >= 2 && S.nE == 0;
+      if (shared_tbl && ctl->cur_cls != ci) {  // CTA-uniform; the first such class was set up in the prologue
+        __syncthreads();  // everybody is done with the previous tables
+        if (threadIdx.x == 0) {
+          ctl->wE = unrank_earlier<T>(P, C, 0, xs, ctl->E, ws);
+          ctl->cur_cls = ci;
+          ctl->cur_seg = 0;
+        }
+        for (int uu = threadIdx.x; uu < S.Rt; uu += nthreads) {
+          xr[uu] = xrel_pow<T>(xs, ctl->E, 0, S.mu, uu);
+          blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
+        }
+        __syncthreads();
+        if (!S.direct) {
+          build_shared_table<T>(P, S, xr, tbl, nthreads);
+        } else if (S.k0 < S.Rt - 1) {
+          build_pair_suffix<T>(S.Rt, S.k0, xr, tbl, threadIdx.x, nthreads);
+          __syncthreads();
+        }
+      }
+      const double wE0 = ctl->wE;
+      int32_t* E = ws.E;
+      int32_t* u0 = ws.u0;
+      while (src.head_is(ci)) {
+        const TileQ& tq = src.pop();
+        const int64_t tk = tq.tk;
+        int64_t w0 = tk * tile;
+        int64_t w1 = w0 + tile;
+        const bool have_dir = a.dir != nullptr && w0 >= lo;  // the tile starts inside the launch range
+        if (w0 < lo) w0 = lo;
+        if (w1 > hi) w1 = hi;
+        const int64_t tw0 = w0;
+        src.open_tile(Acls + w0, (int)(w1 - w0));
+        const DirEntry& de = tq.de;
+        double tsum = 0.0;
+        if (shared_tbl) {
+          if (have_dir) {  // single-run class: the entry is the combination itself
+            __syncwarp();
+            if (lane < S.gt) ws.u[lane] = de.v[lane];
+            __syncwarp();
+          }
+          tsum = walk_tile_any<T>(P, S, tbl, xr, blen, wE0, w0, (int)(w1 - w0), 0, lane, have_dir ? ws.u : nullptr, src, ws);
+        } else {
+          const bool gap = S.direct && S.nE != 0 && S.mu == 1;
+          bool first = true;
+          while (w0 < w1) {  // private tables: segment by segment
+            const int64_t sidx = S.nE ? w0 / S.seg : 0;
+            const int64_t sbase = sidx * S.seg;
+            const int64_t q1 = (S.seg < w1 - sbase) ? S.seg : w1 - sbase;
+            const bool from_dir = first && have_dir;
+            if (from_dir) {
+              const double wE = dir_decode<T>(C, S, de, xs, E, u0);
+              if (priv_cls != ci || priv_seg != sidx) priv_wE = wE;
+            } else if (w0 == sbase) {
+              for (int i = 0; i < S.gt; ++i) u0[i] = i;  // a segment starts with the first combination
+            }
+            if (priv_cls != ci || priv_seg != sidx) {
+              if (!from_dir) priv_wE = unrank_earlier<T>(P, C, sidx, xs, E, ws);
+              __syncwarp();
+              if (!gap) {  // (gap classes relabel x on the fly from ws.E)
+                for (int uu = lane; uu < S.Rt; uu += 32) priv[uu] = xrel_pow<T>(xs, E, S.nE, S.mu, uu);
+                __syncwarp();
+              }
+              priv_cls = ci;
+              priv_seg = sidx;
+            }
+            tsum += walk_tile_any<T>(P, S, gap ? xs : priv, gap ? xs : priv, nullptr, priv_wE, w0 - sbase, (int)(sbase + q1 - w0), (int)(w0 - tw0), lane,
+                                     (from_dir || w0 == sbase) ? u0 : nullptr, src, ws);
+            w0 = sbase + q1;
+            first = false;
+          }
+        }
+        src.close_tile();
+        store_tile(dbase + tk, tsum);
+      }
+    } else {
+      // ---- mode B: chunks of nwarps tiles per CTA (static deal); the CTA rebuilds T once per segment
+      const int64_t chunk = tile * nwarps;
+      for (int64_t jc = src.jc0(ci); ch0 + jc < ch1; jc += G) {
+        const int64_t tk = (ch0 + jc) * nwarps + warp;  // this warp's tile of the chunk
+        const bool exists = tk >= k0 && tk < k1;
+        int64_t tw0 = tk * tile, tw1 = tw0 + tile;
+        if (tw0 < lo) tw0 = lo;
+        if (tw1 > hi) tw1 = hi;
+        const TileQ* tq = nullptr;
+        if (exists) {
+          tq = &src.pop();  // the producer cursor queued exactly this tile
+          src.open_tile(Acls + tw0, (int)(tw1 - tw0));
+        }
+        double tsum = 0.0;
+        int64_t pos = (ch0 + jc) * chunk;
+        int64_t pend = pos + chunk;
+        if (pos < lo) pos = lo;
+        if (pend > hi) pend = hi;
+        while (pos < pend) {
+          const int64_t sidx = pos / S.seg;
+          const int64_t sbase = sidx * S.seg;
+          const int64_t q0 = pos - sbase;
+          const int64_t q1 = (S.seg < pend - sbase) ? S.seg : pend - sbase;
+          if (ctl->cur_cls != ci || ctl->cur_seg != sidx) {  // CTA-uniform
+            __syncthreads();  // everybody is done with the previous tables
+            if (threadIdx.x == 0) {
+              const int64_t tk0 = (sbase + tile - 1) / tile;
+              if (a.dir != nullptr && tk0 * tile < sbase + S.seg && tk0 * tile < csize) {
+                ws.de = a.dir[dbase + tk0];
+                ctl->wE = dir_decode<T>(C, S, ws.de, xs, ctl->E, ws.u0);
+              } else {
+                ctl->wE = unrank_earlier<T>(P, C, sidx, xs, ctl->E, ws);
+              }
+              ctl->cur_cls = ci;
+              ctl->cur_seg = sidx;
+            }
+            __syncthreads();
+            for (int uu = threadIdx.x; uu < S.Rt; uu += nthreads) {
+              xr[uu] = xrel_pow<T>(xs, ctl->E, S.nE, S.mu, uu);
+              blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
+            }
+            __syncthreads();
+            build_shared_table<T>(P, S, xr, tbl, nthreads);
+          }
+          if (exists) {
+            int64_t w0 = tk * tile - sbase, w1 = w0 + tile;
+            const bool at_tile = w0 >= q0;
+            if (w0 < q0) w0 = q0;
+            if (w1 > q1) w1 = q1;
+            if (w0 < w1) {
+              int32_t* u0 = ws.u0;
+              const int32_t* ui = nullptr;
+              if (w0 == 0) {
+                for (int i = 0; i < S.gt; ++i) u0[i] = i;
+                ui = u0;
+              } else if (at_tile && a.dir != nullptr) {
+                dir_decode<T>(C, S, tq->de, xs, ws.E, u0);
+                ui = u0;
+              }
+              tsum += walk_tile_any<T>(P, S, tbl, xr, blen, ctl->wE, w0, (int)(w1 - w0), (int)(sbase + w0 - tw0), lane, ui, src, ws);
+            }
+          }
+          pos = sbase + q1;
+        }
+        if (exists) {
+          src.close_tile();
+          store_tile(dbase + tk, tsum);
+        }
+      }
+    }
+  }
+
+  if (a.tl != nullptr && lane == 0) {
+    unsigned long long ts;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+    a.tl[(size_t)gridDim.x * 16 + (size_t)blockIdx.x * nwarps + warp] = ts;
+  }
+  // one partial per warp of the grid, added in index order by the last CTA to finish (deterministic)
+  total = warp_sum(total);
+  if (lane == 0) a.partials[1 + gw] = total;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(a.counter, 1ULL);
+    const bool last = ticket == (unsigned long long)(G - 1);
+    if (last) {
+      a.counter[0] = 0ULL;
+      __threadfence();
+    }
+    ctl->last = last ? 1 : 0;
+  }
+  __syncthreads();
+  if (ctl->last) {
+    // the last CTA adds the per-warp sums (small classes) and the per-tile sums in index order, and resets the counters
+    double s = 0.0;
+    auto add_slots = [&](const double* p, int64_t i0, int64_t i1) {  // fixed thread -> slot map, 8 loads in flight
+      int64_t i = i0 + threadIdx.x;
+      for (; i + 7 * (int64_t)nthreads < i1; i += 8 * (int64_t)nthreads) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldcg(p + i + j * (int64_t)nthreads);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[j];
+      }
+      for (; i < i1; i += nthreads) s += __ldcg(p + i);
+    };
+    add_slots(a.partials + 1, 0, W);
+    for (int ci = 0; ci < P.ncls; ++ci) {
+      if (!run[ci].mode) continue;
+      add_slots(tile_part + cls_s[ci].tile_base, run[ci].k0, run[ci].k1);
+    }
+    for (int c = threadIdx.x; c < P.ncls; c += nthreads) a.counter[2 + c] = 0ULL;
+    s = warp_sum(s);
+    if (lane == 0) ctl->red[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+      double t = lane < nwarps ? ctl->red[lane] : 0.0;
+      t = warp_sum(t);
+      if (lane == 0) {
+        *a.sum_out = t;
+        if (a.out != nullptr) *a.out = (T)t;
+      }
+    }
+  }
+  stamp(15);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
 static const size_t kClsInfoBytes = sizeof(ClsInfo);
+static const size_t kRingSmemBudget = 227 * 1024 - 64;  // dynamic shared memory of vec_ring_kernel
 int g_variant = 0;
 static int g_use_dir = 1;  // tuning knob "vec_use_dir": 0 unranks every tile start in the kernel
 int g_force_tau = 0;  // test hook: force the tail length (0 = cost model)
+unsigned long long* g_timeline = nullptr;  // debug: device buffer of kTimelineSlots stamps (st_set_tuning vec_timeline 1)
+static const size_t kTimelineSlots = 148 * 16 + 4096;
+int g_ring_direct = 1;                 // ring kernel: allow the table-free pair walk (2: with vec_force_tau 2, force it)
+int64_t g_ring_table_max = 96 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
 int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
 struct StratKey {
-  int dev, rank, esize;
+  int dev, rank, esize, ring;
   int64_t dim, tile;
-  bool operator<(const StratKey& o) const { return std::tie(dev, rank, esize, dim, tile) < std::tie(o.dev, o.rank, o.esize, o.dim, o.tile); }
+  bool operator<(const StratKey& o) const { return std::tie(dev, rank, esize, ring, dim, tile) < std::tie(o.dev, o.rank, o.esize, o.ring, o.dim, o.tile); }
 };
 struct StratEntry {
   TailStrategy* d_strat;
@@ -511,8 +931,21 @@ struct StratEntry {
   int32_t binom_smem;
   size_t smem_bytes;
   bool supported;
+  // ring kernel geometry
+  int32_t nwarps, ring_slots, ring_elems, priv_cap;
+  int64_t tile_elems;
+  // host copies for the launch-time schedule
+  std::vector<TailStrategy> h_strat;
+  std::vector<int64_t> h_tile_base, h_sbase;
 };
 static std::mutex g_smu;
+// ring kernel tuning knobs (st_set_tuning)
+static int g_ring_dynamic = 1;         // deal the tiles of mode-A classes dynamically
+static int g_ring_warps = 16;          // consumer warps per CTA
+static int g_ring_slots = 3;           // ring slots per warp
+static int g_ring_bytes = 2048;        // preferred bytes per slot (shrunk to 1536 / 1024 when the table needs the room)
+static int g_ring_bytes_max = 4096;    // slots grow up to this when shared memory is left over
+static int g_ring_tile_bytes = 32768;    // bytes per tile (directory granularity; rounded to whole slots)
 static std::map<StratKey, StratEntry> g_strats;
 
 static double dbinom(const HostPlan* hp, int64_t n, int k) {
@@ -526,22 +959,27 @@ static double dbinom(const HostPlan* hp, int64_t n, int k) {
 //   table builds   ~0.5 per entry, amortised over a segment (multi-run classes) or over a CTA's share of the
 //                  class (single-run classes, table built once per CTA)
 // Pure host function (also used by the CPU emulation harness in tests/emu).
+// `reserve` > 0 selects the ring kernel's model: that many bytes are kept for the rings (the optional shared-memory
+// copies of the binomial table and the class descriptors are then decided by the caller from what is left) and
+// a block costs `block_cost` warp-instructions.
 bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, std::vector<TailStrategy>& st, int32_t* tbl_cap,
-                           int32_t* binom_smem, int32_t* cdesc_smem, size_t* smem_bytes) {
+                           int32_t* binom_smem, int32_t* cdesc_smem, size_t* smem_bytes, size_t reserve, double block_cost) {
   const int rank = hp->rank;
   const int64_t dim = hp->dim;
-  const size_t smem_budget = 224 * 1024;
+  const size_t smem_budget = reserve ? kRingSmemBudget : 224 * 1024;
   const size_t binom_bytes = (size_t)hp->binom_rows * (rank + 1) * sizeof(int64_t);
-  *binom_smem = binom_bytes <= (size_t)kBinomSmemMax ? (int32_t)(hp->binom_rows * (rank + 1)) : 0;
-  *cdesc_smem = (size_t)hp->ncls * sizeof(ClassDesc) <= 24 * 1024 ? 1 : 0;
+  *binom_smem = (!reserve && binom_bytes <= (size_t)kBinomSmemMax) ? (int32_t)(hp->binom_rows * (rank + 1)) : 0;
+  *cdesc_smem = (!reserve && (size_t)hp->ncls * sizeof(ClassDesc) <= 24 * 1024) ? 1 : 0;
   // everything but the table: xr, xs, blen, the binomial table, class records, per-warp scratch, control block, slack
   const size_t fixed = (size_t)2 * dim * esize + (size_t)dim * 4 + (size_t)*binom_smem * sizeof(int64_t) + (size_t)hp->ncls * kClsInfoBytes +
-                       (*cdesc_smem ? (size_t)hp->ncls * sizeof(ClassDesc) : 0) + (size_t)nwarps * sizeof(WarpScratch) + sizeof(TailCtrl) + 128;
+                       (*cdesc_smem ? (size_t)hp->ncls * sizeof(ClassDesc) : 0) + (size_t)nwarps * sizeof(WarpScratch) + sizeof(TailCtrl) + 128 +
+                       reserve;
   if (fixed + 32 * esize > smem_budget) return false;  // x itself does not fit shared memory
   const int64_t cap = (int64_t)((smem_budget - fixed) / esize);
-  if (cap < (int64_t)nwarps * dim) return false;  // the per-warp private tables (which alias the table) must fit
+  if (!reserve && cap < (int64_t)nwarps * dim) return false;  // vec_tail_kernel: the per-warp private tables alias the table
+  if (cap < 32) return false;
   st.assign(hp->ncls, TailStrategy());
-  int64_t tbl_max = std::max<int64_t>(32, (int64_t)nwarps * dim);
+  int64_t tbl_max = reserve ? 32 : std::max<int64_t>(32, (int64_t)nwarps * dim);
   for (int c = 0; c < hp->ncls; ++c) {
     const ClassDesc& C = hp->h_cls[c];
     TailStrategy& S = st[c];
@@ -556,32 +994,60 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, std::vecto
     S.seg = C.radix[t];
     double best = 1e300;
     int best_tau = 1;
+    bool best_direct = false;
+    // ring kernel: a table may take at most g_ring_table_max bytes of shared memory (the rings need the rest);
+    // beyond that the pair weights are computed on the fly (tau == 2, no table)
+    const bool can_direct = reserve > 0 && g_ring_direct && S.gt >= 2 && S.Rt <= 40000;
     for (int tau = 1; tau <= S.gt; ++tau) {
       int64_t nA = 0, nB = 0;
       table_scratch(hp->h_binom, rank, S.Rt, tau, &nA, &nB);
       const double tn = dbinom(hp, S.Rt, tau);
       if (tau > 1 && tn + (double)nA + (double)nB > (double)cap) break;
+      if (tau > 1 && can_direct && (tn + (double)nA + (double)nB) * esize > (double)g_ring_table_max) break;
       const double nheads = dbinom(hp, S.Rt - tau, S.gt - tau);
       const double avg_block = (double)S.seg / (nheads > 0 ? nheads : 1);
       double cost;
       if (tau == 1) {
-        cost = 0.1 + 150.0 / avg_block + (S.nE ? (400.0 + 0.5 * S.Rt) / (double)S.seg : 0.0);
+        cost = 0.1 + block_cost / avg_block + (S.nE ? (400.0 + 0.5 * S.Rt) / (double)S.seg : 0.0);
       } else {
         // level-by-level build: ~0.3 warp-instructions per entry plus the barriers, once per class (single-run
         // classes) or per segment and CTA (mode B: a chunk sees about two segments)
         const double amort = (S.nE == 0) ? std::max(1.0, (double)C.size / 148.0) : 0.5 * (double)S.seg;
-        cost = 0.1 + 150.0 / avg_block + (0.3 * (tn + (double)nA + (double)nB) + 3000.0) / amort;
+        cost = 0.1 + block_cost / avg_block + (0.3 * (tn + (double)nA + (double)nB) + 3000.0) / amort;
       }
       if (cost < best) { best = cost; best_tau = tau; }
     }
-    if (g_force_tau > 0) best_tau = std::min(g_force_tau, (int)S.gt);
+    if (can_direct) {
+      const double nheads = dbinom(hp, S.Rt - 2, S.gt - 2);
+      const double avg_block = (double)S.seg / (nheads > 0 ? nheads : 1);
+      const double cost = 0.4 + block_cost / avg_block + (S.nE ? (400.0 + 0.5 * S.Rt) / (double)S.seg : 0.0);
+      if (cost < best) { best = cost; best_tau = 2; best_direct = true; }
+    }
+    if (g_force_tau > 0) { best_tau = std::min(g_force_tau, (int)S.gt); best_direct = false; }
+    if (g_force_tau == 2 && g_ring_direct == 2 && can_direct) best_direct = true;  // test hook: force the direct walk
     int64_t nA = 0, nB = 0;
     table_scratch(hp->h_binom, rank, S.Rt, best_tau, &nA, &nB);
-    if (best_tau > 1 && dbinom(hp, S.Rt, best_tau) + (double)nA + (double)nB > (double)cap) { best_tau = 1; nA = nB = 0; }
+    if (best_direct) nA = nB = 0;
+    if (!best_direct && best_tau > 1 && dbinom(hp, S.Rt, best_tau) + (double)nA + (double)nB > (double)cap) { best_tau = 1; nA = nB = 0; }
     S.tau = best_tau;
+    S.direct = best_direct ? 1 : 0;
+    S.k0 = 0;
+    int64_t direct_tbl = 0;
+    if (best_direct) {
+      // suffix table: as many rows as the table budget (and the shared memory left) hold; classes with earlier
+      // runs have per-warp xr tables and no pair table at all
+      S.k0 = S.Rt;
+      if (S.nE == 0) {
+        const int64_t budget = std::min<int64_t>(g_ring_table_max / esize, cap);
+        int64_t m = 1;
+        while (m < S.Rt && (m + 1) * m / 2 <= budget) ++m;   // C(m, 2) entries for the last m values
+        if (m >= 2) { S.k0 = (int32_t)std::max<int64_t>(0, S.Rt - m); direct_tbl = (int64_t)(S.Rt - S.k0) * (S.Rt - S.k0 - 1) / 2; }
+      }
+    }
     S.hn = S.gt - S.tau;
     S.tbl_n = hp->h_binom[(int64_t)S.Rt * (rank + 1) + S.tau];
-    if (S.tau > 1) tbl_max = std::max(tbl_max, S.tbl_n + nA + nB);
+    if (S.tau > 1 && !S.direct) tbl_max = std::max(tbl_max, S.tbl_n + nA + nB);
+    if (S.direct) tbl_max = std::max(tbl_max, direct_tbl);
   }
   *tbl_cap = (int32_t)((tbl_max + 31) / 32 * 32);
   {
@@ -600,14 +1066,71 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, std::vecto
 
 static const int64_t kMaxDirTiles = (int64_t)1 << 23;  // 256 MB of directory at most
 
-static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, StratEntry* out) {
+// ring kernel: strategy + ring geometry + tile size.  The slot size is the preferred one unless a class would lose
+// its best tail length to the rings' shared memory: then smaller slots are tried (small copies cost bandwidth,
+// a shorter tail costs much more).
+static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<TailStrategy>& st, StratEntry& e) {
+  const int NW = g_ring_warps, R = g_ring_slots;
+  // shared memory kept away from the tables: the rings at their preferred slot size, their control structures and --
+  // only when some class needs them -- the per-warp relabelled copies of x
+  const size_t ctrl = (size_t)NW * R * 8 + (size_t)NW * (R + 2) * sizeof(TileQ) + (size_t)hp->ncls * sizeof(ClsRun) + 512;
+  const size_t priv_bytes = (size_t)NW * hp->dim * esize + 16;
+  auto needs_priv = [&](const std::vector<TailStrategy>& s) {
+    for (int c = 0; c < hp->ncls; ++c) {
+      if (s[c].tau == 0) continue;
+      if (s[c].tau == 1) return true;                                  // tau == 1 always walks per-warp tables
+      if (s[c].nE != 0 && s[c].direct && s[c].mu != 1) return true;  // (mu == 1: relabelled on the fly)
+    }
+    return false;
+  };
+  int32_t b0 = 0, c0 = 0;
+  size_t sm0 = 0;
+  bool ok = false;
+  for (int bytes : {g_ring_bytes, 1536, 1024, 512}) {
+    if (bytes > g_ring_bytes) continue;
+    const size_t reserve = (size_t)NW * R * bytes + ctrl;
+    ok = compute_tail_strategy(hp, esize, NW, st, &e.tbl_cap, &b0, &c0, &sm0, reserve, 40.0);
+    if (ok && needs_priv(st)) ok = compute_tail_strategy(hp, esize, NW, st, &e.tbl_cap, &b0, &c0, &sm0, reserve + priv_bytes, 40.0);
+    if (ok) break;
+  }
+  if (!ok) return false;
+  e.nwarps = NW;
+  e.ring_slots = R;
+  e.binom_smem = 0;
+  e.cdesc_smem = 0;
+  e.priv_cap = needs_priv(st) ? (int32_t)(NW * hp->dim) : 0;
+  const size_t base = ring_layout(esize, hp->dim, e.tbl_cap, e.priv_cap, 0, hp->ncls, 0, NW, R, 0).total;
+  if (base + (size_t)NW * R * 512 > kRingSmemBudget) return false;
+  size_t left = kRingSmemBudget - base;
+  auto slot_bytes = [&](size_t avail, int cap_bytes) { return (int)std::min<size_t>((size_t)cap_bytes, avail / ((size_t)NW * R) / 512 * 512); };
+  int bytes = slot_bytes(left, g_ring_bytes);
+  left -= (size_t)NW * R * bytes;
+  const size_t cdesc_bytes = (size_t)hp->ncls * sizeof(ClassDesc) + 32;
+  if (cdesc_bytes <= left && cdesc_bytes <= 24 * 1024) { e.cdesc_smem = 1; left -= cdesc_bytes; }
+  const size_t binom_bytes = (size_t)hp->binom_rows * (hp->rank + 1) * sizeof(int64_t);
+  if (binom_bytes <= left && binom_bytes <= (size_t)kBinomSmemMax) { e.binom_smem = (int32_t)(hp->binom_rows * (hp->rank + 1)); left -= binom_bytes; }
+  if (g_ring_bytes_max > bytes) bytes += slot_bytes(left, g_ring_bytes_max - bytes);
+  e.ring_elems = bytes / esize;
+  int64_t nsub = std::max(1, g_ring_tile_bytes / bytes);
+  {
+    // one workspace slot per tile of the whole tensor: grow the tiles until they fit
+    auto total_tiles = [&](int64_t te) { int64_t n = 0; for (int c = 0; c < hp->ncls; ++c) n += (hp->h_cls[c].size + te - 1) / te; return n; };
+    while (total_tiles(nsub * e.ring_elems) > kWsSlots - kTilePartOff) nsub *= 2;
+  }
+  e.tile_elems = nsub * e.ring_elems;
+  e.smem_bytes = ring_layout(esize, hp->dim, e.tbl_cap, e.priv_cap, e.binom_smem, hp->ncls, e.cdesc_smem, NW, R, e.ring_elems).total;
+  return e.smem_bytes <= kRingSmemBudget;
+}
+
+// `ring`: strategy of vec_ring_kernel (the tile size is part of it: `tile` is ignored); else of vec_tail_kernel
+static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, bool ring, StratEntry* out) {
   const HostPlan* hp = get_host_plan(rank, dim);
   if (!hp) return ST_ERR_INVALID;
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_smu);
-  StratKey key{dev, rank, esize, dim, tile};
+  StratKey key{dev, rank, esize, ring ? 1 : 0, dim, ring ? 0 : tile};
   auto it = g_strats.find(key);
   if (it != g_strats.end()) { *out = it->second; return ST_OK; }
   StratEntry e;
@@ -620,8 +1143,25 @@ static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, StratEnt
   e.tbl_cap = 32;
   e.binom_smem = 0;
   e.smem_bytes = 0;
+  e.nwarps = kTailThreads / 32;
+  e.ring_slots = 0;
+  e.ring_elems = 0;
+  e.priv_cap = 0;
+  e.tile_elems = tile;
   std::vector<TailStrategy> st;
-  e.supported = compute_tail_strategy(hp, esize, kTailThreads / 32, st, &e.tbl_cap, &e.binom_smem, &e.cdesc_smem, &e.smem_bytes);
+  if (ring) {
+    e.supported = compute_ring_strategy(hp, esize, st, e);
+    tile = e.tile_elems;
+    if (getenv("ST_VEC_DEBUG")) {
+      fprintf(stderr, "[st] ring strategy rank %d dim %lld esize %d: supported %d warps %d slots %d slot_bytes %d tile_elems %lld tbl_cap %d binom_smem %d cdesc_smem %d smem %zu tau:",
+              rank, (long long)dim, esize, (int)e.supported, e.nwarps, e.ring_slots, e.ring_elems * esize, (long long)e.tile_elems, e.tbl_cap, e.binom_smem,
+              e.cdesc_smem, e.smem_bytes);
+      for (size_t c = 0; c < st.size(); ++c) { fprintf(stderr, " %d", st[c].tau); if (st[c].direct) fprintf(stderr, "d(k0=%d)", st[c].k0); }
+      fprintf(stderr, "\n");
+    }
+  } else {
+    e.supported = compute_tail_strategy(hp, esize, kTailThreads / 32, st, &e.tbl_cap, &e.binom_smem, &e.cdesc_smem, &e.smem_bytes, 0, 150.0);
+  }
   if (e.supported) {
     rc = check_cuda(cudaMalloc(&e.d_strat, sizeof(TailStrategy) * hp->ncls), "cudaMalloc(strategy)");
     if (rc) return rc;
@@ -631,6 +1171,8 @@ static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, StratEnt
     std::vector<int64_t> tb(hp->ncls + 1, 0);
     for (int c = 0; c < hp->ncls; ++c) tb[c + 1] = tb[c] + (hp->h_cls[c].size + tile - 1) / tile;
     const int64_t ntiles = tb[hp->ncls];
+    e.h_strat = st;
+    e.h_tile_base = tb;
     if (g_use_dir && dim <= 65535 && ntiles > 0 && ntiles <= kMaxDirTiles) {
       PlanView P;
       rc = get_device_plan(rank, dim, &P);
@@ -647,6 +1189,7 @@ static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, StratEnt
       std::vector<int64_t> sb(hp->ncls + 1, 0);
       for (int c = 0; c < hp->ncls; ++c) sb[c + 1] = sb[c] + (st[c].tau == 0 ? hp->h_cls[c].size : 0);
       const int64_t nsmall = sb[hp->ncls];
+      e.h_sbase = sb;
       if (nsmall > 0) {
         rc = check_cuda(cudaMalloc(&e.d_sbase, sizeof(int64_t) * (hp->ncls + 1)), "cudaMalloc(sbase)");
         if (rc) return rc;
@@ -689,9 +1232,9 @@ static int get_counter(cudaStream_t stream, unsigned long long** out) {
   auto it = g_counters.find(key);
   if (it != g_counters.end()) { *out = it->second; return ST_OK; }
   unsigned long long* d = nullptr;
-  rc = check_cuda(cudaMalloc(&d, 2 * sizeof(unsigned long long)), "cudaMalloc(counter)");
+  rc = check_cuda(cudaMalloc(&d, kMaxCounters * sizeof(unsigned long long)), "cudaMalloc(counter)");
   if (rc) return rc;
-  rc = check_cuda(cudaMemset(d, 0, 2 * sizeof(unsigned long long)), "cudaMemset(counter)");
+  rc = check_cuda(cudaMemset(d, 0, kMaxCounters * sizeof(unsigned long long)), "cudaMemset(counter)");
   if (rc) return rc;
   g_counters[key] = d;
   *out = d;
@@ -724,6 +1267,44 @@ static int launch_tail_u(VecArgs<T>& a, const StratEntry& se, int64_t len, int* 
 }
 
 template <typename T>
+static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, int64_t len, int* grid_out, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int rc = check_cuda(cudaFuncSetAttribute(vec_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute");
+    if (rc) return rc;
+    attr_set = true;
+  }
+  // One resident CTA per SM; tiles are dealt to the warps by the kernel (see RingSrc).
+  const int nwarps = se.nwarps;
+  const int64_t ntiles = (len + se.tile_elems - 1) / se.tile_elems;
+  int64_t grid = std::min<int64_t>((int64_t)sm_count(), kMaxCtas);
+  grid = std::min<int64_t>(grid, (kMaxPartials - 1) / nwarps);
+  grid = std::max<int64_t>(1, std::min<int64_t>(grid, (ntiles + nwarps - 1) / nwarps));
+  {
+    int rc = get_counter(stream, &a.counter);
+    if (rc) return rc;
+  }
+  a.dynamic = (g_ring_dynamic && hp->ncls <= kMaxCounters - 2) ? 1 : 0;
+  RingSched sched;
+  sched.n = 0;
+  sched.pad_ = 0;
+  if (hp->ncls <= kMaxSchedCls) {
+    for (int c = 0; c < hp->ncls; ++c) {
+      sched.cls[c].offset = hp->h_cls[c].offset;
+      sched.cls[c].size = hp->h_cls[c].size;
+      sched.cls[c].tile_base = se.h_tile_base.empty() ? 0 : se.h_tile_base[c];
+      sched.cls[c].sbase = se.h_sbase.empty() ? 0 : se.h_sbase[c];
+      sched.cls[c].S = se.h_strat[c];
+    }
+    make_runs(sched.cls, hp->ncls, a.begin, a.end, se.tile_elems, nwarps, (int)grid, sched.run);
+    sched.n = hp->ncls;
+  }
+  vec_ring_kernel<T><<<(int)grid, nwarps * 32, se.smem_bytes, stream>>>(a, sched);
+  *grid_out = 1;  // the kernel leaves the launch's sum in partials[0]
+  return ST_OK;
+}
+
+template <typename T>
 static int launch_tail(VecArgs<T>& a, const StratEntry& se, int64_t len, int* grid_out, cudaStream_t stream) {
   switch (g_batch_slots) {
     case 2: return launch_tail_u<T, 2>(a, se, len, grid_out, stream);
@@ -735,7 +1316,8 @@ static int launch_tail(VecArgs<T>& a, const StratEntry& se, int64_t len, int* gr
 // tail kernel also reduces them (`*fused` = true); otherwise (or on the generic path) the caller finalizes.
 template <typename T>
 static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, int64_t begin, int64_t end, const T* d_x,
-                        double* partials, int* grid_out, T* d_out, bool* fused, cudaStream_t stream) {
+                        double* partials, int* grid_out, T* d_out, bool* fused, cudaStream_t stream, double* ring_ws = nullptr) {
+  // `ring_ws`: separate workspace (kWsSlots) for vec_ring_kernel, whose only output is then partials[0]
   if (fused) *fused = false;
   if (layout != ST_LAYOUT_PERMCLS && layout != ST_LAYOUT_FLAT) { set_error("unknown layout %d", layout); return ST_ERR_INVALID; }
   PlanView P;
@@ -764,14 +1346,24 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   a.tbl_cap = 0;
   a.binom_smem = 0;
   a.counter = nullptr;
+  a.ring_slots = 0;
+  a.ring_elems = 0;
+  a.priv_cap = 0;
+  a.dynamic = 0;
+  a.sum_out = partials;
+  a.tl = g_timeline;
   *grid_out = 1;
   if (end == begin) return check_cuda(cudaMemsetAsync(partials, 0, sizeof(double), stream), "cudaMemsetAsync");
   StratEntry se;
   se.supported = false;
   if (layout == ST_LAYOUT_PERMCLS && rank > 0 && g_variant != 1) {
     a.tile_elems = std::max<int64_t>(ST_CLASS_ALIGN, (g_tile_bytes / (int64_t)sizeof(T)) / ST_CLASS_ALIGN * ST_CLASS_ALIGN);
-    rc = get_strategy(rank, dim, (int)sizeof(T), a.tile_elems, &se);
+    rc = get_strategy(rank, dim, (int)sizeof(T), a.tile_elems, g_variant != 3, &se);
     if (rc) return rc;
+    if (g_variant != 3 && !se.supported) {  // no room for the rings: the register-streamed tail kernel may still fit
+      rc = get_strategy(rank, dim, (int)sizeof(T), a.tile_elems, false, &se);
+      if (rc) return rc;
+    }
     if (!se.supported && g_variant == 2) { set_error("tail-table kernel unavailable for dim %lld", (long long)dim); return ST_ERR_UNSUPPORTED; }
   }
   if (se.supported) {
@@ -784,7 +1376,16 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
     a.sbase = se.d_sbase;
     a.cdesc_smem = se.cdesc_smem;
     a.out = d_out;
-    rc = launch_tail<T>(a, se, end - begin, grid_out, stream);
+    a.ring_slots = se.ring_slots;
+    a.ring_elems = se.ring_elems;
+    a.priv_cap = se.priv_cap;
+    if (se.ring_slots > 0) {
+      a.tile_elems = se.tile_elems;
+      if (ring_ws) a.partials = ring_ws;
+      rc = launch_ring<T>(a, se, get_host_plan(rank, dim), end - begin, grid_out, stream);
+    } else {
+      rc = launch_tail<T>(a, se, end - begin, grid_out, stream);
+    }
     if (rc) return rc;
     count_launch();
     if (fused) *fused = d_out != nullptr;
@@ -886,9 +1487,10 @@ static int contract_vec_host(int layout, int rank, int64_t dim, const T* h_packe
   const int64_t chunk_elems = (int64_t)(kChunkBytes / sizeof(T)) / 32768 * 32768;
   const int64_t n_chunks = std::max<int64_t>(1, (total + chunk_elems - 1) / chunk_elems);
   HostStage* st = nullptr;
-  int rc = get_stage((size_t)dim * sizeof(T), (size_t)n_chunks * kMaxPartials, &st);
+  int rc = get_stage((size_t)dim * sizeof(T), (size_t)kWsSlots + (size_t)n_chunks * kMaxPartials, &st);
   if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(st->d_ws, 0, (size_t)n_chunks * kMaxPartials * sizeof(double), st->s_comp), "cudaMemsetAsync(ws)");
+  double* sums = st->d_ws + kWsSlots;  // per chunk: kMaxPartials slots (the ring kernel uses the first one only)
+  rc = check_cuda(cudaMemsetAsync(sums, 0, (size_t)n_chunks * kMaxPartials * sizeof(double), st->s_comp), "cudaMemsetAsync(ws)");
   if (rc) return rc;
   if (dim > 0) {
     rc = check_cuda(cudaMemcpyAsync(st->d_x, h_x, (size_t)dim * sizeof(T), cudaMemcpyHostToDevice, st->s_comp), "cudaMemcpyAsync(x)");
@@ -909,12 +1511,12 @@ static int contract_vec_host(int layout, int rank, int64_t dim, const T* h_packe
     if (rc) return rc;
     int grid = 1;
     rc = vec_partials<T>(layout, rank, dim, reinterpret_cast<const T*>(st->d_buf[b]), begin, end, reinterpret_cast<const T*>(st->d_x),
-                         st->d_ws + c * kMaxPartials, &grid, nullptr, nullptr, st->s_comp);
+                         sums + c * kMaxPartials, &grid, nullptr, nullptr, st->s_comp, st->d_ws);
     if (rc) return rc;
     rc = check_cuda(cudaEventRecord(st->computed[b], st->s_comp), "cudaEventRecord");
     if (rc) return rc;
   }
-  rc = vec_finalize<T>(st->d_ws, (int)(n_chunks * kMaxPartials), reinterpret_cast<T*>(st->d_out), st->s_comp);
+  rc = vec_finalize<T>(sums, (int)(n_chunks * kMaxPartials), reinterpret_cast<T*>(st->d_out), st->s_comp);
   if (rc) return rc;
   rc = check_cuda(cudaMemcpyAsync(st->h_out, st->d_out, sizeof(T), cudaMemcpyDeviceToHost, st->s_comp), "cudaMemcpyAsync(out)");
   if (rc) return rc;
@@ -930,7 +1532,7 @@ using namespace st;
 
 extern "C" {
 
-int64_t st_contract_vec_workspace_bytes(void) { return (int64_t)sizeof(double) * kMaxPartials; }
+int64_t st_contract_vec_workspace_bytes(void) { return (int64_t)sizeof(double) * kWsSlots; }
 
 int st_set_tuning(const char* key, int64_t value) {
   if (!key) { set_error("null key"); return ST_ERR_INVALID; }
@@ -947,6 +1549,41 @@ int st_set_tuning(const char* key, int64_t value) {
     g_strats.clear();  // rebuilt on next use (old device tables are leaked: test hook)
     return ST_OK;
   }
+  {
+    if (k == "vec_ring_table_max" && value >= 0) {
+      g_ring_table_max = value;
+      std::lock_guard<std::mutex> lk(g_smu);
+      g_strats.clear();
+      return ST_OK;
+    }
+    if (k == "vec_timeline" && (value == 0 || value == 1)) {
+      if (value && !g_timeline) {
+        int rc = check_cuda(cudaMalloc(&g_timeline, kTimelineSlots * sizeof(unsigned long long)), "cudaMalloc(timeline)");
+        if (rc) return rc;
+      }
+      if (!value && g_timeline) { cudaFree(g_timeline); g_timeline = nullptr; }
+      if (g_timeline) cudaMemset(g_timeline, 0, kTimelineSlots * sizeof(unsigned long long));
+      return ST_OK;
+    }
+    if (k == "vec_ring_dynamic" && (value == 0 || value == 1)) { g_ring_dynamic = (int)value; return ST_OK; }
+    if (k == "vec_ring_direct" && value >= 0 && value <= 2) {
+      g_ring_direct = (int)value;
+      std::lock_guard<std::mutex> lk(g_smu);
+      g_strats.clear();
+      return ST_OK;
+    }
+    int* knob = k == "vec_ring_warps" ? &g_ring_warps : k == "vec_ring_slots" ? &g_ring_slots : k == "vec_ring_bytes" ? &g_ring_bytes :
+                k == "vec_ring_bytes_max" ? &g_ring_bytes_max : k == "vec_ring_tile_bytes" ? &g_ring_tile_bytes : nullptr;
+    if (knob) {
+      const bool ok = (knob == &g_ring_warps) ? (value >= 1 && value <= 16) : (knob == &g_ring_slots) ? (value >= 2 && value <= 8) :
+                      (knob == &g_ring_tile_bytes) ? (value >= 512 && value <= (1 << 24)) : (value >= 512 && value <= 65536 && value % 512 == 0);
+      if (!ok) { set_error("value %lld out of range for '%s'", (long long)value, key); return ST_ERR_INVALID; }
+      *knob = (int)value;
+      std::lock_guard<std::mutex> lk(g_smu);
+      g_strats.clear();  // rebuilt on next use (old device tables are leaked: tuning hook)
+      return ST_OK;
+    }
+  }
   if (k == "vec_batch_slots" && (value == 2 || value == 4)) { g_batch_slots = (int)value; return ST_OK; }
   if (k == "vec_tile_bytes" && value >= 1024 && value <= (1 << 28)) { g_tile_bytes = (int)value; return ST_OK; }
   if (k == "vec_force_tau" && value >= 0 && value <= ST_MAX_RANK) {
@@ -959,8 +1596,15 @@ int st_set_tuning(const char* key, int64_t value) {
   return ST_ERR_INVALID;
 }
 
+int st_debug_vec_timeline(unsigned long long* h_out, int64_t n) {
+  if (!g_timeline || !h_out || n < 0 || (size_t)n > kTimelineSlots) { set_error("timeline off or bad size"); return ST_ERR_INVALID; }
+  int rc = check_cuda(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  if (rc) return rc;
+  return check_cuda(cudaMemcpy(h_out, g_timeline, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost), "cudaMemcpy(timeline)");
+}
+
 int st_set_vec_variant(int variant) {
-  if (variant < 0 || variant > 2) { set_error("variant must be 0, 1 or 2"); return ST_ERR_INVALID; }
+  if (variant < 0 || variant > 3) { set_error("variant must be 0 .. 3"); return ST_ERR_INVALID; }
   g_variant = variant;
   std::lock_guard<std::mutex> lk(g_smu);
   g_strats.clear();  // strategies depend on the variant (old device tables are leaked: test hook)

@@ -15,6 +15,9 @@ struct TailStrategy {
   int32_t nE;    // values in earlier runs
   int32_t Rt;    // dim - nE: values available to the last run
   int32_t mu;    // multiplicity of the last run
+  int32_t direct;  // ring kernel, tau == 2: hybrid pair walk -- rows k < k0 of the pair table are walked column-wise with
+                   // weights xr[k] * xr[l] computed on the fly, rows k >= k0 come from a suffix table in shared memory
+  int32_t k0;      // direct: first row held by the suffix table (Rt: no table at all)
   int64_t tbl_n; // C(Rt, tau)
   int64_t seg;   // C(Rt, g_t): components per fixed assignment of the earlier runs
 };
@@ -379,6 +382,576 @@ ST_HD double walk_range(const PlanView& P, const TailStrategy& S, const T* __res
 }
 
 // ------------------------------------------------------------------------------------------------------
+// walk_tile: the walk of the ring kernel (vec_ring_kernel, st_vec.cu).  Same odometer as walk_range, but the
+// components are NOT fetched here: they arrive in shared memory through the warp's ring of cp.async.bulk
+// copies (the memory system runs ahead on its own), and this function only multiplies what is already
+// on chip.  `src.chunk(k)` hands out a pointer to the elements [k * Bel, (k + 1) * Bel) of the warp's
+// current tile (it waits for that copy, and releases -- i.e. refills -- the slots of earlier sub-chunks);
+// the range walked is [q0, q0 + n) of the segment, whose first element sits at position `t0` of the tile.
+// Per element: one LDS of the component, one LDS of the table, one FMA; a piece costs one odometer step.
+// On the host (tests/emu) `src` is a plain array view and the function is replayed lane by lane.
+// ------------------------------------------------------------------------------------------------------
+// DIRECT (strategy `direct`, tau == 2) is the hybrid pair walk: the pair table's rows (fixed k, l = k+1 .. Rt-1,
+// row k starts at table index rs(k) = k Rt - k (k + 1) / 2) with k >= k0 come from a SUFFIX TABLE in shared
+// memory, the rows below k0 -- the long ones -- are walked row by row with the weights xr[k] * xr[l] formed on
+// the fly:  racc += xr[k] * sum_l A[(k, l)] xr[l]  (per component one LDS of the component, one of xr, one FMA;
+// per row a handful of warp-uniform instructions).  A 96 KB suffix table covers 97 % of the components of the
+// rank-4 dim-200 class (1,1,1,1) (the full table would be 159 KB and leave no room for the rings), and the
+// dimension is no longer capped by the table.
+// GAP (direct classes with earlier runs, last-run multiplicity 1): `xr` is x itself, indexed by ACTUAL values, and the
+// relabelling u -> u + #{e : u + e >= E[e]} (skip the values E of the earlier runs, kept ascending in ws.E) is applied
+// on the fly -- a row's columns split into at most nE + 1 contiguous pieces of x -- so that these classes need no
+// per-warp relabelled copy of x in shared memory.
+template <typename T, bool DIRECT, bool GAP, typename Src>
+ST_HD double walk_tile(const PlanView& P, const TailStrategy& S, const T* __restrict__ tbl, const T* __restrict__ xr,
+                       const int32_t* __restrict__ blen, double wE, int64_t q0, int n, int t0, int lane, const int32_t* u_init, Src& src,
+                       WarpScratch& ws) {
+  ST_ASSUME_SHARED(tbl);
+  ST_ASSUME_SHARED(xr);
+  const int64_t* __restrict__ bt = P.binom;
+  const int rk = P.rank;
+  const int gt = S.gt, hn = S.hn, tau = S.tau, Rt = S.Rt;
+  const int tbl_n = (int)S.tbl_n;
+  const int nE = GAP ? S.nE : 0;
+  const int32_t* __restrict__ Ev = ws.E;
+  // relabelled value -> table entry (GAP: skip the earlier runs' values)
+  auto xat = [&](int uu) -> T {
+    if (GAP) for (int e = 0; e < nE; ++e) uu += (uu >= Ev[e]);
+    return xr[uu];
+  };
+  // ---- odometer state at q0 (see walk_range)
+  int32_t* u = ws.u;
+  double* pref = ws.pref;
+  if (u_init) {
+    if (u_init != u) for (int i = 0; i < gt; ++i) u[i] = u_init[i];
+  } else {
+#ifdef __CUDA_ARCH__
+    comb_unrank_warp(bt, rk, q0, Rt, gt, u, lane);
+#else
+    comb_unrank(bt, rk, q0, Rt, gt, u);
+#endif
+  }
+  int row_k = DIRECT ? u[hn] : 0;                                 // row walk: row of the current position ...
+  int row_s = DIRECT ? row_k * Rt - row_k * (row_k + 1) / 2 : 0;  // ... and its first table index rs(row_k)
+  const int tq = DIRECT   ? row_s + (u[hn + 1] - row_k - 1)
+                 : tau == 2 ? u[hn] * Rt - u[hn] * (u[hn] + 1) / 2 + (u[hn + 1] - u[hn] - 1)
+                 : tau == 1 ? u[hn]
+                            : (int)comb_rank(bt, rk, u + hn, Rt, tau);
+  pref[0] = wE;
+  for (int i = 0; i < hn; ++i) pref[i + 1] = pref[i] * (double)xat(u[i]);
+  int u_last = hn ? u[hn - 1] : -1;
+  double pref_prev = hn ? pref[hn - 1] : wE;
+  double hw = pref[hn];
+  int pb = 0;
+  int pe = (tbl_n - tq < n) ? tbl_n - tq : n;
+  int toff = tq;
+  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+  double total = 0.0;
+  auto advance = [&]() {
+    pb = pe;
+    if (hn == 0) { pe = n; return; }
+    if (u_last + 1 <= Rt - tau - 1) {
+      ++u_last;
+    } else {
+      u[hn - 1] = u_last;
+      int j = hn - 1;
+      while (j >= 0 && u[j] + 1 > Rt - (gt - j)) --j;
+      if (j < 0) { pe = n; return; }
+      ++u[j];
+      for (int k = j + 1; k < hn; ++k) u[k] = u[k - 1] + 1;
+      for (int k = j; k < hn - 1; ++k) pref[k + 1] = pref[k] * (double)xat(u[k]);
+      u_last = u[hn - 1];
+      pref_prev = pref[hn - 1];
+    }
+    hw = pref_prev * (double)xat(u_last);
+    const int m = Rt - 1 - u_last;
+    const int bl = DIRECT ? m * (m - 1) / 2 : tau == 1 ? m : (blen ? blen[u_last] : (int)binom_at(bt, rk, m, tau));
+    toff = tbl_n - bl - pb;
+    pe = (bl < n - pb) ? pb + bl : n;
+    if (DIRECT) { row_k = u_last + 1; row_s = tbl_n - bl; }  // the block starts with row u_last + 1
+  };
+  const int qs = DIRECT ? (S.k0 >= Rt - 1 ? tbl_n : S.k0 * Rt - S.k0 * (S.k0 + 1) / 2) : 0;  // first table index held by the suffix table
+  // row walk over the range-relative positions [a, b) of the current piece (all of them in rows below k0); dp[e] = component e
+  auto row_range = [&](const T* __restrict__ dp, int a, int b) {
+    int qa = toff + a;
+    const int qb = toff + b;
+    while (qa < qb) {
+      const int rend = row_s + (Rt - 1 - row_k);
+      const int se = qb < rend ? qb : rend;
+      const T xv = xat(row_k);
+      T r0 = T(0), r1 = T(0);
+      // columns l in [l_lo, l_hi) of row row_k; the component (row_k, l) sits at position l + poff
+      const int poff = row_s - row_k - 1 - toff;
+      int l_lo = row_k + 1 + (qa - row_s);
+      const int l_hi = row_k + 1 + (se - row_s);
+      for (int g = 0; g <= nE; ++g) {  // GAP: pieces of x between the earlier runs' values (one piece otherwise)
+        int l_end = l_hi;
+        if (GAP && g < nE) { const int lim = Ev[g] - g; l_end = lim < l_hi ? lim : l_hi; }
+        if (l_end > l_lo) {
+          const T* __restrict__ xp = xr + (g - poff);  // xp[e] = x of the component at position e
+          int e = l_lo + poff + lane;
+          const int ee = l_end + poff;
+          for (; e + 32 < ee; e += 64) {
+            r0 += dp[e] * xp[e];
+            r1 += dp[e + 32] * xp[e + 32];
+          }
+          if (e < ee) r0 += dp[e] * xp[e];
+          l_lo = l_end;
+        }
+      }
+      s3 += xv * (r0 + r1);
+      qa = se;
+      if (se == rend) { row_s = rend; ++row_k; }
+    }
+  };
+  const int Bel = src.bel();
+  int kc = t0 ? t0 / Bel : 0;  // sub-chunk of the tile that holds the range start
+  int cb = kc * Bel - t0;      // range-relative position of its first element (<= 0)
+  while (true) {
+    const T* __restrict__ dp = src.chunk(kc) - cb;  // dp[e]: component at range-relative position e
+    ST_ASSUME_SHARED(dp);
+    const int ce = (cb + Bel < n) ? cb + Bel : n;
+    bool done = false;
+    while (true) {
+      const int a = pb > cb ? pb : cb;
+      const int b = pe < ce ? pe : ce;
+      int as = a;
+      if (DIRECT) {
+        // rows below k0 row by row, the rest against the suffix table
+        as = qs - toff;  // first position of the piece held by the table
+        as = as < a ? a : (as > b ? b : as);
+        if (a < as) row_range(dp, a, as);
+      }
+      {
+        const T* __restrict__ tp = tbl + (toff - qs);  // tp[e]: weight of range-relative position e
+        for (int f = as + lane; f < b; f += 128) {  // four independent chains; the ragged end is predicated, not looped
+          s0 += dp[f] * tp[f];
+          if (f + 32 < b) s1 += dp[f + 32] * tp[f + 32];
+          if (f + 64 < b) s2 += dp[f + 64] * tp[f + 64];
+          if (f + 96 < b) s3 += dp[f + 96] * tp[f + 96];
+        }
+      }
+      if (pe > ce) break;  // the piece continues in the next sub-chunk
+      total += hw * (((double)s0 + (double)s1) + ((double)s2 + (double)s3));
+      s0 = T(0);
+      s1 = T(0);
+      s2 = T(0);
+      s3 = T(0);
+      if (pe >= n) { done = true; break; }
+      advance();
+      if (pb >= ce) break;
+    }
+    if (done) break;
+    ++kc;
+    cb += Bel;
+  }
+  return total;
+}
+
+template <typename T, typename Src>
+ST_HD double walk_tile_any(const PlanView& P, const TailStrategy& S, const T* __restrict__ tbl, const T* __restrict__ xr,
+                           const int32_t* __restrict__ blen, double wE, int64_t q0, int n, int t0, int lane, const int32_t* u_init, Src& src,
+                           WarpScratch& ws) {
+  if (S.direct) {
+    if (S.nE != 0 && S.mu == 1) return walk_tile<T, true, true, Src>(P, S, tbl, xr, blen, wE, q0, n, t0, lane, u_init, src, ws);
+    return walk_tile<T, true, false, Src>(P, S, tbl, xr, blen, wE, q0, n, t0, lane, u_init, src, ws);
+  }
+  return walk_tile<T, false, false, Src>(P, S, tbl, xr, blen, wE, q0, n, t0, lane, u_init, src, ws);
+}
+
+// host-side source of walk_tile (tests/emu): the tile is a plain array
+template <typename T>
+struct ArraySrc {
+  const T* tile;  // first element of the tile
+  int bel_;
+  ST_HD int bel() const { return bel_; }
+  ST_HD const T* chunk(int k) { return tile + (int64_t)k * bel_; }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// ring kernel plumbing (vec_ring_kernel, st_vec.cu): per-warp TMA rings
+// ------------------------------------------------------------------------------------------------------
+// Per-class record kept in shared memory (everything the scheduling loop needs, so that it never waits on a
+// global load).
+struct ClsInfo {
+  int64_t offset, size;
+  int64_t tile_base;  // tiles of the classes before this one (whole tensor): index into the tile directory
+  int64_t sbase;      // components of the SMALL classes before this one: index into the per-component directory
+  TailStrategy S;
+};
+
+// Per-class record of one launch (computed on the host and passed in the kernel parameters when the class count
+// allows, else by one thread of the CTA): the part of the class inside the launch range, cut into tiles and
+// chunks of NW tiles.  Static schedule: chunk c of the class belongs to CTA (c + rot) mod G.
+struct ClsRun {
+  int64_t lo, hi;    // positions of the class inside the launch range
+  int64_t k0, k1;    // tiles k0 .. k1-1 (tile k = positions [k * tile, (k + 1) * tile))
+  int64_t ch0, ch1;  // chunks ch0 .. ch1-1 (chunk c = tiles [c * NW, (c + 1) * NW))
+  int32_t rot;       // chunks of the earlier classes, mod G
+  int32_t mode;      // 0: not walked (small class / empty range); 1: tiles per warp (mode A); 2: chunks per CTA (mode B)
+};
+
+// the launch's schedule: one record per class (serial)
+ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, int64_t tile, int nwarps, int G, ClsRun* run) {
+  int64_t rot = 0;
+  for (int ci = 0; ci < ncls; ++ci) {
+    ClsRun r;
+    const int64_t coff = cls[ci].offset, csize = cls[ci].size;
+    const TailStrategy& S = cls[ci].S;
+    r.lo = (begin > coff ? begin : coff) - coff;
+    r.hi = (end < coff + csize ? end : coff + csize) - coff;
+    r.mode = (S.tau != 0 && r.lo < r.hi) ? ((S.tau == 1 || S.nE == 0 || S.direct) ? 1 : 2) : 0;
+    if (!r.mode) { r.lo = 0; r.hi = 0; }
+    r.k0 = r.lo / tile;
+    r.k1 = (r.hi + tile - 1) / tile;
+    r.ch0 = r.k0 / nwarps;
+    r.ch1 = (r.k1 + nwarps - 1) / nwarps;
+    r.rot = (int32_t)(rot % G);
+    if (r.mode) rot += r.ch1 - r.ch0;
+    run[ci] = r;
+  }
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// lane 0 only, without a branch: order the generic-proxy reads of the slot before the copy, arm the barrier, copy
+__device__ __forceinline__ void ring_issue(int lane, uint32_t bar, uint32_t dst, const void* src, uint32_t bytes) {
+  asm volatile(
+      "{\n"
+      " .reg .pred p, q;\n"
+      " setp.eq.s32 p, %0, 0;\n"
+      " setp.ne.and.u32 q, %4, 0, p;\n"
+      " @p fence.proxy.async.shared::cta;\n"
+      " @p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %4;\n"
+      " @q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%1];\n"
+      "}\n" ::"r"(lane),
+      "r"(bar), "r"(dst), "l"(src), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#endif
+
+// One tile of a warp's stream, queued by the producer cursor for the consumer cursor (shared memory, per warp)
+struct alignas(16) TileQ {
+  DirEntry de;   // directory entry of the tile (copied asynchronously when the tile is entered)
+  int64_t tk;    // tile index inside the class
+  int32_t ci;    // class
+  int32_t pad_;
+};
+
+// A warp's stream: producer cursor (what to copy next) and consumer cursor (what the walk reads next).  Every
+// warp owns R ring slots of Bel components and one mbarrier per slot; the stream is the concatenation of the
+// warp's tiles, cut into sub-chunks of Bel components.  The warp itself refills a slot as soon as the
+// sub-chunk in it has been consumed (release -> issue), so the producer cursor always runs R sub-chunks ahead
+// of the consumer cursor -- across tiles and classes.
+// Which tiles a warp gets: classes are visited in order; inside a mode-A class either the static round robin
+// (tile tk, tk + G * NW, ...) or -- `ctr` set -- DYNAMICALLY, one atomicAdd on the class's counter per tile:
+// tile costs differ by up to 5x (column walk vs table), and a static deal leaves the slowest warp 50 % behind the
+// median.  The claim for the tile after next is issued one tile early, so its latency is never waited for.
+// Mode-B classes are always static (their chunks are per CTA).  The producer queues every tile it enters
+// (class, tile index, directory entry) and the kernel's loops pop them in the same order.
+// Host build (tests/emu): a copy is a memcpy at issue time, waits are no-ops, claims are the static deal; the
+// cursor logic is the same code.
+template <typename T>
+struct RingSrc {
+  // ring
+  T* ring;         // this warp's R slots of Bel elements
+  uint32_t ring_s, slot_bytes;  // its shared-space address, bytes per slot
+  uint32_t bar0;   // shared-space address of this warp's R mbarriers
+  int R, Bel;
+  int lane;
+  // stream description
+  const ClsRun* run;
+  const ClsInfo* cls;
+  const T* A;      // points at packed coordinate `begin`
+  const DirEntry* dir;      // tile directory (nullptr: none)
+  unsigned long long* ctr;  // per-class tile counters (nullptr: static deal)
+  TileQ* queue;    // this warp's QD queue entries
+  int QD;
+  int64_t begin, tile;
+  int ncls, NW, G, warp, cta;
+  int64_t step;    // G * NW: distance between two tiles of this warp inside a class (static deal)
+  // producer cursor
+  int pci;
+  int64_t ptk, pk0, pk1, plo, phi;  // tile being copied, the class's tiles, class range
+  unsigned long long pend;          // dynamic deal: the next claim of this class (valid in lane 0)
+  bool pdyn, pahead;                // the current class is dealt dynamically / with claims one tile ahead
+  const T* pcbase;                  // first component of the class
+  const T* pbase;                   // first component of the tile being copied
+  int plen, poff;                   // its length, offset of the next sub-chunk
+  int pslot;
+  bool pvalid;
+  int qtail, qtail_i;               // tiles queued so far, and its queue slot
+  // consumer cursor
+  const T* cbase;
+  int clen, cur;  // current tile: first component, length, sub-chunk held (or to be acquired)
+  int cslot;
+  uint32_t cpar;  // parity to wait for on slot cslot
+  bool held;
+  int qhead, qhead_i;
+  int64_t n_issued, n_waited;  // sub-chunk counters (consistency checks of the emulation)
+
+  ST_HD int bel() const { return Bel; }
+  ST_HD int64_t jc0(int ci) const {
+    int j = cta - run[ci].rot;
+    return j < 0 ? j + G : j;
+  }
+
+  ST_HD unsigned long long claim(int ci) {
+#ifdef __CUDA_ARCH__
+    unsigned long long r = 0;
+    if (lane == 0) r = atomicAdd(ctr + ci, 1ULL);
+    return r;
+#else
+    (void)ci;
+    return 0;
+#endif
+  }
+  ST_HD int64_t claimed(unsigned long long raw) const {
+#ifdef __CUDA_ARCH__
+    return pk0 + (int64_t)__shfl_sync(0xffffffffu, raw, 0);
+#else
+    return pk0 + (int64_t)raw;
+#endif
+  }
+  // enter the tile ptk of class pci: source range, queue entry, directory entry
+  ST_HD void set_tile() {
+    int64_t w0 = ptk * tile, w1 = w0 + tile;
+    if (w0 < plo) w0 = plo;
+    if (w1 > phi) w1 = phi;
+    pbase = pcbase + w0;
+    plen = (int)(w1 - w0);
+    poff = 0;
+    TileQ& q = queue[qtail_i];
+    q.tk = ptk;
+    q.ci = pci;
+    if (dir != nullptr) {
+      const DirEntry* src = dir + (cls[pci].tile_base + ptk);
+#ifdef __CUDA_ARCH__
+      if (lane < 2) cp_async16(reinterpret_cast<char*>(&q.de) + 16 * lane, reinterpret_cast<const char*>(src) + 16 * lane);
+#else
+      q.de = *src;
+#endif
+    }
+    ++qtail;
+    if (++qtail_i == QD) qtail_i = 0;
+  }
+  // first tile of this warp in class ci; false: none
+  ST_HD bool enter_class(int ci) {
+    const ClsRun& r = run[ci];
+    if (!r.mode) return false;
+    pk0 = r.k0;
+    pk1 = r.k1;
+    pdyn = ctr != nullptr && r.mode == 1;
+    int64_t tk;
+    if (pdyn) {
+      // classes with many tiles per warp claim one tile ahead (the atomic's latency is never waited for); small
+      // classes claim on demand, or the first warps to arrive would take two tiles each and leave none
+      pahead = (r.k1 - r.k0) >= 4 * step;
+      const unsigned long long first = claim(ci);
+      if (pahead) pend = claim(ci);
+      tk = claimed(first);
+    } else {
+      tk = (r.ch0 + jc0(ci)) * NW + warp;
+      if (tk < r.k0) tk += step;
+    }
+    if (tk >= r.k1) return false;
+    ptk = tk;
+    plo = r.lo;
+    phi = r.hi;
+    pcbase = A + (cls[ci].offset - begin);
+    set_tile();
+    return true;
+  }
+  // position the producer on the next tile of this warp; false: the stream has ended
+  ST_HD bool next_tile() {
+    if (pdyn) {
+      if (pahead) {
+        ptk = claimed(pend);
+        if (ptk < pk1) pend = claim(pci);
+      } else {
+        ptk = claimed(claim(pci));
+      }
+    } else {
+      ptk += step;
+    }
+    if (ptk < pk1) { set_tile(); return true; }
+    while (++pci < ncls)
+      if (enter_class(pci)) return true;
+    return false;
+  }
+  ST_HD void start() {
+    step = (int64_t)G * NW;
+#ifdef __CUDA_ARCH__
+    ring_s = smem_u32(ring);
+#endif
+    slot_bytes = (uint32_t)Bel * (uint32_t)sizeof(T);
+    pslot = 0;
+    pvalid = false;
+    qtail = qhead = 0;
+    qtail_i = qhead_i = 0;
+    pend = 0;
+    pdyn = false;
+    pahead = false;
+    cslot = 0;
+    cpar = 0;
+    held = false;
+    cur = 0;
+    clen = 0;
+    n_issued = 0;
+    n_waited = 0;
+    for (pci = 0; pci < ncls; ++pci)
+      if (enter_class(pci)) { pvalid = true; break; }
+    for (int r = 0; r < R; ++r) issue();
+  }
+  ST_HD void wait_slot() {
+#ifdef __CUDA_ARCH__
+    mbar_wait(bar0 + 8u * cslot, cpar);
+#else
+    ++n_waited;
+#endif
+  }
+  // copy the next sub-chunk of the stream into slot pslot (which must be free)
+  ST_HD void issue() {
+    if (!pvalid) return;
+    int len = plen - poff;
+    if (len > Bel) len = Bel;
+    const uint32_t bytes = (uint32_t)(len * (int)sizeof(T)) & ~15u;  // whole 16-byte units; the rest is fetched by chunk()
+#ifdef __CUDA_ARCH__
+    ring_issue(lane, bar0 + 8u * pslot, ring_s + (uint32_t)pslot * slot_bytes, pbase + poff, bytes);
+#else
+    for (uint32_t i = 0; i < bytes / sizeof(T); ++i) ring[(size_t)pslot * Bel + i] = pbase[poff + i];
+    ++n_issued;
+#endif
+    if (++pslot == R) pslot = 0;
+    poff += len;
+    if (poff >= plen) pvalid = next_tile();
+  }
+  // consumer: is the next tile of the stream a tile of class ci?
+  ST_HD bool head_is(int ci) const { return qhead != qtail && queue[qhead_i].ci == ci; }
+  // consumer: take the next tile of the stream (its directory entry has landed when this returns)
+  ST_HD const TileQ& pop() {
+    const TileQ& q = queue[qhead_i];
+    ++qhead;
+    if (++qhead_i == QD) qhead_i = 0;
+#ifdef __CUDA_ARCH__
+    if (dir != nullptr) {
+      cp_async_wait_all();
+      __syncwarp();
+    }
+#endif
+    return q;
+  }
+  // consumer: open the tile [base, base + len) -- must be the tile just popped
+  ST_HD void open_tile(const T* base, int len) {
+    cbase = base;
+    clen = len;
+    cur = 0;
+    held = false;
+  }
+  ST_HD void release() {
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+#endif
+    held = false;
+    if (++cslot == R) { cslot = 0; cpar ^= 1u; }
+    ++cur;
+    issue();
+  }
+  ST_HD const T* chunk(int k) {
+    while (cur < k) {
+      if (!held) wait_slot();  // not in practice: the walk reads every sub-chunk
+      release();
+    }
+    T* slot = ring + cslot * Bel;
+    if (!held) {
+      wait_slot();
+      held = true;
+      const int len = clen - k * Bel;
+      if (len <= Bel) {  // last sub-chunk: components behind the last whole 16-byte unit of the tile
+        const int nb = (int)(((uint32_t)(len * (int)sizeof(T)) & ~15u) / sizeof(T));
+        if (nb < len) {
+#ifdef __CUDA_ARCH__
+          if (lane < len - nb) slot[nb + lane] = cbase[k * Bel + nb + lane];
+          __syncwarp();
+#else
+          for (int l = 0; l < len - nb; ++l) slot[nb + l] = cbase[k * Bel + nb + l];
+#endif
+        }
+      }
+    }
+    return slot;
+  }
+  ST_HD void close_tile() {
+    while (cur * Bel < clen) {
+      if (!held) wait_slot();
+      release();
+    }
+  }
+};
+
+// shared-memory layout of vec_ring_kernel (host and device agree through this one function)
+struct RingLayout {
+  size_t priv, xr, blen, binom, cls, cdesc, ws, ctl, run, queue, bar, ring, total;
+};
+ST_HD RingLayout ring_layout(int esize, int64_t dim, int tbl_cap, int priv_cap, int binom_smem, int ncls, int cdesc_smem, int nw, int R, int Bel) {
+  RingLayout L;
+  size_t off = ((size_t)tbl_cap * esize + 15) / 16 * 16;
+  L.priv = off;  // per-warp xr tables of the classes with earlier runs (priv_cap = nw * dim entries, or 0)
+  off = (off + (size_t)priv_cap * esize + 15) / 16 * 16;
+  L.xr = off;
+  off = (off + 2 * (size_t)dim * esize + 15) / 16 * 16;
+  L.blen = off;
+  off = (off + (size_t)dim * sizeof(int32_t) + 15) / 16 * 16;
+  L.binom = off;
+  off += (size_t)binom_smem * sizeof(int64_t);
+  L.cls = off;
+  off += (size_t)ncls * sizeof(ClsInfo);
+  L.cdesc = off;
+  off += cdesc_smem ? (size_t)ncls * sizeof(ClassDesc) : 0;
+  off = (off + 15) / 16 * 16;
+  L.ws = off;
+  off += (size_t)nw * sizeof(WarpScratch);
+  L.ctl = off;
+  off = (off + sizeof(TailCtrl) + 15) / 16 * 16;
+  L.run = off;
+  off = (off + (size_t)ncls * sizeof(ClsRun) + 15) / 16 * 16;
+  L.queue = off;
+  off += (size_t)nw * (R + 2) * sizeof(TileQ);
+  L.bar = off;
+  off += (size_t)nw * R * sizeof(uint64_t);
+  off = (off + 127) / 128 * 128;
+  L.ring = off;
+  off += (size_t)nw * R * Bel * esize;
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------------------------------------------
 // tile directory: the distinct values (class order, absolute) of the component at the start of every tile,
 // 16 x uint16 per tile, written once per (rank, dim, tile size) by the GPU index enumerator (st_vec.cu) so that
 // starting a tile costs one 32-byte load instead of a combinatorial unrank.
@@ -444,6 +1017,19 @@ ST_HD void build_table_level(const int64_t* __restrict__ bt, int rk, int Rt, int
     const int64_t so = nt1 - len;
     const T xv = xr[c0];
     for (int64_t i = lane; i < len; i += 32) dst[go + i] = xv * src[so + i];
+  }
+}
+
+// Suffix of the pair table (hybrid pair walk): rows k >= k0, entry (k, l) at  rs(k) - rs(k0) + l - k - 1.
+// Thread `tid` of `nthreads` takes the rows warp by warp; coalesced stores.
+template <typename T>
+ST_HD void build_pair_suffix(int Rt, int k0, const T* __restrict__ xr, T* __restrict__ dst, int tid, int nthreads) {
+  const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+  const int qs = k0 * Rt - k0 * (k0 + 1) / 2;
+  for (int k = k0 + warp; k < Rt - 1; k += nw) {
+    const int go = k * Rt - k * (k + 1) / 2 - qs - k - 1;
+    const T xv = xr[k];
+    for (int l = k + 1 + lane; l < Rt; l += 32) dst[go + l] = xv * xr[l];
   }
 }
 

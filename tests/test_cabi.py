@@ -155,9 +155,9 @@ def emu_lib():
 
 
 def test_tail_kernel_index_walk_emulated_on_cpu(emu_lib):
-    """The tail-table kernel's strategy / segment / block walk (host+device functions of st_vec_core.cuh),
-    replayed serially on the CPU by tests/emu, against the packed oracle -- all classes, forced tail lengths,
-    sharded ranges."""
+    """The ring kernel's strategy / chunk / tile / segment / block walk and its per-warp stream cursors (host+device
+    code of st_vec_core.cuh), replayed serially on the CPU by tests/emu, against the packed oracle -- all classes,
+    forced tail lengths, ring geometries, sharded and ragged ranges."""
     rng = np.random.default_rng(1)
     i64 = ctypes.c_int64
 
@@ -168,35 +168,51 @@ def test_tail_kernel_index_walk_emulated_on_cpu(emu_lib):
             buf[o:o + s] = data[c]
         return buf
 
-    def emu(rank, dim, buf, x, begin=0, end=None, nwarps=4, grid=3, item=64, tau=0, use_dir=1, small=0):
+    def emu(rank, dim, buf, x, begin=0, end=None, nwarps=4, grid=3, item=64, bel=16, slots=2, tau=0, use_dir=1, small=0):
         end = len(buf) if end is None else end
         out = ctypes.c_double()
         taus = (ctypes.c_int32 * comb.class_table(rank, dim).ncls)()
         rc = emu_lib.emu_contract_vec_f64(rank, i64(dim), ctypes.c_void_p(buf[begin:].ctypes.data), i64(begin), i64(end),
-                                          ctypes.c_void_p(x.ctypes.data), nwarps, grid, i64(item), tau, use_dir, i64(small), ctypes.byref(out), taus)
-        assert rc == 0
+                                          ctypes.c_void_p(x.ctypes.data), nwarps, grid, i64(item), bel, slots, tau, use_dir, i64(small),
+                                          ctypes.byref(out), taus)
+        assert rc == 0, rc
         return out.value
 
+    # the table-free pair walk at dimensions that need 8 / 12 column slots and the per-lane fallback (Rt > 384)
+    for rank, dim in [(2, 150), (3, 140), (2, 300), (2, 400), (3, 70)]:
+        data = {c: rng.uniform(0.5, 1.5, io.permclass_size(c, dim)) for c in io.perm_classes(rank)}
+        x = rng.uniform(0.5, 1.5, dim) / np.sqrt(dim)
+        ref = po.contract_all_indices_with_vector(data, rank, dim, x)
+        buf = pack(data, rank, dim)
+        for tau in (-1, -2, -3):
+            for nw, grid, item, bel, slots in [(4, 3, 256, 64, 2), (3, 2, 192, 192, 3)]:
+                got = emu(rank, dim, buf, x, nwarps=nw, grid=grid, item=item, bel=bel, slots=slots, tau=tau)
+                assert abs(got - ref) <= 1e-12 * abs(ref), (rank, dim, tau, nw, grid, item, bel, slots)
     for rank, dim in [(1, 7), (2, 9), (3, 6), (3, 13), (4, 5), (4, 11), (5, 7), (6, 7), (7, 8), (8, 9), (4, 40)]:
         data = {c: rng.uniform(0.5, 1.5, io.permclass_size(c, dim)) for c in io.perm_classes(rank)}
         x = rng.uniform(0.5, 1.5, dim)
         ref = po.contract_all_indices_with_vector(data, rank, dim, x)
         buf = pack(data, rank, dim)
-        for tau in (0, 1, 2, 3):
-            for nw, grid, item in [(4, 3, 64), (16, 5, 2048), (2, 7, 32), (1, 2, 1024)]:
+        for tau in (0, 1, 2, 3, -1, -2, -3):  # < 0: the hybrid pair walk (no table / all table / 2 KB suffix table)
+            for nw, grid, item, bel, slots in [(4, 3, 64, 16, 2), (12, 5, 1024, 256, 2), (2, 7, 32, 32, 3), (1, 2, 1024, 64, 4)]:
                 for use_dir in (0, 1):
-                    got = emu(rank, dim, buf, x, nwarps=nw, grid=grid, item=item, tau=tau, use_dir=use_dir)
-                    assert abs(got - ref) <= 1e-12 * abs(ref), (rank, dim, tau, nw, grid, item, use_dir)
+                    got = emu(rank, dim, buf, x, nwarps=nw, grid=grid, item=item, bel=bel, slots=slots, tau=tau, use_dir=use_dir)
+                    assert abs(got - ref) <= 1e-12 * abs(ref), (rank, dim, tau, nw, grid, item, bel, slots, use_dir)
         for small in (100, 10 ** 9):  # some / all classes through the per-component phase
             assert abs(emu(rank, dim, buf, x, small=small) - ref) <= 1e-12 * abs(ref)
         tot = len(buf)
         cut = (tot // 3) // 32 * 32
         s = sum(emu(rank, dim, buf, x, begin=b, end=e, small=sm) for sm, (b, e) in zip((0, 50, 0), [(0, cut), (cut, 2 * cut), (2 * cut, tot)]))
         assert abs(s - ref) <= 1e-12 * abs(ref)
+        # ragged ends: the last 16-byte unit of a tile is incomplete (fetched outside the bulk copy)
+        e1 = min(tot, cut + 37)
+        s = emu(rank, dim, buf, x, begin=0, end=e1, item=32, bel=32) + emu(rank, dim, buf, x, begin=e1 // 32 * 32, end=tot, item=128, bel=64)
+        s -= emu(rank, dim, buf, x, begin=e1 // 32 * 32, end=e1)
+        assert abs(s - ref) <= 1e-12 * abs(ref)
         # fp32 instantiation (4 components per 16-byte vector)
         buf32, x32 = buf.astype(np.float32), x.astype(np.float32)
         out = ctypes.c_double()
         for tau in (0, 2):
             rc = emu_lib.emu_contract_vec_f32(rank, i64(dim), ctypes.c_void_p(buf32.ctypes.data), i64(0), i64(len(buf32)),
-                                              ctypes.c_void_p(x32.ctypes.data), 4, 3, i64(4096), tau, 1, i64(0), ctypes.byref(out), None)
+                                              ctypes.c_void_p(x32.ctypes.data), 4, 3, i64(4096), 512, 2, tau, 1, i64(0), ctypes.byref(out), None)
             assert rc == 0 and abs(out.value - ref) <= 1e-5 * abs(ref)
