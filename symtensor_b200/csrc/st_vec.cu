@@ -586,6 +586,16 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   src.cta = blockIdx.x;
   // x is requested now and stored after the stream has started (its latency overlaps the first claims and copies)
   const T x_pre = (int64_t)threadIdx.x < P.dim ? a.x[threadIdx.x] : T(0);
+  constexpr int kPre = 3;
+  int64_t b_pre[kPre];
+  int32_t c_pre[kPre];
+  const int nw32 = a.cdesc_smem ? (int)(sizeof(ClassDesc) / 4) * P.ncls : 0;
+#pragma unroll
+  for (int j = 0; j < kPre; ++j) {
+    const int i = threadIdx.x + j * nthreads;
+    b_pre[j] = i < a.binom_smem ? a.P.binom[i] : 0;
+    c_pre[j] = i < nw32 ? reinterpret_cast<const int32_t*>(a.P.cls)[i] : 0;
+  }
   stamp(1);
   src.start();
   stamp(2);
@@ -593,13 +603,18 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   // ---- 2. x, binomials, class descriptors
   if ((int64_t)threadIdx.x < P.dim) xs[threadIdx.x] = x_pre;
   for (int i = threadIdx.x + nthreads; i < P.dim; i += nthreads) xs[i] = a.x[i];
+#pragma unroll
+  for (int j = 0; j < kPre; ++j) {
+    const int i = threadIdx.x + j * nthreads;
+    if (i < a.binom_smem) binom_s[i] = b_pre[j];
+    if (i < nw32) reinterpret_cast<int32_t*>(cdesc_s)[i] = c_pre[j];
+  }
   if (a.binom_smem) {
-    for (int i = threadIdx.x; i < a.binom_smem; i += nthreads) binom_s[i] = a.P.binom[i];
+    for (int i = threadIdx.x + kPre * nthreads; i < a.binom_smem; i += nthreads) binom_s[i] = a.P.binom[i];
     P.binom = binom_s;
   }
   if (a.cdesc_smem) {
-    const int nw32 = (int)(sizeof(ClassDesc) / 4) * P.ncls;
-    for (int i = threadIdx.x; i < nw32; i += nthreads) reinterpret_cast<int32_t*>(cdesc_s)[i] = reinterpret_cast<const int32_t*>(a.P.cls)[i];
+    for (int i = threadIdx.x + kPre * nthreads; i < nw32; i += nthreads) reinterpret_cast<int32_t*>(cdesc_s)[i] = reinterpret_cast<const int32_t*>(a.P.cls)[i];
     P.cls = cdesc_s;
   }
   __syncthreads();
@@ -634,53 +649,9 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // this warp
   double total = 0.0;
 
-  // ---- 3. SMALL classes (tau == 0 in the strategy): one component per thread from the per-component directory
-  {
-    int64_t sm_base = 0;
-    const int64_t nthr = W * 32, tid = gw * 32 + lane;
-    for (int ci = 0; ci < P.ncls; ++ci) {
-      if (cls_s[ci].S.tau != 0) continue;
-      const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
-      const int64_t lo = (a.begin > coff ? a.begin : coff) - coff;
-      const int64_t hi = (a.end < coff + csize ? a.end : coff + csize) - coff;
-      if (lo >= hi) continue;
-      const ClassDesc& C = P.cls[ci];
-      const T* Acls = a.A + (coff - a.begin);
-      const int nvals = C.nvals;
-      const double gamma = (double)C.gamma;
-      for (int64_t p = lo + (tid - sm_base % nthr + nthr) % nthr; p < hi; p += nthr) {
-        const double v = (double)__ldcs(Acls + p);
-        double w = gamma;
-        if (a.sdir != nullptr) {
-          const uint4* q = reinterpret_cast<const uint4*>(a.sdir + (cls_s[ci].sbase + p));
-          const uint4 e0 = __ldg(q), e1 = __ldg(q + 1);
-          const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-          for (int k = 0; k < ST_MAX_RANK; ++k) {
-            if (k < nvals) {
-              const int val = (int)((words[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
-              const double xv = (double)xs[val];
-              const int m = C.mult[k];
-              for (int mm = 0; mm < m; ++mm) w *= xv;
-            }
-          }
-        } else {
-          int32_t vals[ST_MAX_RANK];
-          permcls_unrank_vals(P, C, p, vals);
-          for (int k = 0; k < nvals; ++k) {
-            const double xv = (double)xs[vals[k]];
-            for (int m = 0; m < C.mult[k]; ++m) w *= xv;
-          }
-        }
-        total += v * w;
-      }
-      sm_base += hi - lo;
-    }
-  }
-
-  stamp(4);
-  // ---- 4. tail-table classes, in stream order.  Every tile's sum goes to its own slot of the workspace (the deal
+  // ---- 3. tail-table classes, in stream order.  Every tile's sum goes to its own slot of the workspace (the deal
   // may be dynamic: the final reduction must not depend on who walked which tile).
+  unsigned long long dbg_tiles = 0, dbg_maxdur = 0, dbg_last = 0, dbg_maxtile = 0;  // debug timeline only
   double* tile_part = a.partials + kTilePartOff;
   auto store_tile = [&](int64_t slot, double v) {
     v = warp_sum(v);
@@ -689,7 +660,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   for (int ci = 0; ci < P.ncls; ++ci) {
     const ClsRun rr = run[ci];
     if (!rr.mode) continue;
-    if (ci < 8) stamp(5 + ci);
+    if (ci < 5) stamp(5 + ci);
     const TailStrategy S = cls_s[ci].S;
     const ClassDesc& C = P.cls[ci];
     const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
@@ -722,6 +693,8 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
       int32_t* E = ws.E;
       int32_t* u0 = ws.u0;
       while (src.head_is(ci)) {
+        unsigned long long t_begin = 0;
+        if (a.tl != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
         const TileQ& tq = src.pop();
         const int64_t tk = tq.tk;
         int64_t w0 = tk * tile;
@@ -772,6 +745,13 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
         }
         src.close_tile();
         store_tile(dbase + tk, tsum);
+        if (a.tl != nullptr) {
+          unsigned long long t_end;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+          ++dbg_tiles;
+          if (t_end - t_begin > dbg_maxdur) { dbg_maxdur = t_end - t_begin; dbg_maxtile = (unsigned long long)(dbase + tk); }
+          dbg_last = t_begin;
+        }
       }
     } else {
       // ---- mode B: chunks of nwarps tiles per CTA (static deal); the CTA rebuilds T once per segment
@@ -844,17 +824,74 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
         }
       }
     }
+    if (a.tl != nullptr && lane == 0 && ci < 8) {
+      unsigned long long ts;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+      a.tl[(size_t)148 * 16 + 4096 + (size_t)gw * 8 + ci] = ts;
+    }
   }
 
+  // ---- 4. SMALL classes (tau == 0 in the strategy): one component per thread from the per-component directory; last,
+  // where they fill the gaps of the launch's tail instead of holding up the stream at its start
+  {
+    int64_t sm_base = 0;
+    const int64_t nthr = W * 32, tid = gw * 32 + lane;
+    for (int ci = 0; ci < P.ncls; ++ci) {
+      if (cls_s[ci].S.tau != 0) continue;
+      const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
+      const int64_t lo = (a.begin > coff ? a.begin : coff) - coff;
+      const int64_t hi = (a.end < coff + csize ? a.end : coff + csize) - coff;
+      if (lo >= hi) continue;
+      const ClassDesc& C = P.cls[ci];
+      const T* Acls = a.A + (coff - a.begin);
+      const int nvals = C.nvals;
+      const double gamma = (double)C.gamma;
+      for (int64_t p = lo + (tid - sm_base % nthr + nthr) % nthr; p < hi; p += nthr) {
+        const double v = (double)__ldcs(Acls + p);
+        double w = gamma;
+        if (a.sdir != nullptr) {
+          const uint4* q = reinterpret_cast<const uint4*>(a.sdir + (cls_s[ci].sbase + p));
+          const uint4 e0 = __ldg(q), e1 = __ldg(q + 1);
+          const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+          for (int k = 0; k < ST_MAX_RANK; ++k) {
+            if (k < nvals) {
+              const int val = (int)((words[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+              const double xv = (double)xs[val];
+              const int m = C.mult[k];
+              for (int mm = 0; mm < m; ++mm) w *= xv;
+            }
+          }
+        } else {
+          int32_t vals[ST_MAX_RANK];
+          permcls_unrank_vals(P, C, p, vals);
+          for (int k = 0; k < nvals; ++k) {
+            const double xv = (double)xs[vals[k]];
+            for (int m = 0; m < C.mult[k]; ++m) w *= xv;
+          }
+        }
+        total += v * w;
+      }
+      sm_base += hi - lo;
+    }
+  }
+
+  stamp(4);
   if (a.tl != nullptr && lane == 0) {
     unsigned long long ts;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
-    a.tl[(size_t)gridDim.x * 16 + (size_t)blockIdx.x * nwarps + warp] = ts;
+    a.tl[(size_t)148 * 16 + (size_t)blockIdx.x * nwarps + warp] = ts;
+    unsigned long long* d = a.tl + (size_t)148 * 16 + 4096 + (size_t)gw * 8;
+    d[5] = dbg_tiles;
+    d[6] = dbg_maxdur;
+    d[7] = dbg_last;
+    d[2] = dbg_maxtile;
   }
   // one partial per warp of the grid, added in index order by the last CTA to finish (deterministic)
   total = warp_sum(total);
   if (lane == 0) a.partials[1 + gw] = total;
   __syncthreads();
+  stamp(10);
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned long long ticket = atomicAdd(a.counter, 1ULL);
@@ -866,19 +903,25 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
     ctl->last = last ? 1 : 0;
   }
   __syncthreads();
+  stamp(11);
   if (ctl->last) {
     // the last CTA adds the per-warp sums (small classes) and the per-tile sums in index order, and resets the counters
     double s = 0.0;
-    auto add_slots = [&](const double* p, int64_t i0, int64_t i1) {  // fixed thread -> slot map, 8 loads in flight
-      int64_t i = i0 + threadIdx.x;
-      for (; i + 7 * (int64_t)nthreads < i1; i += 8 * (int64_t)nthreads) {
-        double v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldcg(p + i + j * (int64_t)nthreads);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += v[j];
+    auto add_slots = [&](const double* p, int64_t i0, int64_t i1) {  // fixed thread -> slot map; 16-byte loads, 20 in flight
+      if (i0 < i1 && ((uintptr_t)(p + i0) & 15u)) {  // peel to a 16-byte boundary
+        if (threadIdx.x == 0) s += __ldcg(p + i0);
+        ++i0;
       }
-      for (; i < i1; i += nthreads) s += __ldcg(p + i);
+      const int64_t nv = (i1 - i0) >> 1;
+      const double2* pv = reinterpret_cast<const double2*>(p + i0);
+      for (int64_t i = threadIdx.x; i < nv; i += 20 * (int64_t)nthreads) {
+        double2 v[20];
+#pragma unroll
+        for (int j = 0; j < 20; ++j) v[j] = (i + j * (int64_t)nthreads < nv) ? __ldcg(pv + i + j * (int64_t)nthreads) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int j = 0; j < 20; ++j) s += v[j].x + v[j].y;
+      }
+      if (((i1 - i0) & 1) && threadIdx.x == 1) s += __ldcg(p + i1 - 1);
     };
     add_slots(a.partials + 1, 0, W);
     for (int ci = 0; ci < P.ncls; ++ci) {
@@ -886,6 +929,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
       add_slots(tile_part + cls_s[ci].tile_base, run[ci].k0, run[ci].k1);
     }
     for (int c = threadIdx.x; c < P.ncls; c += nthreads) a.counter[2 + c] = 0ULL;
+    stamp(12);
     s = warp_sum(s);
     if (lane == 0) ctl->red[warp] = s;
     __syncthreads();
@@ -910,9 +954,9 @@ int g_variant = 0;
 static int g_use_dir = 1;  // tuning knob "vec_use_dir": 0 unranks every tile start in the kernel
 int g_force_tau = 0;  // test hook: force the tail length (0 = cost model)
 unsigned long long* g_timeline = nullptr;  // debug: device buffer of kTimelineSlots stamps (st_set_tuning vec_timeline 1)
-static const size_t kTimelineSlots = 148 * 16 + 4096;
+static const size_t kTimelineSlots = 148 * 16 + 4096 + 4096 * 8;
 int g_ring_direct = 1;                 // ring kernel: allow the table-free pair walk (2: with vec_force_tau 2, force it)
-int64_t g_ring_table_max = 96 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
+int64_t g_ring_table_max = 64 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
 int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
 struct StratKey {
@@ -937,13 +981,14 @@ struct StratEntry {
   // host copies for the launch-time schedule
   std::vector<TailStrategy> h_strat;
   std::vector<int64_t> h_tile_base, h_sbase;
+  std::vector<int64_t> h_ntail;  // per class: trailing tiles made of many tiny blocks (dealt first)
 };
 static std::mutex g_smu;
 // ring kernel tuning knobs (st_set_tuning)
 static int g_ring_dynamic = 1;         // deal the tiles of mode-A classes dynamically
 static int g_ring_warps = 16;          // consumer warps per CTA
-static int g_ring_slots = 3;           // ring slots per warp
-static int g_ring_bytes = 2048;        // preferred bytes per slot (shrunk to 1536 / 1024 when the table needs the room)
+static int g_ring_slots = 2;           // ring slots per warp
+static int g_ring_bytes = 4096;        // preferred bytes per slot (shrunk to 1536 / 1024 when the table needs the room)
 static int g_ring_bytes_max = 4096;    // slots grow up to this when shared memory is left over
 static int g_ring_tile_bytes = 32768;    // bytes per tile (directory granularity; rounded to whole slots)
 static std::map<StratKey, StratEntry> g_strats;
@@ -1173,6 +1218,26 @@ static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, bool rin
     const int64_t ntiles = tb[hp->ncls];
     e.h_strat = st;
     e.h_tile_base = tb;
+    e.h_ntail.assign(hp->ncls, 0);
+    if (ring) {
+      // a tile that starts where the blocks are shorter than 512 components holds many pieces and costs several times
+      // the usual: such tiles sit at the end of a single-run class (the head values only grow)
+      const PlanView hv = hp->host_view();
+      for (int c = 0; c < hp->ncls; ++c) {
+        const TailStrategy& S = st[c];
+        if (S.tau == 0 || S.nE != 0 || S.hn == 0) continue;
+        const int64_t nt = tb[c + 1] - tb[c];
+        int64_t n = 0;
+        while (n < nt && n < 1024 && n < nt / 4) {
+          int32_t u[ST_MAX_RANK];
+          comb_unrank(hv.binom, hv.rank, (nt - 1 - n) * tile, S.Rt, S.gt, u);
+          const int64_t bl = binom_at(hv.binom, hv.rank, S.Rt - 1 - u[S.hn - 1], S.tau);
+          if (bl >= 512) break;
+          ++n;
+        }
+        e.h_ntail[c] = n;
+      }
+    }
     if (g_use_dir && dim <= 65535 && ntiles > 0 && ntiles <= kMaxDirTiles) {
       PlanView P;
       rc = get_device_plan(rank, dim, &P);
@@ -1297,6 +1362,13 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
       sched.cls[c].S = se.h_strat[c];
     }
     make_runs(sched.cls, hp->ncls, a.begin, a.end, se.tile_elems, nwarps, (int)grid, sched.run);
+    for (int c = 0; c < hp->ncls; ++c) {  // the costly tail is dealt first when the launch covers the end of the class
+      ClsRun& r = sched.run[c];
+      if (r.mode == 1 && a.dynamic && r.hi == hp->h_cls[c].size) {
+        r.ntail = std::min<int64_t>(se.h_ntail[c], r.k1 - r.k0);
+        if (r.ntail > r.ns) r.ntail = r.ntail;  // (the static first deal follows the same order)
+      }
+    }
     sched.n = hp->ncls;
   }
   vec_ring_kernel<T><<<(int)grid, nwarps * 32, se.smem_bytes, stream>>>(a, sched);

@@ -414,9 +414,13 @@ ST_HD double walk_tile(const PlanView& P, const TailStrategy& S, const T* __rest
   const int tbl_n = (int)S.tbl_n;
   const int nE = GAP ? S.nE : 0;
   const int32_t* __restrict__ Ev = ws.E;
+  const int e0 = GAP ? Ev[0] : 0;
   // relabelled value -> table entry (GAP: skip the earlier runs' values)
   auto xat = [&](int uu) -> T {
-    if (GAP) for (int e = 0; e < nE; ++e) uu += (uu >= Ev[e]);
+    if (GAP) {
+      if (nE == 1) uu += (uu >= e0);
+      else for (int e = 0; e < nE; ++e) uu += (uu >= Ev[e]);
+    }
     return xr[uu];
   };
   // ---- odometer state at q0 (see walk_range)
@@ -471,34 +475,56 @@ ST_HD double walk_tile(const PlanView& P, const TailStrategy& S, const T* __rest
     if (DIRECT) { row_k = u_last + 1; row_s = tbl_n - bl; }  // the block starts with row u_last + 1
   };
   const int qs = DIRECT ? (S.k0 >= Rt - 1 ? tbl_n : S.k0 * Rt - S.k0 * (S.k0 + 1) / 2) : 0;  // first table index held by the suffix table
-  // row walk over the range-relative positions [a, b) of the current piece (all of them in rows below k0); dp[e] = component e
+  // row walk over the range-relative positions [a, b) of the current piece (all of them in rows below k0); dp[e] = component e.
+  // Two forms.  Long rows (classes without earlier runs: the rows below k0 are the long ones): row by row, the warp
+  // along the row.  GAP classes (every row of the pair table, average length Rt / 3, each cut in two by the
+  // relabelling): 32 consecutive positions at a time, one per lane; the row of the group's first position is
+  // tracked warp-uniformly and a lane steps at most one row further (more only in the last 32 rows).
   auto row_range = [&](const T* __restrict__ dp, int a, int b) {
+    if (GAP) {
+      // weight of the component with table index q, starting the row search at the warp-uniform row (row_k, row_s)
+      auto pair_w = [&](int q) -> T {
+        int k = row_k, rs = row_s, len = Rt - 1 - row_k;
+        while (q >= rs + len) { rs += len; ++k; --len; }
+        int l = q - rs + k + 1;
+        if (nE == 1) {  // the common case: one earlier value, kept in a register
+          k += (k >= e0);
+          l += (l >= e0);
+        } else {
+          for (int e = 0; e < nE; ++e) { k += (k >= Ev[e]); l += (l >= Ev[e]); }
+        }
+        return xr[k] * xr[l];
+      };
+      for (int g0 = a; g0 < b; g0 += 128) {  // four groups of 32 positions per step (independent chains)
+        const int qg = toff + g0;
+        while (qg >= row_s + (Rt - 1 - row_k)) { row_s += Rt - 1 - row_k; ++row_k; }
+        const int e = g0 + lane;
+        const T w0 = e < b ? pair_w(qg + lane) : T(0);
+        const T w1 = e + 32 < b ? pair_w(qg + 32 + lane) : T(0);
+        const T w2 = e + 64 < b ? pair_w(qg + 64 + lane) : T(0);
+        const T w3 = e + 96 < b ? pair_w(qg + 96 + lane) : T(0);
+        if (e < b) s0 += dp[e] * w0;
+        if (e + 32 < b) s1 += dp[e + 32] * w1;
+        if (e + 64 < b) s2 += dp[e + 64] * w2;
+        if (e + 96 < b) s3 += dp[e + 96] * w3;
+      }
+      return;
+    }
     int qa = toff + a;
     const int qb = toff + b;
     while (qa < qb) {
       const int rend = row_s + (Rt - 1 - row_k);
       const int se = qb < rend ? qb : rend;
-      const T xv = xat(row_k);
+      const T xv = xr[row_k];
+      const T* __restrict__ xp = xr + (row_k + 1 - row_s + toff);  // xp[e] = xr[l] for the component (row_k, l) at position e
       T r0 = T(0), r1 = T(0);
-      // columns l in [l_lo, l_hi) of row row_k; the component (row_k, l) sits at position l + poff
-      const int poff = row_s - row_k - 1 - toff;
-      int l_lo = row_k + 1 + (qa - row_s);
-      const int l_hi = row_k + 1 + (se - row_s);
-      for (int g = 0; g <= nE; ++g) {  // GAP: pieces of x between the earlier runs' values (one piece otherwise)
-        int l_end = l_hi;
-        if (GAP && g < nE) { const int lim = Ev[g] - g; l_end = lim < l_hi ? lim : l_hi; }
-        if (l_end > l_lo) {
-          const T* __restrict__ xp = xr + (g - poff);  // xp[e] = x of the component at position e
-          int e = l_lo + poff + lane;
-          const int ee = l_end + poff;
-          for (; e + 32 < ee; e += 64) {
-            r0 += dp[e] * xp[e];
-            r1 += dp[e + 32] * xp[e + 32];
-          }
-          if (e < ee) r0 += dp[e] * xp[e];
-          l_lo = l_end;
-        }
+      int e = qa - toff + lane;
+      const int ee = se - toff;
+      for (; e + 32 < ee; e += 64) {
+        r0 += dp[e] * xp[e];
+        r1 += dp[e + 32] * xp[e + 32];
       }
+      if (e < ee) r0 += dp[e] * xp[e];
       s3 += xv * (r0 + r1);
       qa = se;
       if (se == rend) { row_s = rend; ++row_k; }
@@ -587,13 +613,16 @@ struct ClsRun {
   int64_t lo, hi;    // positions of the class inside the launch range
   int64_t k0, k1;    // tiles k0 .. k1-1 (tile k = positions [k * tile, (k + 1) * tile))
   int64_t ch0, ch1;  // chunks ch0 .. ch1-1 (chunk c = tiles [c * NW, (c + 1) * NW))
+  int64_t ntail;     // dynamic deal: the class's last ntail tiles (many tiny blocks: the costly ones) are dealt FIRST, last tile first
+  int64_t s0, ns;    // dynamic deal: the class's first ns tiles go to the warps s0 .. s0 + ns - 1 of the grid without a claim
   int32_t rot;       // chunks of the earlier classes, mod G
   int32_t mode;      // 0: not walked (small class / empty range); 1: tiles per warp (mode A); 2: chunks per CTA (mode B)
 };
 
 // the launch's schedule: one record per class (serial)
 ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, int64_t tile, int nwarps, int G, ClsRun* run) {
-  int64_t rot = 0;
+  int64_t rot = 0, wused = 0;
+  const int64_t W = (int64_t)G * nwarps;
   for (int ci = 0; ci < ncls; ++ci) {
     ClsRun r;
     const int64_t coff = cls[ci].offset, csize = cls[ci].size;
@@ -608,6 +637,11 @@ ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, i
     r.ch1 = (r.k1 + nwarps - 1) / nwarps;
     r.rot = (int32_t)(rot % G);
     if (r.mode) rot += r.ch1 - r.ch0;
+    // the first tiles of the stream are dealt statically, one per warp, so that no warp starts with an atomic
+    r.ntail = 0;
+    r.s0 = wused;
+    r.ns = 0;
+    if (r.mode == 1) { r.ns = r.k1 - r.k0 < W - wused ? r.k1 - r.k0 : W - wused; wused += r.ns; }
     run[ci] = r;
   }
 }
@@ -698,6 +732,7 @@ struct RingSrc {
   // producer cursor
   int pci;
   int64_t ptk, pk0, pk1, plo, phi;  // tile being copied, the class's tiles, class range
+  int64_t pdbase, pntail, pn;       // dynamic deal: deal index of claim 0, tiles of the costly tail, deal index of the current tile
   unsigned long long pend;          // dynamic deal: the next claim of this class (valid in lane 0)
   bool pdyn, pahead;                // the current class is dealt dynamically / with claims one tile ahead
   const T* pcbase;                  // first component of the class
@@ -731,11 +766,19 @@ struct RingSrc {
     return 0;
 #endif
   }
-  ST_HD int64_t claimed(unsigned long long raw) const {
+  // n-th tile of the class in deal order: the costly tail first (from the end), then the rest in address order;
+  // >= pk1 when the class is exhausted
+  ST_HD int64_t deal_tile(int64_t n) {
+    pn = n;
+    if (n < pntail) return pk1 - 1 - n;
+    const int64_t t = pk0 + (n - pntail);
+    return t < pk1 - pntail ? t : pk1;
+  }
+  ST_HD int64_t claimed(unsigned long long raw) {
 #ifdef __CUDA_ARCH__
-    return pk0 + (int64_t)__shfl_sync(0xffffffffu, raw, 0);
+    return deal_tile(pdbase + (int64_t)__shfl_sync(0xffffffffu, raw, 0));
 #else
-    return pk0 + (int64_t)raw;
+    return deal_tile(pdbase + (int64_t)raw);
 #endif
   }
   // enter the tile ptk of class pci: source range, queue entry, directory entry
@@ -772,9 +815,17 @@ struct RingSrc {
       // classes with many tiles per warp claim one tile ahead (the atomic's latency is never waited for); small
       // classes claim on demand, or the first warps to arrive would take two tiles each and leave none
       pahead = (r.k1 - r.k0) >= 4 * step;
-      const unsigned long long first = claim(ci);
-      if (pahead) pend = claim(ci);
-      tk = claimed(first);
+      pdbase = r.ns;
+      pntail = r.ntail;
+      const int64_t gw = (int64_t)cta * NW + warp;
+      if (gw >= r.s0 && gw < r.s0 + r.ns) {
+        tk = deal_tile(gw - r.s0);  // this warp's statically dealt tile of the class
+        if (pahead) pend = claim(ci);
+      } else {
+        const unsigned long long first = claim(ci);
+        if (pahead) pend = claim(ci);
+        tk = claimed(first);
+      }
     } else {
       tk = (r.ch0 + jc0(ci)) * NW + warp;
       if (tk < r.k0) tk += step;
@@ -792,7 +843,12 @@ struct RingSrc {
     if (pdyn) {
       if (pahead) {
         ptk = claimed(pend);
-        if (ptk < pk1) pend = claim(pci);
+        // the last 2 * step tiles (two per warp of the grid) are claimed on demand: a warp sitting on a claimed but
+        // unstarted tile while others have run dry is what the tail of the launch is made of
+        if (ptk < pk1) {
+          if ((pk1 - pk0) - pn > 2 * step) pend = claim(pci);
+          else pahead = false;
+        }
       } else {
         ptk = claimed(claim(pci));
       }
@@ -815,6 +871,9 @@ struct RingSrc {
     qtail = qhead = 0;
     qtail_i = qhead_i = 0;
     pend = 0;
+    pdbase = 0;
+    pntail = 0;
+    pn = 0;
     pdyn = false;
     pahead = false;
     cslot = 0;

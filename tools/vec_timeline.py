@@ -38,15 +38,15 @@ torch.cuda.synchronize()
 check(lib.st_set_tuning(b"vec_timeline", c_i64(1)))
 run()
 torch.cuda.synchronize()
-n = 148 * 16 + 4096
+n = 148 * 16 + 4096 + 4096 * 8
 raw = np.zeros(n, dtype=np.uint64)
 check(lib.st_debug_vec_timeline(raw.ctypes.data, c_i64(n)))
 ph = raw[:148 * 16].reshape(148, 16).astype(np.int64)
 live = ph[:, 0] > 0
 ph = ph[live]
 t0 = ph[:, 0].min()
-names = ["start", "cls+bars+runs", "stream started", "x/binom/cdesc", "small classes done"] + [f"class {i} begins" for i in range(8)] + \
-        ["-", "all warps done (ticket)", "end"]
+names = ["start", "cls+bars+runs", "stream started", "x/binom/cdesc+table", "small classes done (warp 0)"] + [f"class {i} begins" for i in range(5)] + \
+        ["all warps of the CTA done", "ticket taken", "last CTA: slots added", "-", "-", "end"]
 print(f"{live.sum()} CTAs; times in us after the first CTA start")
 for s, name in enumerate(names):
     col = ph[:, s]
@@ -54,10 +54,27 @@ for s, name in enumerate(names):
     if len(col) == 0:
         continue
     r = (col - t0) / 1e3
-    print(f"  [{s:2d}] {name:26s} min {r.min():8.2f}  med {np.median(r):8.2f}  max {r.max():8.2f}")
-wf = raw[148 * 16:].astype(np.int64)
-wf = wf[wf > 0]
+    print(f"  [{s:2d}] {name:30s} min {r.min():8.2f}  med {np.median(r):8.2f}  max {r.max():8.2f}")
+wf_all = raw[148 * 16:148 * 16 + 4096].astype(np.int64)
+wf = wf_all[wf_all > 0]
 if len(wf):
     r = (wf - t0) / 1e3
     q = np.percentile(r, [0, 5, 25, 50, 75, 95, 100])
     print("  warp finish times: " + "  ".join(f"p{p}={v:.1f}" for p, v in zip([0, 5, 25, 50, 75, 95, 100], q)))
+
+ce = raw[148 * 16 + 4096:].reshape(4096, 8).astype(np.int64)
+for ci in range(5):
+    col = ce[:, ci]
+    m = col > 0
+    if m.sum() == 0:
+        continue
+    r = (col[m] - t0) / 1e3
+    q = np.percentile(r, [0, 50, 95, 99, 100])
+    print(f"  warps leave class {ci}: " + "  ".join(f"p{p}={v:.1f}" for p, v in zip([0, 50, 95, 99, 100], q)))
+late = np.argsort(-wf_all)[:12]
+print("  latest warps (cta, warp, finish us, left class 3 at us, tiles walked, longest tile us (directory index), last tile began at us):")
+for w in late:
+    if wf_all[w] > 0:
+        print(f"    cta {w // 16:3d} warp {w % 16:2d}  {(wf_all[w] - t0) / 1e3:7.1f}  {(ce[w, 3] - t0) / 1e3 if ce[w, 3] > 0 else -1:7.1f}  {ce[w, 5]:3d}  {ce[w, 6] / 1e3:6.1f} ({ce[w, 2]})  {(ce[w, 7] - t0) / 1e3:7.1f}")
+m = wf_all > 0
+print(f"  tiles per warp: min {ce[m, 5].min()} med {np.median(ce[m, 5]):.0f} max {ce[m, 5].max()};  longest tile over all warps {ce[m, 6].max() / 1e3:.1f} us, median of the per-warp longest {np.median(ce[m, 6]) / 1e3:.1f} us")
