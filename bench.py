@@ -359,7 +359,7 @@ def run_gpu(args):
                        "l2": "input (549 MB per GPU) is larger than the 126 MB L2: no flush needed", "result": result},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n_comps), "peak_source": peak_src,
-                         "kernel": "vec_tail_kernel<double, 4> (one launch per step: streaming pass with the fused deterministic finalize)",
+                         "kernel": "vec_ring_kernel<double> (one launch per step: per-warp cp.async.bulk rings, dynamic tile deal, per-tile partial sums added in index order by the last CTA)",
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks.summary(),
             "gpu_launches": int(launches),

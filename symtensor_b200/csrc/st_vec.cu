@@ -7,15 +7,16 @@
 // kernel is HBM-bound (algorithmic bytes = sizeof(T) per packed component).
 //
 // Two kernels:
-//  * vec_tail_kernel ("tail table", the production path for ST_LAYOUT_PERMCLS).  Storage order is
-//    lexicographic in the distinct values, so for a fixed "head" (all values but the last tau values of
-//    the last run) the tail components are CONTIGUOUS in memory and their weights are a contiguous slice of
-//    a head-independent table  T[q] = prod_{u in q-th tau-combination} xrel[u]^mu  kept in shared memory.
-//    A warp walks the heads of its range with a warp-uniform odometer and streams each block as a
-//    coalesced dot product  hw * <A[block], T[slice]>  (per element: one LDG, one LDS, one FMA).
+//  * vec_ring_kernel (the production path for ST_LAYOUT_PERMCLS).  Storage order is lexicographic in the distinct
+//    values, so for a fixed "head" (all values but the last tau values of the last run) the tail components
+//    are CONTIGUOUS in memory and their weights are a contiguous slice of a head-independent table
+//    T[q] = prod_{u in q-th tau-combination} xrel[u]^mu  kept in shared memory (for tau == 2 at large dimensions: the
+//    suffix of that table that fits, the long first rows being formed on the fly).  A warp walks the heads of
+//    its tiles with a warp-uniform odometer; the components arrive through per-warp rings of cp.async.bulk
+//    copies, tiles are dealt to the warps dynamically, and every tile's sum has its own slot, so the result does
+//    not depend on the deal.
 //  * vec_generic_kernel (one full unrank per element; any layout; also the flat-layout path and the
 //    cross-check used by the tests).
-// Both write one fp64 partial per CTA; vec_finalize_kernel adds them in a fixed order (deterministic).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -36,11 +37,7 @@ static const int kMaxPartials = 4096;   // fp64 partial sums per launch (one per
 static const int kTilePartOff = kMaxPartials + 8;
 static const int64_t kWsSlots = (int64_t)1 << 19;  // 4 MB of fp64 slots
 static const int kMaxCounters = 2 + 256;  // ticket pair + one tile counter per class
-static const int kTailThreads = 512;    // 16 warps per CTA, one CTA per SM (the tail table fills shared memory)
-static int g_batch_slots = 4;           // 16-byte vectors per lane and batch; two batches in flight (tuning knob)
 static const int kBinomSmemMax = 40 * 1024;  // the binomial table is copied to shared memory when it is at most this big
-// tuning knob (st_set_tuning): bytes per tile
-static int g_tile_bytes = 16 * 1024;
 
 template <typename T>
 struct VecArgs {
@@ -177,7 +174,7 @@ __global__ void vec_dir_kernel(PlanView P, int64_t tile, const int64_t* __restri
 
 // CTA-wide build of the shared tail table (xr must be in place and visible); ends with a barrier
 template <typename T>
-__device__ __forceinline__ void build_shared_table(const PlanView& P, const TailStrategy& S, const T* xr, T* tbl, int nthreads = kTailThreads) {
+__device__ __forceinline__ void build_shared_table(const PlanView& P, const TailStrategy& S, const T* xr, T* tbl, int nthreads) {
   int64_t nA, nB;
   table_scratch(P.binom, P.rank, S.Rt, S.tau, &nA, &nB);
   for (int t = 2; t <= S.tau; ++t) {
@@ -185,318 +182,6 @@ __device__ __forceinline__ void build_shared_table(const PlanView& P, const Tail
     T* dst = table_level_buffer<T>(tbl, S.tbl_n, nA, S.tau, t);
     build_table_level<T>(P.binom, P.rank, S.Rt, t, xr, src, dst, threadIdx.x, nthreads);
     __syncthreads();
-  }
-}
-
-// Scheduling (device part of the plan): the packed range is walked CLASS BY CLASS (a class is one phase: its
-// tables are built once, then no CTA-wide barrier is needed until the next class).  Inside a class the work is
-// cut into TILES of `tile` components (16 KB) numbered in address order, and tile t belongs to warp
-// (t mod W) of the grid (W = all warps): at any moment the whole grid reads one compact window of a few tens
-// of MB that slides through the tensor, which is what the memory system wants (wide windows lose up to 2x,
-// tools/membench), every warp streams independently of the others (no per-tile barrier, no atomics), and the
-// per-warp sums are added in a fixed order -- the result is deterministic.
-//   mode A  (tau == 1: per-warp private tables; or a single-segment class: one shared table per class)
-//           tiles are per warp;
-//   mode B  (tau >= 2 and several segments: the shared table T depends on the segment) chunks of 16 tiles are
-//           per CTA, T is rebuilt with __syncthreads when the segment changes, warps split the chunk.
-// Shared memory: [T / private xr tables][xr: dim][xs: dim][blen: dim x i32][binomial table (optional)]
-//                [ClsInfo x ncls][ctrl]
-template <typename T, int U>
-__global__ void __launch_bounds__(kTailThreads, 1) vec_tail_kernel(VecArgs<T> a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  PlanView P = a.P;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int nwarps = kTailThreads / 32;
-  T* tbl = reinterpret_cast<T*>(smem_raw);
-  T* priv = tbl + (size_t)warp * P.dim;  // this warp's private xr table (tau == 1 classes); aliases the shared table
-  size_t off = ((size_t)a.tbl_cap * sizeof(T) + 15) / 16 * 16;
-  T* xr = reinterpret_cast<T*>(smem_raw + off);
-  T* xs = xr + P.dim;
-  off = (off + 2 * (size_t)P.dim * sizeof(T) + 15) / 16 * 16;
-  int32_t* blen = reinterpret_cast<int32_t*>(smem_raw + off);
-  off = (off + (size_t)P.dim * sizeof(int32_t) + 15) / 16 * 16;
-  int64_t* binom_s = reinterpret_cast<int64_t*>(smem_raw + off);
-  off += (size_t)a.binom_smem * sizeof(int64_t);
-  ClsInfo* cls_s = reinterpret_cast<ClsInfo*>(smem_raw + off);
-  off += (size_t)P.ncls * sizeof(ClsInfo);
-  ClassDesc* cdesc_s = reinterpret_cast<ClassDesc*>(smem_raw + off);  // class descriptors (when a.cdesc_smem)
-  off += a.cdesc_smem ? (size_t)P.ncls * sizeof(ClassDesc) : 0;
-  off = (off + 15) / 16 * 16;
-  WarpScratch& ws = reinterpret_cast<WarpScratch*>(smem_raw + off)[warp];
-  off += (size_t)nwarps * sizeof(WarpScratch);
-  TailCtrl* ctl = reinterpret_cast<TailCtrl*>(smem_raw + off);
-  if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
-  for (int i = threadIdx.x; i < P.dim; i += kTailThreads) xs[i] = a.x[i];
-  if (a.binom_smem) {
-    for (int i = threadIdx.x; i < a.binom_smem; i += kTailThreads) binom_s[i] = a.P.binom[i];
-    P.binom = binom_s;
-  }
-  if (a.cdesc_smem) {
-    const int nw = (int)(sizeof(ClassDesc) / 4) * P.ncls;
-    for (int i = threadIdx.x; i < nw; i += kTailThreads) reinterpret_cast<int32_t*>(cdesc_s)[i] = reinterpret_cast<const int32_t*>(a.P.cls)[i];
-    P.cls = cdesc_s;
-  }
-  for (int c = threadIdx.x; c < P.ncls; c += kTailThreads) {
-    cls_s[c].offset = a.P.cls[c].offset;
-    cls_s[c].size = a.P.cls[c].size;
-    cls_s[c].tile_base = a.tile_base ? a.tile_base[c] : 0;
-    cls_s[c].sbase = a.sbase ? a.sbase[c] : 0;
-    cls_s[c].S = a.strat[c];
-  }
-  __syncthreads();
-  int priv_cls = -1;       // (class, segment) the private table was built for -- warp-uniform
-  int64_t priv_seg = -1;
-  double priv_wE = 0.0;
-  const int64_t W = (int64_t)gridDim.x * nwarps;         // warps of the grid
-  const int64_t gw = (int64_t)blockIdx.x * nwarps + warp;  // this warp
-  const int64_t tile = a.tile_elems;
-  int64_t tile_base = 0;  // tiles of the classes before the current one (rotates the tile -> warp map)
-  double total = 0.0;
-  constexpr int kBatchElems = U * 32 * (16 / (int)sizeof(T));
-  T bufA[U][16 / sizeof(T)], bufB[U][16 / sizeof(T)];  // the stream's two register batches (see walk_range)
-
-  // ---- phase 0: SMALL classes (tau == 0 in the strategy), one component per thread with a full unrank of its
-  // index (the bulk form of the index enumerator): no tables, no barriers, all the grid's threads at once.
-  // The per-lane sums stay in `total` (fixed thread -> component map: deterministic).
-  {
-    int64_t sm_base = 0;  // components of the small classes before the current one
-    const int64_t nthreads = W * 32, tid = gw * 32 + lane;
-    for (int ci = 0; ci < P.ncls; ++ci) {
-      if (cls_s[ci].S.tau != 0) continue;
-      const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
-      const int64_t lo = (a.begin > coff ? a.begin : coff) - coff;
-      const int64_t hi = (a.end < coff + csize ? a.end : coff + csize) - coff;
-      if (lo >= hi) continue;
-      const ClassDesc& C = P.cls[ci];
-      const T* Acls = a.A + (coff - a.begin);
-      const int nvals = C.nvals;
-      const double gamma = (double)C.gamma;
-      for (int64_t p = lo + (tid - sm_base % nthreads + nthreads) % nthreads; p < hi; p += nthreads) {
-        const double v = (double)__ldcs(Acls + p);
-        double w = gamma;
-        if (a.sdir != nullptr) {
-          // the component's values come from the per-component directory of the small classes (written once per
-          // plan by the index enumerator): no unrank, no thread-local arrays
-          const uint4* q = reinterpret_cast<const uint4*>(a.sdir + (cls_s[ci].sbase + p));
-          const uint4 e0 = __ldg(q), e1 = __ldg(q + 1);
-          const uint32_t words[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
-#pragma unroll
-          for (int k = 0; k < ST_MAX_RANK; ++k) {
-            if (k < nvals) {
-              const int val = (int)((words[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
-              const double xv = (double)xs[val];
-              const int m = C.mult[k];
-              for (int mm = 0; mm < m; ++mm) w *= xv;
-            }
-          }
-        } else {
-          int32_t vals[ST_MAX_RANK];
-          permcls_unrank_vals(P, C, p, vals);
-          for (int k = 0; k < nvals; ++k) {
-            const double xv = (double)xs[vals[k]];
-            for (int m = 0; m < C.mult[k]; ++m) w *= xv;
-          }
-        }
-        total += v * w;
-      }
-      sm_base += hi - lo;
-    }
-  }
-
-  for (int ci = 0; ci < P.ncls; ++ci) {
-    if (cls_s[ci].S.tau == 0) continue;  // done in phase 0
-    const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;
-    // positions [lo, hi) of class ci inside the launch range
-    const int64_t lo = (a.begin > coff ? a.begin : coff) - coff;
-    const int64_t hi = (a.end < coff + csize ? a.end : coff + csize) - coff;
-    if (lo >= hi) continue;
-    const TailStrategy S = cls_s[ci].S;
-    const ClassDesc& C = P.cls[ci];
-    const T* Acls = a.A + (coff - a.begin);
-    const int64_t k0 = lo / tile, k1 = (hi + tile - 1) / tile;  // tiles k0 .. k1-1, tile k = [k*tile, (k+1)*tile)
-    if (S.tau == 1 || S.nE == 0) {
-      // ---- mode A
-      if (S.tau >= 2) {
-        // one shared table for the whole class (no earlier runs)
-        __syncthreads();  // everybody is done with the previous tables
-        if (threadIdx.x == 0) {
-          ctl->wE = unrank_earlier<T>(P, C, 0, xs, ctl->E, ws);
-          ctl->cur_cls = ci;
-          ctl->cur_seg = 0;
-        }
-        priv_cls = -1;  // the shared table overwrites the private ones
-        for (int uu = threadIdx.x; uu < S.Rt; uu += kTailThreads) {
-          xr[uu] = xrel_pow<T>(xs, ctl->E, 0, S.mu, uu);
-          blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
-        }
-        __syncthreads();
-        build_shared_table<T>(P, S, xr, tbl);
-      } else if (ctl->cur_cls != -1) {  // CTA-uniform: the private tables overwrite the shared table
-        __syncthreads();
-        if (threadIdx.x == 0) { ctl->cur_cls = -1; ctl->cur_seg = -1; }
-        __syncthreads();
-      }
-      const double wE0 = ctl->wE;
-      const int64_t dbase = cls_s[ci].tile_base;
-      int64_t j = (gw - tile_base % W + W) % W;  // first tile of this class that belongs to this warp
-      uint4 dn0 = make_uint4(0, 0, 0, 0), dn1 = dn0;  // the next tile's directory entry, fetched one tile ahead
-      auto fetch_entry = [&](int64_t t) {
-        const uint4* q = reinterpret_cast<const uint4*>(a.dir + t);
-        dn0 = __ldg(q);
-        dn1 = __ldg(q + 1);
-      };
-      if (a.dir && k0 + j < k1) fetch_entry(dbase + k0 + j);
-      bool preloaded = false;
-      int32_t* E = ws.E;
-      int32_t* u0 = ws.u0;
-      for (; k0 + j < k1; j += W) {
-        int64_t w0 = (k0 + j) * tile;
-        int64_t w1 = w0 + tile;
-        const bool have_dir = a.dir != nullptr && w0 >= lo;  // the tile starts inside the launch range
-        if (w0 < lo) w0 = lo;
-        if (w1 > hi) w1 = hi;
-        __syncwarp();
-        reinterpret_cast<uint4*>(&ws.de)[0] = dn0;
-        reinterpret_cast<uint4*>(&ws.de)[1] = dn1;
-        __syncwarp();
-        const DirEntry& de = ws.de;
-        if (a.dir && k0 + j + W < k1) fetch_entry(dbase + k0 + j + W);  // latency hidden behind this tile
-        if (S.tau >= 2) {
-          if (have_dir) {  // single-run class: the entry is the combination itself
-            for (int i = 0; i < S.gt; ++i) u0[i] = de.v[i];
-          }
-          // stream across tiles: this tile requests the first two batches of the warp's next tile when both
-          // are whole tiles (even number of batches, 16-byte aligned starts)
-          const int64_t nk = k0 + j + W;
-          const bool chain = (w1 - w0 == tile) && nk < k1 && nk * tile >= lo && (nk + 1) * tile <= hi && (tile % (2 * kBatchElems) == 0);
-          total += walk_range<T, U>(P, S, tbl, xr, blen, wE0, Acls, w0, w1, lane, have_dir ? u0 : nullptr, bufA, bufB, preloaded,
-                                    chain ? Acls + nk * tile : nullptr, ws);
-          preloaded = chain;
-          continue;
-        }
-        bool first = true;
-        while (w0 < w1) {  // private tables: segment by segment
-          const int64_t sidx = S.nE ? w0 / S.seg : 0;
-          const int64_t sbase = sidx * S.seg;
-          const int64_t q1 = (S.seg < w1 - sbase) ? S.seg : w1 - sbase;
-          const bool from_dir = first && have_dir;
-          if (from_dir) {
-            const double wE = dir_decode<T>(C, S, de, xs, E, u0);
-            if (priv_cls != ci || priv_seg != sidx) priv_wE = wE;
-          } else if (w0 == sbase) {
-            for (int i = 0; i < S.gt; ++i) u0[i] = i;  // a segment starts with the first combination
-          }
-          if (priv_cls != ci || priv_seg != sidx) {
-            if (!from_dir) priv_wE = unrank_earlier<T>(P, C, sidx, xs, E, ws);
-            __syncwarp();
-            for (int uu = lane; uu < S.Rt; uu += 32) priv[uu] = xrel_pow<T>(xs, E, S.nE, S.mu, uu);
-            __syncwarp();
-            priv_cls = ci;
-            priv_seg = sidx;
-          }
-          total += walk_range<T, U>(P, S, priv, priv, nullptr, priv_wE, Acls + sbase, w0 - sbase, q1, lane,
-                                    (from_dir || w0 == sbase) ? u0 : nullptr, bufA, bufB, false, nullptr, ws);
-          w0 = sbase + q1;
-          first = false;
-        }
-      }
-    } else {
-      // ---- mode B: chunks of nwarps tiles per CTA; the CTA rebuilds T once per segment
-      const int64_t ch0 = k0 / nwarps, ch1 = (k1 + nwarps - 1) / nwarps;
-      const int64_t chunk = tile * nwarps;
-      int64_t jc = ((int64_t)blockIdx.x - (tile_base / nwarps) % gridDim.x + gridDim.x) % gridDim.x;
-      for (; ch0 + jc < ch1; jc += gridDim.x) {
-        int64_t pos = (ch0 + jc) * chunk;
-        int64_t pend = pos + chunk;
-        if (pos < lo) pos = lo;
-        if (pend > hi) pend = hi;
-        while (pos < pend) {
-          const int64_t sidx = pos / S.seg;
-          const int64_t sbase = sidx * S.seg;
-          const int64_t q0 = pos - sbase;
-          const int64_t q1 = (S.seg < pend - sbase) ? S.seg : pend - sbase;
-          if (ctl->cur_cls != ci || ctl->cur_seg != sidx) {  // CTA-uniform
-            __syncthreads();  // everybody is done with the previous tables
-            if (threadIdx.x == 0) {
-              // the earlier runs of this segment: from the directory entry of a tile that starts inside the
-              // segment when there is one (cheap), else by unranking the segment index
-              const int64_t tk0 = (sbase + tile - 1) / tile;
-              if (a.dir != nullptr && tk0 * tile < sbase + S.seg && tk0 * tile < csize) {
-                ws.de = a.dir[cls_s[ci].tile_base + tk0];
-                ctl->wE = dir_decode<T>(C, S, ws.de, xs, ctl->E, ws.u0);
-              } else {
-                ctl->wE = unrank_earlier<T>(P, C, sidx, xs, ctl->E, ws);
-              }
-              ctl->cur_cls = ci;
-              ctl->cur_seg = sidx;
-            }
-            priv_cls = -1;  // the shared table overwrites the private ones
-            __syncthreads();
-            for (int uu = threadIdx.x; uu < S.Rt; uu += kTailThreads) {
-              xr[uu] = xrel_pow<T>(xs, ctl->E, S.nE, S.mu, uu);
-              blen[uu] = (int32_t)binom_at(P.binom, P.rank, S.Rt - 1 - uu, S.tau);
-            }
-            __syncthreads();
-            build_shared_table<T>(P, S, xr, tbl);
-          }
-          // warp w takes tile w of the chunk, clipped to this segment's piece [q0, q1): it starts either at a
-          // tile start (directory) or at the start of the segment (first combination)
-          {
-            const int64_t tk = (ch0 + jc) * nwarps + warp;  // tile index inside the class
-            int64_t w0 = tk * tile - sbase, w1 = w0 + tile;
-            const bool at_tile = w0 >= q0;
-            if (w0 < q0) w0 = q0;
-            if (w1 > q1) w1 = q1;
-            if (w0 < w1) {
-              int32_t* u0 = ws.u0;
-              const int32_t* ui = nullptr;
-              if (w0 == 0) {
-                for (int i = 0; i < S.gt; ++i) u0[i] = i;
-                ui = u0;
-              } else if (at_tile && a.dir != nullptr) {
-                __syncwarp();
-                ws.de = a.dir[cls_s[ci].tile_base + tk];
-                __syncwarp();
-                dir_decode<T>(C, S, ws.de, xs, ws.E, u0);
-                ui = u0;
-              }
-              total += walk_range<T, U>(P, S, tbl, xr, blen, ctl->wE, Acls + sbase, w0, w1, lane, ui, bufA, bufB, false, nullptr, ws);
-            }
-          }
-          pos = sbase + q1;
-        }
-      }
-    }
-    tile_base += k1 - k0;
-  }
-
-  // one partial per warp of the grid, added in index order by the last CTA to finish (deterministic; saves the
-  // second launch).  The ticket counter is self-resetting.
-  total = warp_sum(total);
-  if (lane == 0) a.partials[gw] = total;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long ticket = atomicAdd(a.counter, 1ULL);
-    const bool last = ticket == gridDim.x - 1;
-    if (last) {
-      a.counter[0] = 0ULL;
-      __threadfence();
-    }
-    ctl->last = last ? 1 : 0;
-  }
-  __syncthreads();
-  if (a.out != nullptr && ctl->last) {
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < W; i += kTailThreads) s += __ldcg(a.partials + i);
-    s = warp_sum(s);
-    if (lane == 0) ctl->red[warp] = s;
-    __syncthreads();
-    if (warp == 0) {
-      double t = lane < nwarps ? ctl->red[lane] : 0.0;
-      t = warp_sum(t);
-      if (lane == 0) *a.out = (T)t;
-    }
   }
 }
 
@@ -956,7 +641,7 @@ int g_force_tau = 0;  // test hook: force the tail length (0 = cost model)
 unsigned long long* g_timeline = nullptr;  // debug: device buffer of kTimelineSlots stamps (st_set_tuning vec_timeline 1)
 static const size_t kTimelineSlots = 148 * 16 + 4096 + 4096 * 8;
 int g_ring_direct = 1;                 // ring kernel: allow the table-free pair walk (2: with vec_force_tau 2, force it)
-int64_t g_ring_table_max = 64 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
+int64_t g_ring_table_max = 72 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
 int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
 struct StratKey {
@@ -990,7 +675,7 @@ static int g_ring_warps = 16;          // consumer warps per CTA
 static int g_ring_slots = 2;           // ring slots per warp
 static int g_ring_bytes = 4096;        // preferred bytes per slot (shrunk to 1536 / 1024 when the table needs the room)
 static int g_ring_bytes_max = 4096;    // slots grow up to this when shared memory is left over
-static int g_ring_tile_bytes = 32768;    // bytes per tile (directory granularity; rounded to whole slots)
+static int g_ring_tile_bytes = 49152;    // bytes per tile (directory granularity; rounded to whole slots)
 static std::map<StratKey, StratEntry> g_strats;
 
 static double dbinom(const HostPlan* hp, int64_t n, int k) {
@@ -1021,10 +706,9 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, std::vecto
                        reserve;
   if (fixed + 32 * esize > smem_budget) return false;  // x itself does not fit shared memory
   const int64_t cap = (int64_t)((smem_budget - fixed) / esize);
-  if (!reserve && cap < (int64_t)nwarps * dim) return false;  // vec_tail_kernel: the per-warp private tables alias the table
   if (cap < 32) return false;
   st.assign(hp->ncls, TailStrategy());
-  int64_t tbl_max = reserve ? 32 : std::max<int64_t>(32, (int64_t)nwarps * dim);
+  int64_t tbl_max = 32;
   for (int c = 0; c < hp->ncls; ++c) {
     const ClassDesc& C = hp->h_cls[c];
     TailStrategy& S = st[c];
@@ -1167,15 +851,17 @@ static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<Tai
   return e.smem_bytes <= kRingSmemBudget;
 }
 
-// `ring`: strategy of vec_ring_kernel (the tile size is part of it: `tile` is ignored); else of vec_tail_kernel
-static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, bool ring, StratEntry* out) {
+// strategy of vec_ring_kernel for (device, rank, dim, element size): tail lengths, ring geometry, tile size, directories
+static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
+  const bool ring = true;
+  int64_t tile = 0;
   const HostPlan* hp = get_host_plan(rank, dim);
   if (!hp) return ST_ERR_INVALID;
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_smu);
-  StratKey key{dev, rank, esize, ring ? 1 : 0, dim, ring ? 0 : tile};
+  StratKey key{dev, rank, esize, 1, dim, 0};
   auto it = g_strats.find(key);
   if (it != g_strats.end()) { *out = it->second; return ST_OK; }
   StratEntry e;
@@ -1188,7 +874,7 @@ static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, bool rin
   e.tbl_cap = 32;
   e.binom_smem = 0;
   e.smem_bytes = 0;
-  e.nwarps = kTailThreads / 32;
+  e.nwarps = g_ring_warps;
   e.ring_slots = 0;
   e.ring_elems = 0;
   e.priv_cap = 0;
@@ -1204,8 +890,6 @@ static int get_strategy(int rank, int64_t dim, int esize, int64_t tile, bool rin
       for (size_t c = 0; c < st.size(); ++c) { fprintf(stderr, " %d", st[c].tau); if (st[c].direct) fprintf(stderr, "d(k0=%d)", st[c].k0); }
       fprintf(stderr, "\n");
     }
-  } else {
-    e.supported = compute_tail_strategy(hp, esize, kTailThreads / 32, st, &e.tbl_cap, &e.binom_smem, &e.cdesc_smem, &e.smem_bytes, 0, 150.0);
   }
   if (e.supported) {
     rc = check_cuda(cudaMalloc(&e.d_strat, sizeof(TailStrategy) * hp->ncls), "cudaMalloc(strategy)");
@@ -1306,31 +990,6 @@ static int get_counter(cudaStream_t stream, unsigned long long** out) {
   return ST_OK;
 }
 
-template <typename T, int U>
-static int launch_tail_u(VecArgs<T>& a, const StratEntry& se, int64_t len, int* grid_out, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(vec_tail_kernel<T, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024),
-                        "cudaFuncSetAttribute");
-    if (rc) return rc;
-    attr_set = true;
-  }
-  // One resident CTA per SM; tiles are dealt round-robin to the warps of the grid (see the kernel).
-  const int nwarps = kTailThreads / 32;
-  const int64_t tile = a.tile_elems;
-  const int64_t ntiles = (len + tile - 1) / tile;
-  int64_t grid = std::min<int64_t>((int64_t)sm_count(), kMaxCtas);
-  grid = std::min<int64_t>(grid, kMaxPartials / nwarps);
-  grid = std::max<int64_t>(1, std::min<int64_t>(grid, (ntiles + nwarps - 1) / nwarps));
-  {
-    int rc = get_counter(stream, &a.counter);
-    if (rc) return rc;
-  }
-  vec_tail_kernel<T, U><<<(int)grid, kTailThreads, se.smem_bytes, stream>>>(a);
-  *grid_out = (int)grid * nwarps;  // number of partials written
-  return ST_OK;
-}
-
 template <typename T>
 static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, int64_t len, int* grid_out, cudaStream_t stream) {
   static bool attr_set = false;
@@ -1374,14 +1033,6 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
   vec_ring_kernel<T><<<(int)grid, nwarps * 32, se.smem_bytes, stream>>>(a, sched);
   *grid_out = 1;  // the kernel leaves the launch's sum in partials[0]
   return ST_OK;
-}
-
-template <typename T>
-static int launch_tail(VecArgs<T>& a, const StratEntry& se, int64_t len, int* grid_out, cudaStream_t stream) {
-  switch (g_batch_slots) {
-    case 2: return launch_tail_u<T, 2>(a, se, len, grid_out, stream);
-    default: return launch_tail_u<T, 4>(a, se, len, grid_out, stream);
-  }
 }
 
 // Launch the main pass over [begin, end): writes `*grid_out` fp64 partials to `partials`.  With `d_out` the
@@ -1429,13 +1080,8 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   StratEntry se;
   se.supported = false;
   if (layout == ST_LAYOUT_PERMCLS && rank > 0 && g_variant != 1) {
-    a.tile_elems = std::max<int64_t>(ST_CLASS_ALIGN, (g_tile_bytes / (int64_t)sizeof(T)) / ST_CLASS_ALIGN * ST_CLASS_ALIGN);
-    rc = get_strategy(rank, dim, (int)sizeof(T), a.tile_elems, g_variant != 3, &se);
+    rc = get_strategy(rank, dim, (int)sizeof(T), &se);
     if (rc) return rc;
-    if (g_variant != 3 && !se.supported) {  // no room for the rings: the register-streamed tail kernel may still fit
-      rc = get_strategy(rank, dim, (int)sizeof(T), a.tile_elems, false, &se);
-      if (rc) return rc;
-    }
     if (!se.supported && g_variant == 2) { set_error("tail-table kernel unavailable for dim %lld", (long long)dim); return ST_ERR_UNSUPPORTED; }
   }
   if (se.supported) {
@@ -1451,17 +1097,13 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
     a.ring_slots = se.ring_slots;
     a.ring_elems = se.ring_elems;
     a.priv_cap = se.priv_cap;
-    if (se.ring_slots > 0) {
-      a.tile_elems = se.tile_elems;
-      if (ring_ws) a.partials = ring_ws;
-      rc = launch_ring<T>(a, se, get_host_plan(rank, dim), end - begin, grid_out, stream);
-    } else {
-      rc = launch_tail<T>(a, se, end - begin, grid_out, stream);
-    }
+    a.tile_elems = se.tile_elems;
+    if (ring_ws) a.partials = ring_ws;
+    rc = launch_ring<T>(a, se, get_host_plan(rank, dim), end - begin, grid_out, stream);
     if (rc) return rc;
     count_launch();
     if (fused) *fused = d_out != nullptr;
-    return check_cuda(cudaGetLastError(), "vec_tail_kernel");
+    return check_cuda(cudaGetLastError(), "vec_ring_kernel");
   }
   const int64_t n = end - begin;
   int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
@@ -1656,8 +1298,6 @@ int st_set_tuning(const char* key, int64_t value) {
       return ST_OK;
     }
   }
-  if (k == "vec_batch_slots" && (value == 2 || value == 4)) { g_batch_slots = (int)value; return ST_OK; }
-  if (k == "vec_tile_bytes" && value >= 1024 && value <= (1 << 28)) { g_tile_bytes = (int)value; return ST_OK; }
   if (k == "vec_force_tau" && value >= 0 && value <= ST_MAX_RANK) {
     g_force_tau = (int)value;
     std::lock_guard<std::mutex> lk(g_smu);
@@ -1676,7 +1316,7 @@ int st_debug_vec_timeline(unsigned long long* h_out, int64_t n) {
 }
 
 int st_set_vec_variant(int variant) {
-  if (variant < 0 || variant > 3) { set_error("variant must be 0 .. 3"); return ST_ERR_INVALID; }
+  if (variant < 0 || variant > 2) { set_error("variant must be 0, 1 or 2"); return ST_ERR_INVALID; }
   g_variant = variant;
   std::lock_guard<std::mutex> lk(g_smu);
   g_strats.clear();  // strategies depend on the variant (old device tables are leaked: test hook)

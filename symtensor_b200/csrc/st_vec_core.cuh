@@ -40,7 +40,6 @@ struct TailCtrl {
   int32_t E[ST_MAX_RANK];  // values of the earlier runs, ascending
   int32_t cur_cls;
   int64_t cur_seg;
-  long long item[2];       // work item broadcast (dynamic scheduling), double-buffered
   int32_t last;            // this CTA is the last one to finish (fused finalize)
 };
 
@@ -136,253 +135,12 @@ __device__ __forceinline__ void comb_unrank_warp(const int64_t* __restrict__ tbl
 }
 #endif
 
-// one 16-byte vector of components (streaming load: every component is read exactly once)
-template <typename T>
-ST_HD void ld_vec16(const T* __restrict__ p, T* v) {
-#ifdef __CUDA_ARCH__
-  if (sizeof(T) == 8) {
-    const double2 r = __ldcs(reinterpret_cast<const double2*>(p));
-    v[0] = (T)r.x;
-    v[1] = (T)r.y;
-  } else {
-    const float4 r = __ldcs(reinterpret_cast<const float4*>(p));
-    v[0] = (T)r.x;
-    v[1] = (T)r.y;
-    v[2 % (16 / (int)sizeof(T))] = (T)r.z;
-    v[3 % (16 / (int)sizeof(T))] = (T)r.w;
-  }
-#else
-  for (int k = 0; k < 16 / (int)sizeof(T); ++k) v[k] = p[k];
-#endif
-}
-
 // ------------------------------------------------------------------------------------------------------
-// walk_range: one warp's walk over segment positions [q0, q1) of one segment (q1 - q0 < 2^30).
-//
-// Memory and index arithmetic are DECOUPLED.  The components are fetched in BATCHES of U slots (a slot is one
-// 16-byte vector per lane: 512 contiguous bytes per warp), all U loads of a batch issued back to back into
-// registers; two batches are kept (one being consumed, the next in flight) so a warp always has loads
-// outstanding.  Batches start at the 16-byte boundary at or below the range start and ignore block boundaries.  The odometer hands out "pieces" (block ∩ range, positions relative to q0):
-//     weight(idx) = hw * tbl[toff + idx]   for idx in [pb, pe)
-// A batch inside one piece takes the fast path (per 16-byte vector: one LDG.128, VEC table loads, VEC FMAs);
-// otherwise the batch is consumed piece by piece with per-element predicates.  The warp-uniform odometer's
-// common step -- increment the last head value -- costs a handful of instructions; carries take the general
-// path over the local arrays u[] / pref[].  `tbl` is the tail table (T for tau >= 2, xr for tau == 1), `xr`
-// the head-factor table, `blen` the optional table blen[u] = C(Rt-1-u, tau) of block lengths (nullptr:
-// computed from the binomial table).  `u_init` is the last run's combination at q0 when the caller knows it (tile
-// directory, start of a segment); otherwise it is unranked here, after the first two batches have been requested.
-// The same code runs on the host (tests/emu replays it lane by lane).
-// ------------------------------------------------------------------------------------------------------
-template <typename T, int U>
-ST_HD double walk_range(const PlanView& P, const TailStrategy& S, const T* __restrict__ tbl, const T* __restrict__ xr,
-                        const int32_t* __restrict__ blen, double wE, const T* __restrict__ Aseg, int64_t q0, int64_t q1, int lane,
-                        const int32_t* u_init, T (&bufA)[U][16 / sizeof(T)], T (&bufB)[U][16 / sizeof(T)], bool preloaded,
-                        const T* __restrict__ next_ap, WarpScratch& ws) {
-  ST_ASSUME_SHARED(tbl);
-  ST_ASSUME_SHARED(xr);
-  constexpr int VEC = 16 / (int)sizeof(T);  // components per 16-byte vector
-  constexpr int SLOT = 32 * VEC;            // components per slot
-  constexpr int BATCH = U * SLOT;
-  const int64_t* __restrict__ bt = P.binom;
-  const int rk = P.rank;
-  const int gt = S.gt, hn = S.hn, tau = S.tau, Rt = S.Rt;
-  const int tbl_n = (int)S.tbl_n;
-  const int n = (int)(q1 - q0);
-  const T* __restrict__ ap = Aseg + q0;
-  // components between the 16-byte boundary at or below `ap` and `ap` (they belong to whoever owns them: masked out)
-  const int a_pre = (int)(((uintptr_t)ap & 15u) / sizeof(T));
-  const T* __restrict__ lp = ap - a_pre + lane * VEC;  // this lane's vector of slot 0 of the batch at position -a_pre
-  int pos = -a_pre;                                    // position (relative to q0) of the current batch
-  // bufA / bufB: two batches in registers, one being consumed, one in flight.  They belong to the caller so that
-  // the stream can continue ACROSS ranges: with `next_ap` (16-byte aligned start of the caller's next range, at
-  // least two whole batches long; only legal when this range has an even number of batches) the first two
-  // batches of the next range are requested as soon as the buffers free up, and the next call passes
-  // `preloaded`.
-  // fetch the batch at position p (whole vectors while they end inside the range, single components up to n,
-  // zeros beyond: only the last batch of a range is partial)
-  auto load = [&](T (&buf)[U][VEC], int p) {
-    const T* __restrict__ bp = lp + (p + a_pre);
-    if (p + BATCH <= n) {
-#pragma unroll
-      for (int s = 0; s < U; ++s) ld_vec16(bp + s * SLOT, buf[s]);
-    } else {
-#pragma unroll
-      for (int s = 0; s < U; ++s) {
-        const int i0 = p + s * SLOT + lane * VEC;
-        if (i0 + VEC <= n) {
-          ld_vec16(bp + s * SLOT, buf[s]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) buf[s][k] = (i0 + k < n && i0 + k >= 0) ? bp[s * SLOT + k] : T(0);
-        }
-      }
-    }
-  };
-  if (!preloaded) {
-    load(bufA, pos);
-    if (pos + BATCH < n) load(bufB, pos + BATCH);
-  }
-  int nx = 0;  // batches of the next range requested so far
-  auto load_next = [&](T (&buf)[U][VEC]) {
-    const T* __restrict__ bp = next_ap + nx * BATCH + lane * VEC;
-#pragma unroll
-    for (int s = 0; s < U; ++s) ld_vec16(bp + s * SLOT, buf[s]);
-    ++nx;
-  };
-
-  // ---- odometer state at q0
-  int32_t* u = ws.u;       // head combination (relabelled values), warp-uniform; slow path only
-  double* pref = ws.pref;  // pref[i] = wE * prod_{j<i} xr[u[j]];                 slow path only
-  if (u_init) {
-    for (int i = 0; i < gt; ++i) u[i] = u_init[i];  // from the tile directory / the start of a segment
-  } else {
-#ifdef __CUDA_ARCH__
-    comb_unrank_warp(bt, rk, q0, Rt, gt, u, lane);
-#else
-    comb_unrank(bt, rk, q0, Rt, gt, u);
-#endif
-  }
-  const int tq = (int)comb_rank(bt, rk, u + hn, Rt, tau);  // table index of the first tail
-  pref[0] = wE;
-  for (int i = 0; i < hn; ++i) pref[i + 1] = pref[i] * (double)xr[u[i]];
-  int u_last = hn ? u[hn - 1] : -1;           // == u[hn-1]
-  double pref_prev = hn ? pref[hn - 1] : wE;  // == pref[hn-1]
-  double hw = pref[hn];
-  int pb = 0;                                  // current piece [pb, pe), positions relative to q0
-  int pe = (tbl_n - tq < n) ? tbl_n - tq : n;
-  int toff = tq;
-  T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);  // per-lane partials of the current piece (independent FMA chains)
-  double total = 0.0;                            // per-lane running total
-
-  // next block: lexicographic successor of the head combination
-  auto advance = [&]() {
-    pb = pe;
-    if (hn == 0) { pe = n; return; }  // defensive: a segment with hn == 0 is a single block
-    if (u_last + 1 <= Rt - tau - 1) {
-      ++u_last;  // fast path: no carry
-    } else {
-      u[hn - 1] = u_last;
-      int j = hn - 1;
-      while (j >= 0 && u[j] + 1 > Rt - (gt - j)) --j;
-      if (j < 0) { pe = n; return; }  // defensive: cannot happen inside a segment
-      ++u[j];
-      for (int k = j + 1; k < hn; ++k) u[k] = u[k - 1] + 1;
-      for (int k = j; k < hn - 1; ++k) pref[k + 1] = pref[k] * (double)xr[u[k]];
-      u_last = u[hn - 1];
-      pref_prev = pref[hn - 1];
-    }
-    hw = pref_prev * (double)xr[u_last];
-    // first tail of the new head is (b+1, b+2, ..), b = u_last: block length C(Rt-1-b, tau), at the table's end
-    const int bl = tau == 1 ? Rt - 1 - u_last : (blen ? blen[u_last] : (int)binom_at(bt, rk, Rt - 1 - u_last, tau));
-    toff = tbl_n - bl - pb;
-    pe = (bl < n - pb) ? pb + bl : n;
-  };
-  auto flush = [&]() {
-    total += hw * (((double)s0 + (double)s1) + ((double)s2 + (double)s3));
-    s0 = T(0);
-    s1 = T(0);
-    s2 = T(0);
-    s3 = T(0);
-  };
-  // slot s of a batch, entirely inside the current piece: no predicates
-  auto slot_full = [&](const T (&v)[VEC], const T* __restrict__ tp, int s) {
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const T t = tp[k];
-      switch ((s * VEC + k) & 3) {
-        case 0: s0 += v[k] * t; break;
-        case 1: s1 += v[k] * t; break;
-        case 2: s2 += v[k] * t; break;
-        default: s3 += v[k] * t; break;
-      }
-    }
-  };
-
-  // consume the batch at `pos`, valid up to bend = min(pos + BATCH, n); invariant on entry: pb <= max(pos, 0) < pe
-  auto consume = [&](T (&cur)[U][VEC]) {
-    const int bend = (pos + BATCH < n) ? pos + BATCH : n;
-    if (pb <= pos && pe >= pos + BATCH) {
-      // one piece covers the whole batch
-      const T* __restrict__ tp = tbl + (toff + pos + lane * VEC);
-#pragma unroll
-      for (int s = 0; s < U; ++s) slot_full(cur[s], tp + s * SLOT, s);
-      if (pe == bend) {
-        flush();
-        if (pe < n) advance();
-      }
-      return;
-    }
-    while (true) {
-      // the part of the current piece inside this batch: slots it covers entirely take the plain path, the
-      // (at most two) slots holding its ends are predicated per component
-#pragma unroll
-      for (int s = 0; s < U; ++s) {
-        const int sb = pos + s * SLOT;
-        if (pe > sb && pb < sb + SLOT) {  // the piece overlaps this slot (warp-uniform)
-          if (pb <= sb && pe >= sb + SLOT) {
-            slot_full(cur[s], tbl + (toff + sb + lane * VEC), s);
-          } else {
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-              const int idx = sb + lane * VEC + k;
-              const bool in = (idx >= pb) & (idx < pe);
-              const T tv = tbl[toff + (in ? idx : pb)];
-              s0 += (in ? cur[s][k] : T(0)) * tv;
-            }
-          }
-        }
-      }
-      if (pe > bend) break;  // the piece continues in the next batch
-      flush();
-      if (pe >= n) break;    // end of the range
-      advance();
-      if (pb >= bend) break; // the next piece starts with the next batch
-    }
-  };
-
-  while (true) {
-    // tight run: while the current piece covers the two batches in registers and the two batches after them are
-    // whole, stream with no per-batch bookkeeping (per 16-byte vector: one LDG.128, VEC table loads, VEC FMAs)
-    if (pb <= pos && pos + 2 * BATCH <= pe && pos + 4 * BATCH <= n) {
-      const T* __restrict__ tp = tbl + (toff + pos + lane * VEC);
-      const T* __restrict__ gp = lp + (pos + a_pre) + 2 * BATCH;  // this lane's vector of the batch after next
-      int run = (pe - pos) / (2 * BATCH);
-      const int run_n = (n - pos - 2 * BATCH) / (2 * BATCH);
-      if (run_n < run) run = run_n;
-      pos += run * (2 * BATCH);
-      for (; run > 0; --run) {
-#pragma unroll
-        for (int s = 0; s < U; ++s) slot_full(bufA[s], tp + s * SLOT, s);
-#pragma unroll
-        for (int s = 0; s < U; ++s) ld_vec16(gp + s * SLOT, bufA[s]);
-#pragma unroll
-        for (int s = 0; s < U; ++s) slot_full(bufB[s], tp + BATCH + s * SLOT, s);
-#pragma unroll
-        for (int s = 0; s < U; ++s) ld_vec16(gp + BATCH + s * SLOT, bufB[s]);
-        tp += 2 * BATCH;
-        gp += 2 * BATCH;
-      }
-      if (pe == pos) {  // the piece ended exactly here (pos < n: two more batches were loaded)
-        flush();
-        advance();
-      }
-    }
-    consume(bufA);
-    pos += BATCH;
-    if (pos + BATCH < n) load(bufA, pos + BATCH);
-    else if (next_ap != nullptr && nx < 2) load_next(bufA);
-    if (pos >= n) break;
-    consume(bufB);
-    pos += BATCH;
-    if (pos + BATCH < n) load(bufB, pos + BATCH);
-    else if (next_ap != nullptr && nx < 2) load_next(bufB);
-    if (pos >= n) break;
-  }
-  return total + hw * (((double)s0 + (double)s1) + ((double)s2 + (double)s3));
-}
-
-// ------------------------------------------------------------------------------------------------------
-// walk_tile: the walk of the ring kernel (vec_ring_kernel, st_vec.cu).  Same odometer as walk_range, but the
+// walk_tile: one warp's walk over positions [q0, q0 + n) of one segment (vec_ring_kernel, st_vec.cu).  The odometer
+// hands out "pieces" (block ∩ range, positions relative to q0) with  weight(idx) = hw * tbl[toff + idx]; its common
+// step -- increment the last head value -- costs a handful of warp-uniform instructions, carries take the general
+// path over the arrays u[] / pref[] of the warp's scratch.  `u_init` is the last run's combination at q0 when the
+// caller knows it (tile directory, start of a segment); otherwise it is unranked here.  The
 // components are NOT fetched here: they arrive in shared memory through the warp's ring of cp.async.bulk
 // copies (the memory system runs ahead on its own), and this function only multiplies what is already
 // on chip.  `src.chunk(k)` hands out a pointer to the elements [k * Bel, (k + 1) * Bel) of the warp's
@@ -423,7 +181,7 @@ ST_HD double walk_tile(const PlanView& P, const TailStrategy& S, const T* __rest
     }
     return xr[uu];
   };
-  // ---- odometer state at q0 (see walk_range)
+  // ---- odometer state at q0
   int32_t* u = ws.u;
   double* pref = ws.pref;
   if (u_init) {

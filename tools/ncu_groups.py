@@ -52,7 +52,6 @@ def main():
     agg = load(sys.argv[1])
     core = markers(os.path.join(ROOT, "symtensor_b200/csrc/st_vec_core.cuh"), [
         ("core: helpers (unrank_earlier, xrel_pow, comb_unrank_warp)", "ST_HD double unrank_earlier("),
-        ("core: old walk_range", "ST_HD double walk_range("),
         ("walk: init + advance", "ST_HD double walk_tile(const PlanView& P"),
         ("walk: row walk", "auto row_range = [&]"),
         ("walk: sub-chunk / piece control", "const int Bel = src.bel();"),
@@ -72,8 +71,8 @@ def main():
         ("kernel: (other kernels)", "__global__ void vec_finalize_kernel"),
         ("kernel: prologue", "vec_ring_kernel(const __grid_constant__"),
         ("kernel: prologue table build", "// the first class with a class-wide table"),
-        ("kernel: small classes", "// ---- 3. SMALL classes"),
-        ("kernel: class loop setup", "// ---- 4. tail-table classes, in stream order"),
+        ("kernel: small classes", "// ---- 4. SMALL classes"),
+        ("kernel: class loop setup", "// ---- 3. tail-table classes, in stream order"),
         ("kernel: mode A tile loop", "while (src.head_is(ci)) {"),
         ("kernel: mode B", "// ---- mode B: chunks of nwarps tiles per CTA (static deal)"),
         ("kernel: epilogue (ticket, final reduce)", "// one partial per warp of the grid, added in index order by the last CTA"),

@@ -51,19 +51,18 @@ def main():
         print(f"r{rank} d{dim} {str(tdt)[6:]} OLD tail kernel: {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s  val={val:.12g}", flush=True)
         check(lib.st_set_vec_variant(0))
     combos = []
-    for warps, slots, nbytes, tmax in [(16, 3, 2048, 96), (16, 3, 2048, 112), (16, 3, 2048, 80), (16, 2, 4096, 80), (16, 2, 4096, 64), (16, 2, 3072, 96),
-                                       (16, 2, 3584, 88), (16, 4, 2048, 64), (12, 3, 3072, 96), (12, 2, 4096, 112), (16, 2, 2048, 128)]:
+    for warps, slots, nbytes, tmax in [(16, 2, 4096, 64), (16, 2, 4096, 56), (16, 2, 4096, 72), (16, 2, 4096, 48), (16, 2, 3584, 80), (16, 2, 3072, 96),
+                                       (16, 3, 2560, 64), (14, 2, 4096, 80), (12, 2, 4096, 96), (16, 2, 4608, 48), (16, 2, 5120, 40)]:
         combos.append((warps, slots, nbytes, 32768, tmax))
-    for tile in (16384, 65536):
-        combos.append((16, 3, 2048, tile, 96))
-        combos.append((16, 2, 4096, tile, 80))
+    for tile in (16384, 24576, 49152, 65536):
+        combos.append((16, 2, 4096, tile, 64))
     if "--static" in sys.argv:
         check(lib.st_set_tuning(b"vec_ring_dynamic", c_i64(0)))
     for warps, slots, nbytes, tile, tmax in combos:
         check(lib.st_set_tuning(b"vec_ring_table_max", c_i64(tmax * 1024)))
         check(lib.st_set_tuning(b"vec_ring_warps", c_i64(warps)))
         check(lib.st_set_tuning(b"vec_ring_slots", c_i64(slots)))
-        check(lib.st_set_tuning(b"vec_ring_bytes", c_i64(min(nbytes, 2048))))
+        check(lib.st_set_tuning(b"vec_ring_bytes", c_i64(nbytes)))
         check(lib.st_set_tuning(b"vec_ring_bytes_max", c_i64(nbytes)))
         check(lib.st_set_tuning(b"vec_ring_tile_bytes", c_i64(tile)))
         try:
