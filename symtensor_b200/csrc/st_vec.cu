@@ -32,9 +32,12 @@ namespace st {
 
 static const int kMaxCtas = 148 * 8;
 static const int kMaxPartials = 4096;   // fp64 partial sums per launch (one per warp of the grid / per CTA)
-// vec_ring_kernel's workspace: [0] the launch's sum, [1, 1 + warps) per-warp sums (small classes), then one slot per
-// tile of the whole tensor (kTilePartOff + directory index); the tile size grows so that the tiles fit
-static const int kTilePartOff = kMaxPartials + 8;
+// vec_ring_kernel's workspace: [0] the launch's sum, [8, 8 + warps) per-warp sums (small classes), then one 32-byte
+// slot per tile of the whole tensor (kTilePartOff + 4 * directory index); the tile size grows so that the tiles fit.
+// Every store to it is a whole, aligned 32-byte sector: 8-byte stores scattered over time leave partially written
+// sectors behind, and reading those back (and fencing them) cost the last CTA ~15 us
+static const int kWarpPartOff = 8;       // per-warp sums start here (64-byte aligned: a CTA's sums are whole sectors)
+static const int kTilePartOff = kMaxPartials + 16;  // per-tile sums: one 32-byte sector each (the sum, then zeros)
 static const int64_t kWsSlots = (int64_t)1 << 19;  // 4 MB of fp64 slots
 static const int kMaxCounters = 2 + 256;  // ticket pair + one tile counter per class
 static const int kBinomSmemMax = 40 * 1024;  // the binomial table is copied to shared memory when it is at most this big
@@ -196,6 +199,30 @@ __device__ __forceinline__ void build_shared_table(const PlanView& P, const Tail
 // how fast the arithmetic runs: the index arithmetic (odometer steps, table rebuilds, class changes) overlaps
 // with the memory stream instead of stalling it.  A warp's stream is the concatenation of its tiles, so the
 // ring also prefetches ACROSS tiles and classes (the first copies are issued before the tables are built).
+// Final reduction of vec_ring_kernel (last CTA): this thread's share of the concatenated slot ranges in ctl.  Its own
+// function, not inlined: inside the kernel the register allocator serialised the loads (one L2 round trip per
+// slot, ~10 us); here 16 slots are requested before the first is added.
+__device__ __noinline__ double reduce_slots(const TailCtrl* ctl, int tid, int nthreads, bool first_pass) {
+  const int n = ctl->red_n;
+  double s = 0.0;
+  for (int r = 0; r < n; ++r) {
+    const int64_t len = ctl->red_start[r + 1] - ctl->red_start[r];
+    const int stride = (r == 0 && first_pass) ? 1 : 4;  // per-warp sums are dense, tile sums one per 32-byte sector
+    const double* p = ctl->red_ptr[r];
+    for (int64_t base = tid; base < len; base += 16 * (int64_t)nthreads) {
+      double v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int64_t idx = base + j * (int64_t)nthreads;
+        v[j] = idx < len ? __ldcg(p + stride * idx) : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s += v[j];
+    }
+  }
+  return s;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant__ VecArgs<T> a, const __grid_constant__ RingSched sched) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -340,7 +367,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   double* tile_part = a.partials + kTilePartOff;
   auto store_tile = [&](int64_t slot, double v) {
     v = warp_sum(v);
-    if (lane == 0) tile_part[slot] = v;
+    if (lane < 4) tile_part[slot * 4 + lane] = lane == 0 ? v : 0.0;  // one aligned 32-byte sector
   };
   for (int ci = 0; ci < P.ncls; ++ci) {
     const ClsRun rr = run[ci];
@@ -574,7 +601,12 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   }
   // one partial per warp of the grid, added in index order by the last CTA to finish (deterministic)
   total = warp_sum(total);
-  if (lane == 0) a.partials[1 + gw] = total;
+  if (lane == 0) ctl->red[warp] = total;
+  __syncthreads();
+  if (warp == 0) {  // the CTA's per-warp sums as whole sectors (slots beyond nwarps up to a multiple of 4: zeros)
+    const int nw4 = (nwarps + 3) & ~3;
+    if (lane < nw4) a.partials[kWarpPartOff + (int64_t)blockIdx.x * nw4 + lane] = lane < nwarps ? ctl->red[lane] : 0.0;
+  }
   __syncthreads();
   stamp(10);
   if (threadIdx.x == 0) {
@@ -592,27 +624,34 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   if (ctl->last) {
     // the last CTA adds the per-warp sums (small classes) and the per-tile sums in index order, and resets the counters
     double s = 0.0;
-    auto add_slots = [&](const double* p, int64_t i0, int64_t i1) {  // fixed thread -> slot map; 16-byte loads, 20 in flight
-      if (i0 < i1 && ((uintptr_t)(p + i0) & 15u)) {  // peel to a 16-byte boundary
-        if (threadIdx.x == 0) s += __ldcg(p + i0);
-        ++i0;
+    // All slot ranges (per-warp sums, then the tiles of every walked class) form one concatenated index space with a
+    // fixed thread -> slot map; every thread requests its (up to 32) slots before it adds any: one round trip to L2.
+    int ci_next = 0;
+    bool first_pass = true;
+    while (first_pass || ci_next < P.ncls) {
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int n = 0;
+        int64_t pos = 0;
+        if (first_pass) { ctl->red_start[0] = 0; ctl->red_ptr[0] = a.partials + kWarpPartOff; pos = (int64_t)G * ((nwarps + 3) & ~3); n = 1; }
+        int c = ci_next;
+        for (; c < P.ncls && n < ST_MAX_RED; ++c) {
+          if (!run[c].mode) continue;
+          ctl->red_start[n] = pos;
+          ctl->red_ptr[n] = tile_part + 4 * (cls_s[c].tile_base + run[c].k0);
+          pos += run[c].k1 - run[c].k0;
+          ++n;
+        }
+        ctl->red_start[n] = pos;
+        ctl->red_n = n;
+        ctl->item_next = c;
       }
-      const int64_t nv = (i1 - i0) >> 1;
-      const double2* pv = reinterpret_cast<const double2*>(p + i0);
-      for (int64_t i = threadIdx.x; i < nv; i += 20 * (int64_t)nthreads) {
-        double2 v[20];
-#pragma unroll
-        for (int j = 0; j < 20; ++j) v[j] = (i + j * (int64_t)nthreads < nv) ? __ldcg(pv + i + j * (int64_t)nthreads) : make_double2(0.0, 0.0);
-#pragma unroll
-        for (int j = 0; j < 20; ++j) s += v[j].x + v[j].y;
-      }
-      if (((i1 - i0) & 1) && threadIdx.x == 1) s += __ldcg(p + i1 - 1);
-    };
-    add_slots(a.partials + 1, 0, W);
-    for (int ci = 0; ci < P.ncls; ++ci) {
-      if (!run[ci].mode) continue;
-      add_slots(tile_part + cls_s[ci].tile_base, run[ci].k0, run[ci].k1);
+      __syncthreads();
+      s += reduce_slots(ctl, threadIdx.x, nthreads, first_pass);
+      ci_next = ctl->item_next;
+      first_pass = false;
     }
+    stamp(14);
     for (int c = threadIdx.x; c < P.ncls; c += nthreads) a.counter[2 + c] = 0ULL;
     stamp(12);
     s = warp_sum(s);
@@ -844,7 +883,7 @@ static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<Tai
   {
     // one workspace slot per tile of the whole tensor: grow the tiles until they fit
     auto total_tiles = [&](int64_t te) { int64_t n = 0; for (int c = 0; c < hp->ncls; ++c) n += (hp->h_cls[c].size + te - 1) / te; return n; };
-    while (total_tiles(nsub * e.ring_elems) > kWsSlots - kTilePartOff) nsub *= 2;
+    while (4 * total_tiles(nsub * e.ring_elems) > kWsSlots - kTilePartOff) nsub *= 2;
   }
   e.tile_elems = nsub * e.ring_elems;
   e.smem_bytes = ring_layout(esize, hp->dim, e.tbl_cap, e.priv_cap, e.binom_smem, hp->ncls, e.cdesc_smem, NW, R, e.ring_elems).total;
@@ -1002,7 +1041,7 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
   const int nwarps = se.nwarps;
   const int64_t ntiles = (len + se.tile_elems - 1) / se.tile_elems;
   int64_t grid = std::min<int64_t>((int64_t)sm_count(), kMaxCtas);
-  grid = std::min<int64_t>(grid, (kMaxPartials - 1) / nwarps);
+  grid = std::min<int64_t>(grid, (kMaxPartials - kWarpPartOff) / ((nwarps + 3) & ~3));
   grid = std::max<int64_t>(1, std::min<int64_t>(grid, (ntiles + nwarps - 1) / nwarps));
   {
     int rc = get_counter(stream, &a.counter);

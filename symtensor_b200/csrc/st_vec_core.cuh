@@ -34,6 +34,7 @@ struct TailStrategy {
 //   shared  (tau >= 2)  T and xr live once per CTA and are rebuilt (with __syncthreads) when E changes;
 //   private (tau == 1)  T == xr, one copy per warp, rebuilt by the warp itself when it enters a new segment --
 //                       used when segments are too short to amortise a CTA-wide rebuild.
+#define ST_MAX_RED 26  // 1 + the classes a RingSched can hold (more classes: several passes)
 struct TailCtrl {
   double red[32];
   double wE;               // gamma * prod over earlier runs x[v]^m
@@ -41,6 +42,10 @@ struct TailCtrl {
   int32_t cur_cls;
   int64_t cur_seg;
   int32_t last;            // this CTA is the last one to finish (fused finalize)
+  // final reduction (ring kernel): the slot ranges to add, as one concatenated index space
+  int32_t red_n, item_next;
+  int64_t red_start[ST_MAX_RED + 1];
+  const double* red_ptr[ST_MAX_RED];
 };
 
 // Warp-uniform small arrays of the walk.  On the device one copy per warp lives in SHARED memory: as thread-local
@@ -240,31 +245,42 @@ ST_HD double walk_tile(const PlanView& P, const TailStrategy& S, const T* __rest
   // tracked warp-uniformly and a lane steps at most one row further (more only in the last 32 rows).
   auto row_range = [&](const T* __restrict__ dp, int a, int b) {
     if (GAP) {
-      // weight of the component with table index q, starting the row search at the warp-uniform row (row_k, row_s)
-      auto pair_w = [&](int q) -> T {
-        int k = row_k, rs = row_s, len = Rt - 1 - row_k;
-        while (q >= rs + len) { rs += len; ++k; --len; }
-        int l = q - rs + k + 1;
-        if (nE == 1) {  // the common case: one earlier value, kept in a register
-          k += (k >= e0);
-          l += (l >= e0);
-        } else {
-          for (int e = 0; e < nE; ++e) { k += (k >= Ev[e]); l += (l >= Ev[e]); }
-        }
-        return xr[k] * xr[l];
-      };
       for (int g0 = a; g0 < b; g0 += 128) {  // four groups of 32 positions per step (independent chains)
-        const int qg = toff + g0;
-        while (qg >= row_s + (Rt - 1 - row_k)) { row_s += Rt - 1 - row_k; ++row_k; }
-        const int e = g0 + lane;
-        const T w0 = e < b ? pair_w(qg + lane) : T(0);
-        const T w1 = e + 32 < b ? pair_w(qg + 32 + lane) : T(0);
-        const T w2 = e + 64 < b ? pair_w(qg + 64 + lane) : T(0);
-        const T w3 = e + 96 < b ? pair_w(qg + 96 + lane) : T(0);
-        if (e < b) s0 += dp[e] * w0;
-        if (e + 32 < b) s1 += dp[e + 32] * w1;
-        if (e + 64 < b) s2 += dp[e + 64] * w2;
-        if (e + 96 < b) s3 += dp[e + 96] * w3;
+        T w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          w[j] = T(0);
+          if (g0 + 32 * j < b) {  // warp-uniform
+            const int qj = toff + g0 + 32 * j;
+            int len = Rt - 1 - row_k;
+            while (qj >= row_s + len) { row_s += len; ++row_k; --len; }  // row of the group's first position
+            const int q = qj + lane;
+            if (g0 + 32 * j + lane < b) {  // this lane's position exists
+              int k = row_k, rs = row_s;
+              if (len >= 32) {  // warp-uniform: at most one row boundary inside the group
+                const int ns = row_s + len;
+                if (q >= ns) { k = row_k + 1; rs = ns; }
+              } else {          // the last 32 rows of the pair table: several short rows per group
+                int ln = len;
+                while (q >= rs + ln) { rs += ln; ++k; --ln; }
+              }
+              int l = q - rs + k + 1;
+              if (nE == 1) {  // the common case: one earlier value, kept in a register
+                k += (k >= e0);
+                l += (l >= e0);
+              } else {
+                for (int e = 0; e < nE; ++e) { k += (k >= Ev[e]); l += (l >= Ev[e]); }
+              }
+              w[j] = xr[k] * xr[l];
+            }
+          }
+        }
+        const T* __restrict__ d0 = dp + (g0 + lane);
+        const int left = b - g0 - lane;  // this lane's positions g0 + lane + 32 j exist for 32 j < left
+        if (left > 0) s0 += d0[0] * w[0];
+        if (left > 32) s1 += d0[32] * w[1];
+        if (left > 64) s2 += d0[64] * w[2];
+        if (left > 96) s3 += d0[96] * w[3];
       }
       return;
     }
@@ -276,13 +292,17 @@ ST_HD double walk_tile(const PlanView& P, const TailStrategy& S, const T* __rest
       const T xv = xr[row_k];
       const T* __restrict__ xp = xr + (row_k + 1 - row_s + toff);  // xp[e] = xr[l] for the component (row_k, l) at position e
       T r0 = T(0), r1 = T(0);
-      int e = qa - toff + lane;
-      const int ee = se - toff;
-      for (; e + 32 < ee; e += 64) {
-        r0 += dp[e] * xp[e];
-        r1 += dp[e + 32] * xp[e + 32];
+      const int e = qa - toff + lane;
+      const T* __restrict__ d0 = dp + e;
+      const T* __restrict__ x0 = xp + e;
+      int left = se - toff - e;  // this lane's components of the row: offsets 0, 32, 64, ... below `left`
+      for (; left > 32; left -= 64) {
+        r0 += d0[0] * x0[0];
+        r1 += d0[32] * x0[32];
+        d0 += 64;
+        x0 += 64;
       }
-      if (e < ee) r0 += dp[e] * xp[e];
+      if (left > 0) r0 += d0[0] * x0[0];
       s3 += xv * (r0 + r1);
       qa = se;
       if (se == rend) { row_s = rend; ++row_k; }
@@ -428,17 +448,23 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // lane 0 only, without a branch: order the generic-proxy reads of the slot before the copy, arm the barrier, copy
-__device__ __forceinline__ void ring_issue(int lane, uint32_t bar, uint32_t dst, const void* src, uint32_t bytes) {
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void ring_issue(int lane, uint32_t bar, uint32_t dst, const void* src, uint32_t bytes, int fence, uint64_t pol) {
   asm volatile(
       "{\n"
-      " .reg .pred p, q;\n"
+      " .reg .pred p, q, f;\n"
       " setp.eq.s32 p, %0, 0;\n"
       " setp.ne.and.u32 q, %4, 0, p;\n"
-      " @p fence.proxy.async.shared::cta;\n"
+      " setp.ne.and.s32 f, %5, 0, p;\n"
+      " @f fence.proxy.async.shared::cta;\n"
       " @p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %4;\n"
-      " @q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%2], [%3], %4, [%1];\n"
+      " @q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%2], [%3], %4, [%1], %6;\n"
       "}\n" ::"r"(lane),
-      "r"(bar), "r"(dst), "l"(src), "r"(bytes)
+      "r"(bar), "r"(dst), "l"(src), "r"(bytes), "r"(fence), "l"(pol)
       : "memory");
 }
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -473,6 +499,8 @@ struct RingSrc {
   // ring
   T* ring;         // this warp's R slots of Bel elements
   uint32_t ring_s, slot_bytes;  // its shared-space address, bytes per slot
+  uint64_t l2pol;  // L2 policy of the stream: evict first (every component is read once; the directory, the tile sums and
+                   // the tables' global sources are what should stay in L2)
   uint32_t bar0;   // shared-space address of this warp's R mbarriers
   int R, Bel;
   int lane;
@@ -622,6 +650,9 @@ struct RingSrc {
     step = (int64_t)G * NW;
 #ifdef __CUDA_ARCH__
     ring_s = smem_u32(ring);
+    l2pol = l2_evict_first_policy();
+#else
+    l2pol = 0;
 #endif
     slot_bytes = (uint32_t)Bel * (uint32_t)sizeof(T);
     pslot = 0;
@@ -643,7 +674,7 @@ struct RingSrc {
     n_waited = 0;
     for (pci = 0; pci < ncls; ++pci)
       if (enter_class(pci)) { pvalid = true; break; }
-    for (int r = 0; r < R; ++r) issue();
+    for (int r = 0; r < R; ++r) issue(true);
   }
   ST_HD void wait_slot() {
 #ifdef __CUDA_ARCH__
@@ -653,13 +684,16 @@ struct RingSrc {
 #endif
   }
   // copy the next sub-chunk of the stream into slot pslot (which must be free)
-  ST_HD void issue() {
+  ST_HD void issue(bool fresh = false) {
+    (void)fresh;
     if (!pvalid) return;
     int len = plen - poff;
     if (len > Bel) len = Bel;
     const uint32_t bytes = (uint32_t)(len * (int)sizeof(T)) & ~15u;  // whole 16-byte units; the rest is fetched by chunk()
 #ifdef __CUDA_ARCH__
-    ring_issue(lane, bar0 + 8u * pslot, ring_s + (uint32_t)pslot * slot_bytes, pbase + poff, bytes);
+    // (the first fill of a slot needs no proxy fence: nothing has read the slot; and a fence there would wait for the
+    // prologue's prefetch loads)
+    ring_issue(lane, bar0 + 8u * pslot, ring_s + (uint32_t)pslot * slot_bytes, pbase + poff, bytes, fresh ? 0 : 1, l2pol);
 #else
     for (uint32_t i = 0; i < bytes / sizeof(T); ++i) ring[(size_t)pslot * Bel + i] = pbase[poff + i];
     ++n_issued;

@@ -46,7 +46,7 @@ live = ph[:, 0] > 0
 ph = ph[live]
 t0 = ph[:, 0].min()
 names = ["start", "cls+bars+runs", "stream started", "x/binom/cdesc+table", "small classes done (warp 0)"] + [f"class {i} begins" for i in range(5)] + \
-        ["all warps of the CTA done", "ticket taken", "last CTA: slots added", "-", "-", "end"]
+        ["all warps of the CTA done", "ticket taken", "last CTA: counters reset", "last CTA: ranges built", "last CTA: slots added", "end"]
 print(f"{live.sum()} CTAs; times in us after the first CTA start")
 for s, name in enumerate(names):
     col = ph[:, s]
