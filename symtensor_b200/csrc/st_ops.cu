@@ -337,6 +337,235 @@ __global__ void __launch_bounds__(256) mat_step_kernel(PlanView P, int k, int m,
   }
 }
 
+// ---- fp64 mode-chain step on the FP64 tensor pipe (mma.sync m8n8k4, DMMA) ---------------------------------
+// flat rank (rank m + 1) of sort(a, I): the merged tuple walked from its largest element down
+ST_HD int64_t merged_rank(const PlanView& P, const int32_t* I, int m, int64_t a) {
+  const int64_t d = P.dim;
+  int64_t pos = binom_at(P.binom, P.rank, d + m, m + 1) - 1;
+  int q = m - 1;
+  bool placed = false;
+  for (int t = 0; t <= m; ++t) {
+    int32_t z;
+    if (!placed && (q < 0 || I[q] <= a)) { z = (int32_t)a; placed = true; }
+    else z = I[q--];
+    pos -= binom_at(P.binom, P.rank, d - 1 + t - z, t + 1);
+  }
+  return pos;
+}
+
+// gather map of one step, built once and shared by all J: tbl[a * nI + i] = flat rank of sort(a, I_i)
+__global__ void __launch_bounds__(256) mat_index_kernel(PlanView P, int m, int64_t nI, int32_t* __restrict__ tbl) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nI) return;
+  int32_t I[ST_MAX_RANK];
+  flat_unrank_r(P, i, m, I);
+  for (int64_t a = 0; a < P.dim; ++a) tbl[a * nI + i] = (int32_t)merged_rank(P, I, m, a);
+}
+
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// CTA: one J, a strip of NT tiles of 64 rows I, 64 columns j.  The A-operand chunk S[a][i] is gathered from the packed
+// row Tk[J][.] through the step's gather map (or, when the map would be too large, by ranking on the fly), W
+// streams through shared memory; 8 warps, each a 16 x 32 block of the tile as 2 x 4 m8n8k4 accumulators.  The
+// (tile, chunk) sequence of the strip is software-pipelined: the gathers of the next chunk are in flight (in
+// registers) while the tensor pipe works on the current one.  Warps whose 32 columns lie entirely below max(J)
+// (not sorted (k+1)-tuples) skip the arithmetic.
+template <bool USE_TBL>
+__global__ void __launch_bounds__(256, 2) mat_step_dmma_kernel(PlanView P, int k, int m, const double* __restrict__ Tk, const double* __restrict__ W,
+                                                            double* __restrict__ Tn, int64_t nJ, int64_t nI, int64_t nI1,
+                                                            const int32_t* __restrict__ tblI, int NT) {
+  constexpr int TI = 64, TJ = 64, TK = 32, LD = 68;  // LD = 4 mod 16: conflict-free fragment loads
+  constexpr int PER = TI * TK / 256;                 // gathered components (and W entries) per thread and chunk
+  __shared__ double Ss[TK][LD];
+  __shared__ double Ws[TK][LD];
+  __shared__ int64_t orow[TJ];
+  __shared__ int32_t Js[ST_MAX_RANK];
+  const int64_t d = P.dim;
+  const int64_t tilesI = (nI + TI - 1) / TI;
+  const int64_t strips = (tilesI + NT - 1) / NT;
+  const int64_t jidx = blockIdx.x / strips;
+  const int64_t t0 = (blockIdx.x % strips) * NT;
+  const int64_t t1 = t0 + NT < tilesI ? t0 + NT : tilesI;
+  const int64_t j0 = (int64_t)blockIdx.y * TJ;
+  if (threadIdx.x == 0) flat_unrank_r(P, jidx, k, Js);
+  __syncthreads();
+  const int jlast = k ? Js[k - 1] : 0;
+  if (j0 + TJ <= jlast) return;  // every column of this tile is below max(J)
+  if (threadIdx.x < TJ) {        // output row of every column: flat rank of the sorted (k+1)-tuple (J, j)
+    const int64_t jj = j0 + threadIdx.x;
+    int32_t Jn[ST_MAX_RANK];
+    for (int q = 0; q < k; ++q) Jn[q] = Js[q];
+    Jn[k] = (int32_t)jj;
+    orow[threadIdx.x] = (jj < d && jj >= jlast) ? flat_rank_r(P, Jn, k + 1) : -1;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wr = warp & 3, wc = warp >> 2;  // 16-row block, 32-column block
+  const bool active = j0 + wc * 32 + 32 > jlast && j0 + wc * 32 < d;
+  const double* __restrict__ row = Tk + jidx * nI1;
+  const int nchunk = (int)((d + TK - 1) / TK);
+  double sreg[PER], wreg[PER];
+  // request chunk c of tile t: this thread's PER components of S (row r = e % TI, a = a0 + e / TI) and entries of W
+  auto fetch = [&](int64_t t, int c) {
+    const int64_t i0 = t * TI, a0 = (int64_t)c * TK;
+#pragma unroll
+    for (int u = 0; u < PER; ++u) {
+      const int e = threadIdx.x + u * 256;
+      const int r = e % TI, aa = e / TI;
+      const int64_t a = a0 + aa;
+      double v = 0.0;
+      if (i0 + r < nI && a < d) {
+        int64_t pos;
+        if (USE_TBL) {
+          pos = (int64_t)__ldg(tblI + a * nI + i0 + r);
+        } else {
+          int32_t I[ST_MAX_RANK];
+          flat_unrank_r(P, i0 + r, m, I);
+          pos = merged_rank(P, I, m, a);
+        }
+        v = row[pos];
+      }
+      sreg[u] = v;
+      const int cc = e % TJ;
+      wreg[u] = (a < d && j0 + cc < d) ? W[a * d + j0 + cc] : 0.0;
+    }
+  };
+  fetch(t0, 0);
+  for (int64_t t = t0; t < t1; ++t) {
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+      __syncthreads();  // the previous chunk's fragments have been read
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int e = threadIdx.x + u * 256;
+        Ss[e / TI][e % TI] = sreg[u];
+        Ws[e / TJ][e % TJ] = wreg[u];
+      }
+      __syncthreads();
+      if (c + 1 < nchunk) fetch(t, c + 1);
+      else if (t + 1 < t1) fetch(t + 1, 0);
+      if (active) {
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+          double af[2], bf[4];
+#pragma unroll
+          for (int i = 0; i < 2; ++i) af[i] = Ss[kk + (lane & 3)][wr * 16 + i * 8 + (lane >> 2)];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bf[j] = Ws[kk + (lane & 3)][wc * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j], af[i], bf[j]);
+        }
+      }
+    }
+    if (active) {
+      // store: accumulator (i, j) holds rows wr*16 + i*8 + lane/4, columns wc*32 + j*8 + 2*(lane%4) + {0, 1}
+      const int64_t i0 = t * TI;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int64_t orw = orow[wc * 32 + j * 8 + 2 * (lane & 3) + h];
+          if (orw < 0) continue;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int64_t ii = i0 + wr * 16 + i * 8 + (lane >> 2);
+            if (ii < nI) Tn[orw * nI + ii] = acc[i][j][h];
+          }
+        }
+    }
+  }
+}
+
+// Last step of the chain (m == 0: no row indices left): Tn[(J, j)] = sum_a W[a][j] Tk[J][a] for j >= max(J), a plain
+// [nJ x d] x [d x d] product whose rows are the sorted k-tuples J.  CTA: 64 consecutive J (their tuples by one
+// unrank and 63 successor steps), 64 columns.  The output position of (J, j) is  c_J - (d - 1 - j)  with
+// c_J = flat rank of (J, d - 1): consecutive j are consecutive output entries.
+__global__ void __launch_bounds__(256, 2) mat_last_dmma_kernel(PlanView P, int k, const double* __restrict__ Tk, const double* __restrict__ W,
+                                                               double* __restrict__ Tn, int64_t nJ) {
+  constexpr int TI = 64, TJ = 64, TK = 32, LD = 68;
+  __shared__ double Ss[TK][LD];
+  __shared__ double Ws[TK][LD];
+  __shared__ int64_t cJ[TI];
+  __shared__ int32_t jl[TI];
+  __shared__ int32_t Jt[TI][ST_MAX_RANK];
+  const int64_t d = P.dim;
+  const int64_t r0 = (int64_t)blockIdx.x * TI;
+  const int64_t j0 = (int64_t)blockIdx.y * TJ;
+  if (threadIdx.x == 0) {
+    flat_unrank_r(P, r0, k, Jt[0]);
+    for (int r = 1; r < TI && r0 + r < nJ; ++r) {  // successor of a sorted k-tuple over range(d)
+      int q = k - 1;
+      while (q >= 0 && Jt[r - 1][q] == d - 1) --q;
+      for (int s = 0; s < k; ++s) Jt[r][s] = s < q ? Jt[r - 1][s] : Jt[r - 1][q] + 1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < TI && r0 + threadIdx.x < nJ) {
+    int32_t Jn[ST_MAX_RANK];
+    for (int q = 0; q < k; ++q) Jn[q] = Jt[threadIdx.x][q];
+    Jn[k] = (int32_t)(d - 1);
+    cJ[threadIdx.x] = flat_rank_r(P, Jn, k + 1);
+    jl[threadIdx.x] = k ? Jn[k - 1] : 0;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wr = warp & 3, wc = warp >> 2;
+  double acc[2][4][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int64_t a0 = 0; a0 < d; a0 += TK) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < TI * TK; e += 256) {
+      const int aa = e % TK, r = e / TK;  // a fastest: the rows of Tk are contiguous in a
+      Ss[aa][r] = (r0 + r < nJ && a0 + aa < d) ? Tk[(r0 + r) * d + a0 + aa] : 0.0;
+    }
+    for (int e = threadIdx.x; e < TJ * TK; e += 256) {
+      const int c = e % TJ, aa = e / TJ;
+      Ws[aa][c] = (a0 + aa < d && j0 + c < d) ? W[(a0 + aa) * d + j0 + c] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; kk += 4) {
+      double af[2], bf[4];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) af[i] = Ss[kk + (lane & 3)][wr * 16 + i * 8 + (lane >> 2)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = Ws[kk + (lane & 3)][wc * 32 + j * 8 + (lane >> 2)];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma_8x8x4(acc[i][j], af[i], bf[j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = wr * 16 + i * 8 + (lane >> 2);
+    if (r0 + r >= nJ) continue;
+    const int64_t c = cJ[r];
+    const int jlast = jl[r];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int64_t jj = j0 + wc * 32 + j * 8 + 2 * (lane & 3) + h;
+        if (jj < d && jj >= jlast) Tn[c - (d - 1 - jj)] = acc[i][j][h];
+      }
+  }
+}
+
+static const int64_t kMatTableMaxBytes = (int64_t)4 << 30;
+int g_mat_dmma = 1;  // fp64 mode chain on the FP64 tensor pipe (0: the DFMA register-tile kernel; test hook)
+// bytes of the gather map of step k (0: the step ranks on the fly)
+static int64_t mat_table_bytes(const HostPlan* hp, int rank, int k);
+
 static int grid_1d(int64_t n, int threads) {
   int64_t g = (n + threads - 1) / threads;
   const int64_t cap = 148 * 32;
@@ -345,6 +574,15 @@ static int grid_1d(int64_t n, int threads) {
 
 static int64_t flat_size_host(const HostPlan* hp, int r) {
   return r == 0 ? 1 : hp->h_binom[(hp->dim + r - 1) * (hp->rank + 1) + r];
+}
+
+static int64_t mat_table_bytes(const HostPlan* hp, int rank, int k) {
+  const int m = rank - k - 1;
+  const int64_t nI = flat_size_host(hp, m), nI1 = flat_size_host(hp, m + 1), nJ = flat_size_host(hp, k);
+  (void)nJ;
+  if (m == 0 || nI1 >= 2147483647LL) return 0;  // the last step needs no map / does not fit int32
+  const __int128 bytes = (__int128)nI * hp->dim * 4;
+  return bytes <= kMatTableMaxBytes ? (int64_t)bytes : 0;
 }
 
 static double binom_double(int n, int k) {
@@ -483,7 +721,29 @@ static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, 
     const int64_t gx = nJ * tilesI;
     if (gx > 2147483647LL) { set_error("mode-chain step %d needs %lld CTAs", k, (long long)gx); return ST_ERR_UNSUPPORTED; }
     const dim3 grid((unsigned)gx, (unsigned)((dim + 63) / 64));
-    mat_step_kernel<T><<<grid, 256, 0, stream>>>(P, k, m, src, d_W, dst, nJ, nI, nI1);
+    if (sizeof(T) == 8 && g_mat_dmma) {
+      const int64_t tb = mat_table_bytes(hp, rank, k);
+      int32_t* tbl = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(d_ws) + 2 * (size_t)maxT * sizeof(T));
+      // strips of NT row tiles per CTA (software-pipelined): as long as there are enough CTAs to fill the machine
+      int NT = 1;
+      while (NT < 8 && nJ * ((tilesI + 2 * NT - 1) / (2 * NT)) >= 148 * 8) NT *= 2;
+      const dim3 sgrid((unsigned)(nJ * ((tilesI + NT - 1) / NT)), (unsigned)((dim + 63) / 64));
+      if (m == 0) {
+        const dim3 lgrid((unsigned)((nJ + 63) / 64), (unsigned)((dim + 63) / 64));
+        mat_last_dmma_kernel<<<lgrid, 256, 0, stream>>>(P, k, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
+                                                       reinterpret_cast<double*>(dst), nJ);
+      } else if (tb > 0) {
+        mat_index_kernel<<<(unsigned)((nI + 255) / 256), 256, 0, stream>>>(P, m, nI, tbl);
+        count_launch();
+        mat_step_dmma_kernel<true><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
+                                                              reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, NT);
+      } else {
+        mat_step_dmma_kernel<false><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
+                                                               reinterpret_cast<double*>(dst), nJ, nI, nI1, nullptr, NT);
+      }
+    } else {
+      mat_step_kernel<T><<<grid, 256, 0, stream>>>(P, k, m, src, d_W, dst, nJ, nI, nI1);
+    }
     count_launch();
     src = dst;
   }
@@ -553,8 +813,11 @@ int st_contract_mat_workspace_bytes(int rank, int64_t dim, int elem_size, int64_
   if (!out_bytes) { set_error("null pointer"); return ST_ERR_INVALID; }
   __int128 maxT = 0;
   for (int k = 0; k <= rank; ++k) maxT = std::max(maxT, (__int128)flat_size_host(hp, k) * flat_size_host(hp, rank - k));
-  if (maxT * 2 * elem_size > (__int128)INT64_MAX) { set_error("workspace does not fit int64"); return ST_ERR_OVERFLOW; }
-  *out_bytes = (int64_t)(maxT * 2 * elem_size);
+  int64_t tbl = 0;
+  if (elem_size == 8)
+    for (int k = 0; k < rank; ++k) tbl = std::max(tbl, mat_table_bytes(hp, rank, k));
+  if (maxT * 2 * elem_size + tbl > (__int128)INT64_MAX) { set_error("workspace does not fit int64"); return ST_ERR_OVERFLOW; }
+  *out_bytes = (int64_t)(maxT * 2 * elem_size) + tbl;
   return ST_OK;
 }
 int st_contract_mat_f64(int rank, int64_t dim, const double* d_a_flat, const double* d_W, double* d_out_flat, void* d_workspace, void* stream) {
