@@ -26,6 +26,33 @@ def shard_bounds(total: int, world: int, align: int = ALIGN) -> List[int]:
     return cuts + [total]
 
 
+def rebalance(cuts: List[int], times: List[float], align: int = ALIGN) -> List[int]:
+    """New cut points from the measured time of every slice: the cost per coordinate differs along the packed range
+    (classes with earlier runs and the long first rows of the big class cost several times the table walk), so
+    slices of equal bytes are not slices of equal time.  The cost density is taken as constant inside each old
+    slice; the new cuts split the cumulative cost evenly.  Pure host arithmetic (unit-tested on the CPU)."""
+    world = len(cuts) - 1
+    if world != len(times) or world < 1:
+        raise ValueError("need one time per slice")
+    total_t = float(sum(times))
+    if world == 1 or total_t <= 0:
+        return list(cuts)
+    new = [cuts[0]]
+    acc = 0.0  # cost up to cuts[r]
+    r = 0
+    for k in range(1, world):
+        target = total_t * k / world
+        while r < world - 1 and acc + times[r] < target:
+            acc += times[r]
+            r += 1
+        length = cuts[r + 1] - cuts[r]
+        frac = (target - acc) / times[r] if times[r] > 0 else 0.0
+        x = cuts[r] + int(length * min(max(frac, 0.0), 1.0))
+        x = min(cuts[-1], max(new[-1], (x + align - 1) // align * align))
+        new.append(x)
+    return new + [cuts[-1]]
+
+
 def my_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     cuts = shard_bounds(total, world)
     return cuts[rank], cuts[rank + 1]
@@ -40,10 +67,12 @@ def all_reduce_sum(value: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def contract_vec_sharded(rank_: int, dim: int, shard: torch.Tensor, x: torch.Tensor, begin: int, end: int, out: torch.Tensor,
-                         ws: Optional[torch.Tensor] = None, group=None, partial_fn: Optional[Callable] = None) -> torch.Tensor:
+                         ws: Optional[torch.Tensor] = None, group=None, partial_fn: Optional[Callable] = None, async_op: bool = False):
     """Vector contraction of a range-sharded permcls tensor: local streaming kernel over ``[begin, end)`` (``shard``
     starts at coordinate ``begin``), then the scalar all-reduce.  ``partial_fn(shard, x, begin, end) -> float`` replaces
-    the CUDA launch in the CPU (gloo) tests of the host logic."""
+    the CUDA launch in the CPU (gloo) tests of the host logic.  With ``async_op`` the all-reduce is only enqueued (on the
+    collective's own stream, ordered after the kernel) and its work handle is returned: the caller may launch the next
+    contraction -- into another ``out`` -- before waiting, so that the collective overlaps the next kernel."""
     if partial_fn is not None:
         out.fill_(partial_fn(shard, x, begin, end))
     else:
@@ -57,4 +86,9 @@ def contract_vec_sharded(rank_: int, dim: int, shard: torch.Tensor, x: torch.Ten
             from ._cabi import lib
             ws = torch.empty(int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=shard.device)
         ops.contract_vec_device(d, x, out, ws, begin, end, packed=shard)
+    if async_op:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            return dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        return None
     return all_reduce_sum(out, group)

@@ -89,3 +89,19 @@ def test_range_sharded_vector_contraction_world2_gloo(rank_t, dim):
     assert sum(r[3] for r in res) == total
     for _, got, ref, _ in res:  # every rank holds the all-reduced value
         assert abs(got - ref) <= 1e-12 * abs(ref)
+
+
+def test_rebalance_equalises_cost():
+    """sharding.rebalance: slices of equal measured time from slices of equal bytes (pure host arithmetic)."""
+    from symtensor_b200 import sharding
+    total = 1 << 20
+    cuts = sharding.shard_bounds(total, 4)
+    # cost density 3 on the first quarter of the range, 1 elsewhere
+    dens = lambda a, b: 3.0 * max(0, min(b, total // 4) - a) + 1.0 * max(0, b - max(a, total // 4))  # noqa: E731
+    for _ in range(4):
+        times = [dens(cuts[r], cuts[r + 1]) for r in range(4)]
+        cuts = sharding.rebalance(cuts, times)
+        assert cuts[0] == 0 and cuts[-1] == total and all(c % 32 == 0 for c in cuts[:-1]) and cuts == sorted(cuts)
+    times = [dens(cuts[r], cuts[r + 1]) for r in range(4)]
+    assert max(times) / (sum(times) / 4) < 1.02
+    assert sharding.rebalance([0, 100], [1.0]) == [0, 100]
