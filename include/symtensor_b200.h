@@ -107,8 +107,11 @@ int st_flat_rank(int rank, int64_t dim, int64_t n, const int32_t* d_idx, int64_t
  * over the packed coordinates [begin, end) of the buffer (whole tensor: begin = 0, end = total).  Ranges
  * let callers shard the tensor over GPUs or stream it from the host; `d_packed` points at coordinate
  * `begin` (i.e. the local shard), begin must be a multiple of ST_CLASS_ALIGN.
- * d_out receives ONE value (the partial sum of the range), written by a second deterministic pass.
- * d_workspace: st_contract_vec_workspace_bytes() bytes of device scratch (no initialisation needed).
+ * d_out receives ONE value (the partial sum of the range).  The result is deterministic: every tile of the
+ * range has its own partial-sum slot in the workspace and the slots are added in index order by the last CTA
+ * of the same launch (permcls layout; the flat layout uses a second single-CTA pass).
+ * d_workspace: st_contract_vec_workspace_bytes() bytes (4 MiB) of device scratch, no initialisation needed;
+ *              launches that may overlap (different streams) need different workspaces.
  * The caller handles the reference's early exits (len(x) != dim -> ValueError, all-zero x -> 0).
  * ------------------------------------------------------------------------------------------------ */
 int64_t st_contract_vec_workspace_bytes(void);
@@ -181,11 +184,13 @@ int st_contract_mat_f64(int rank, int64_t dim, const double* d_a_flat, const dou
 int st_contract_mat_f32(int rank, int64_t dim, const float* d_a_flat, const float* d_W, float* d_out_flat, void* d_workspace,
                         void* stream);
 
-/* kernel variant selection for benchmarking / tests: 0 = auto, 1 = generic per-element enumerator,
- * 2 = tail-table segmented kernel.  Process-wide. */
+/* kernel variant selection for benchmarking / tests: 0 = auto (small classes per component, the rest through the
+ * ring kernel), 1 = generic per-element enumerator, 2 = every class through the ring kernel.  Process-wide. */
 int st_set_vec_variant(int variant);
-/* tuning hooks (process-wide; defaults are the tuned values): "vec_tile_bytes" in [1024, 2^28],
- * "vec_force_tau" in [0, ST_MAX_RANK] (0 = cost model). */
+/* tuning hooks (process-wide; defaults are the tuned values): "vec_force_tau" in [0, ST_MAX_RANK] (0 = cost model),
+ * "vec_small_class", "vec_use_dir", and for the ring kernel "vec_ring_warps", "vec_ring_slots", "vec_ring_bytes",
+ * "vec_ring_bytes_max", "vec_ring_tile_bytes", "vec_ring_table_max", "vec_ring_direct", "vec_ring_dynamic"
+ * (0: static tile deal), "vec_timeline" (debug stamps, see st_debug_vec_timeline). */
 int st_set_tuning(const char* key, int64_t value);
 /* debug: with st_set_tuning("vec_timeline", 1) the vector-contraction kernel stamps %globaltimer at its phase
  * boundaries ([cta][16] stamps, then one finish stamp per warp of the grid); this copies the first n stamps of

@@ -28,7 +28,7 @@ def run():
 
 
 for tile in (8192, 16384, 32768):
-    check(lib.st_set_tuning(b"vec_tile_bytes", c_i64(tile)))
+    check(lib.st_set_tuning(b"vec_ring_tile_bytes", c_i64(tile)))
     for slots in (2, 3, 4):
         check(lib.st_set_tuning(b"vec_batch_slots", c_i64(slots)))
         for dbg in (0,):

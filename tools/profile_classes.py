@@ -17,7 +17,7 @@ def main():
     rank, dim = int(sys.argv[1]), int(sys.argv[2])
     tdt = torch.float32 if sys.argv[3] == "f32" else torch.float64
     if len(sys.argv) > 4:
-        check(lib.st_set_tuning(b"vec_tile_bytes", c_i64(int(sys.argv[4]))))
+        check(lib.st_set_tuning(b"vec_ring_tile_bytes", c_i64(int(sys.argv[4]))))
     t = comb.class_table(rank, dim)
     buf = torch.rand(t.total, dtype=tdt, device=DEV) + 0.5
     x = (torch.rand(dim, dtype=tdt, device=DEV) + 0.5) / dim ** 0.5
