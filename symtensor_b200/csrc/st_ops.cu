@@ -140,6 +140,85 @@ __global__ void __launch_bounds__(256) outer_vec_kernel(PlanView P, int ra, int 
   }
 }
 
+// ---- symmetrized outer product, compile-time ranks (RA + RB <= 8) -----------------------------------------------
+// The flat rank of a sorted r-tuple s is  C(d+r-1, r) - 1 - sum_i F[r-1-i][s[i]],  F[t][v] = C(d-1+t-v, t+1): a sum of
+// per-element terms.  F (a few KB) lives in shared memory, the per-component values G[t][p] = F[t][K[p]] in
+// registers, and the C(n, RA) position subsets are unrolled at compile time: every subset costs n - 2 integer
+// adds, two gathers and one FMA (the run-time-rank kernel spends ~150 instructions per subset on splitting K,
+// ranking twice through the global binomial table and Gosper's hack).
+__host__ __device__ constexpr int popc_const(unsigned m) { return m == 0 ? 0 : (int)(m & 1u) + popc_const(m >> 1); }
+
+template <typename T, int RA, int RB>
+__device__ __forceinline__ double outer_terms(const int32_t* __restrict__ F, int d, const int32_t* K, const T* __restrict__ af,
+                                              const T* __restrict__ bf, int base_a, int base_b) {
+  constexpr int N = RA + RB, TM = RA > RB ? RA : RB;
+  int32_t G[TM][N];
+#pragma unroll
+  for (int t = 0; t < TM; ++t)
+#pragma unroll
+    for (int p = 0; p < N; ++p) G[t][p] = F[t * d + K[p]];
+  double acc = 0.0;
+#pragma unroll
+  for (unsigned mask = 0; mask < (1u << N); ++mask) {
+    if (popc_const(mask) != RA) continue;
+    int sa = 0, sb = 0, ia = 0, ib = 0;
+#pragma unroll
+    for (int p = 0; p < N; ++p) {
+      if ((mask >> p) & 1u) { sa += G[RA - 1 - ia][p]; ++ia; }
+      else { sb += G[RB - 1 - ib][p]; ++ib; }
+    }
+    acc += (double)af[base_a - sa] * (double)bf[base_b - sb];
+  }
+  return acc;
+}
+
+template <typename T, int RA, int RB, bool VEC>
+__global__ void __launch_bounds__(256) outer_fast_kernel(PlanView P, const T* __restrict__ af, const T* __restrict__ bf, T* __restrict__ out,
+                                                         const T* __restrict__ x, double* __restrict__ partials, int64_t begin, int64_t end,
+                                                         double inv_count) {
+  constexpr int N = RA + RB, TM = RA > RB ? RA : RB;
+  extern __shared__ int32_t Fs[];  // [TM][d]
+  __shared__ double red[32];
+  const int d = (int)P.dim;
+  for (int e = threadIdx.x; e < TM * d; e += blockDim.x) {
+    const int tt = e / d, v = e % d;
+    Fs[e] = (int32_t)binom_at(P.binom, P.rank, d - 1 + tt - v, tt + 1);
+  }
+  __syncthreads();
+  const int base_a = (int)(binom_at(P.binom, P.rank, d + RA - 1, RA) - 1), base_b = (int)(binom_at(P.binom, P.rank, d + RB - 1, RB) - 1);
+  double total = 0.0;
+  for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
+    int32_t K[ST_MAX_RANK];
+    if (!permcls_coord_sorted(P, c, K)) {
+      if (!VEC) out[c - begin] = T(0);
+      continue;
+    }
+    int32_t Kr[N];
+#pragma unroll
+    for (int p = 0; p < N; ++p) Kr[p] = K[p];
+    const double acc = outer_terms<T, RA, RB>(Fs, d, Kr, af, bf, base_a, base_b);
+    if (VEC) {
+      double w = (double)P.cls[class_of_coord(P, c)].gamma;
+#pragma unroll
+      for (int p = 0; p < N; ++p) w *= (double)x[Kr[p]];
+      total += acc * inv_count * w;
+    } else {
+      out[c - begin] = (T)(acc * inv_count);
+    }
+  }
+  if (VEC) {
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = total;
+    __syncthreads();
+    if (warp == 0) {
+      double s = lane < (blockDim.x >> 5) ? red[lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) partials[blockIdx.x] = s;
+    }
+  }
+}
+
 __global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* out64, float* out32) {
   __shared__ double red[32];
   double s = 0.0;
@@ -616,6 +695,26 @@ static int flat_to_permcls(int rank, int64_t dim, const T* d_in, T* d_out, int64
   return check_cuda(cudaGetLastError(), "flat_to_permcls_kernel");
 }
 
+int g_outer_fast = 1;  // compile-time-rank outer kernels (0: the run-time-rank kernel; test hook)
+
+// launch the compile-time-rank kernel for (ra, rb) if there is one (ra >= rb; the symmetrized product commutes, so the
+// caller swaps the operands otherwise); false: not instantiated / operands too large for 32-bit ranks
+template <typename T, bool VEC>
+static bool launch_outer_fast(const HostPlan* hp, const PlanView& P, int ra, int rb, const T* a, const T* b, T* out, const T* x, double* partials,
+                              int64_t begin, int64_t end, int grid, cudaStream_t stream) {
+  if (!g_outer_fast || ra < rb || rb < 1 || ra > 4) return false;
+  if (flat_size_host(hp, ra) >= 2147483647LL || hp->dim >= 2147483647LL / 8) return false;
+  const size_t smem = (size_t)ra * hp->dim * sizeof(int32_t);
+  if (smem > 40 * 1024) return false;
+  const double inv = 1.0 / binom_double(ra + rb, ra);
+#define ST_OUTER_CASE(RA, RB) \
+  if (ra == RA && rb == RB) { outer_fast_kernel<T, RA, RB, VEC><<<grid, 256, smem, stream>>>(P, a, b, out, x, partials, begin, end, inv); return true; }
+  ST_OUTER_CASE(1, 1) ST_OUTER_CASE(2, 1) ST_OUTER_CASE(2, 2) ST_OUTER_CASE(3, 1) ST_OUTER_CASE(3, 2) ST_OUTER_CASE(3, 3)
+  ST_OUTER_CASE(4, 1) ST_OUTER_CASE(4, 2) ST_OUTER_CASE(4, 3) ST_OUTER_CASE(4, 4)
+#undef ST_OUTER_CASE
+  return false;
+}
+
 template <typename T>
 static int outer(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_b_flat, T* d_out, int64_t begin, int64_t end, cudaStream_t stream) {
   if (ra < 0 || rb < 0 || ra + rb > ST_MAX_RANK) { set_error("ranks %d + %d exceed %d", ra, rb, ST_MAX_RANK); return ST_ERR_INVALID; }
@@ -625,8 +724,14 @@ static int outer(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_b_fl
   if (begin < 0 || end < begin || end > P.total) { set_error("range [%lld, %lld) outside [0, %lld]", (long long)begin, (long long)end, (long long)P.total); return ST_ERR_INVALID; }
   if (end == begin) return ST_OK;
   if (!d_a_flat || !d_b_flat || !d_out) { set_error("null pointer"); return ST_ERR_INVALID; }
-  outer_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_out, begin, end,
-                                                                  1.0 / binom_double(ra + rb, ra));
+  {
+    const HostPlan* hp = get_host_plan(ra + rb, dim);
+    const bool sw = ra < rb;  // A (x) B symmetrized == B (x) A symmetrized
+    if (!hp || !launch_outer_fast<T, false>(hp, P, sw ? rb : ra, sw ? ra : rb, sw ? d_b_flat : d_a_flat, sw ? d_a_flat : d_b_flat, d_out, nullptr,
+                                            nullptr, begin, end, grid_1d(end - begin, 256), stream))
+      outer_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_out, begin, end,
+                                                                      1.0 / binom_double(ra + rb, ra));
+  }
   count_launch();
   return check_cuda(cudaGetLastError(), "outer_kernel");
 }
@@ -643,7 +748,13 @@ static int outer_vec(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_
   if (begin < 0 || end < begin || end > P.total) { set_error("range outside the packed tensor"); return ST_ERR_INVALID; }
   if (!d_a_flat || !d_b_flat || !d_out || !d_ws || (dim > 0 && !d_x)) { set_error("null pointer"); return ST_ERR_INVALID; }
   const int grid = std::min(grid_1d(std::max<int64_t>(end - begin, 1), 256), kOuterVecCtas);
-  outer_vec_kernel<T><<<grid, 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_x, d_ws, begin, end, 1.0 / binom_double(ra + rb, ra));
+  {
+    const HostPlan* hp = get_host_plan(ra + rb, dim);
+    const bool sw = ra < rb;
+    if (!hp || !launch_outer_fast<T, true>(hp, P, sw ? rb : ra, sw ? ra : rb, sw ? d_b_flat : d_a_flat, sw ? d_a_flat : d_b_flat, nullptr, d_x, d_ws,
+                                           begin, end, grid, stream))
+      outer_vec_kernel<T><<<grid, 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_x, d_ws, begin, end, 1.0 / binom_double(ra + rb, ra));
+  }
   if (sizeof(T) == 8) sum_partials_kernel<<<1, 256, 0, stream>>>(d_ws, grid, reinterpret_cast<double*>(d_out), nullptr);
   else sum_partials_kernel<<<1, 256, 0, stream>>>(d_ws, grid, nullptr, reinterpret_cast<float*>(d_out));
   count_launch(2);

@@ -203,22 +203,34 @@ __device__ __forceinline__ void build_shared_table(const PlanView& P, const Tail
 // function, not inlined: inside the kernel the register allocator serialised the loads (one L2 round trip per
 // slot, ~10 us); here 16 slots are requested before the first is added.
 __device__ __noinline__ double reduce_slots(const TailCtrl* ctl, int tid, int nthreads, bool first_pass) {
+  // the ranges as one concatenated index space; this thread's indices tid, tid + nthreads, ... only grow, so the
+  // range of an index is tracked incrementally; 32 slots are requested before the first is added
   const int n = ctl->red_n;
+  const int64_t nslots = ctl->red_start[n];
   double s = 0.0;
-  for (int r = 0; r < n; ++r) {
-    const int64_t len = ctl->red_start[r + 1] - ctl->red_start[r];
-    const int stride = (r == 0 && first_pass) ? 1 : 4;  // per-warp sums are dense, tile sums one per 32-byte sector
-    const double* p = ctl->red_ptr[r];
-    for (int64_t base = tid; base < len; base += 16 * (int64_t)nthreads) {
-      double v[16];
+  int r = 0;
+  int64_t r_lo = 0, r_hi = ctl->red_start[1];
+  const double* r_ptr = ctl->red_ptr[0];
+  int stride = first_pass ? 1 : 4;  // per-warp sums are dense, tile sums one per 32-byte sector
+  for (int64_t base = tid; base < nslots; base += 32 * (int64_t)nthreads) {
+    double v[32];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int64_t idx = base + j * (int64_t)nthreads;
-        v[j] = idx < len ? __ldcg(p + stride * idx) : 0.0;
+    for (int j = 0; j < 32; ++j) {
+      const int64_t idx = base + j * (int64_t)nthreads;
+      v[j] = 0.0;
+      if (idx < nslots) {
+        while (idx >= r_hi) {
+          ++r;
+          r_lo = r_hi;
+          r_hi = ctl->red_start[r + 1];
+          r_ptr = ctl->red_ptr[r];
+          stride = 4;
+        }
+        v[j] = __ldcg(r_ptr + stride * (idx - r_lo));
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) s += v[j];
     }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += v[j];
   }
   return s;
 }
@@ -681,6 +693,8 @@ unsigned long long* g_timeline = nullptr;  // debug: device buffer of kTimelineS
 static const size_t kTimelineSlots = 148 * 16 + 4096 + 4096 * 8;
 int g_ring_direct = 1;                 // ring kernel: allow the table-free pair walk (2: with vec_force_tau 2, force it)
 int64_t g_ring_table_max = 72 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
+extern int g_mat_dmma, g_outer_fast;  // st_ops.cu
+int64_t g_short_segment = 1024;  // classes whose segments are shorter than this take the per-component phase (tuning knob)
 int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
 struct StratKey {
@@ -754,6 +768,11 @@ bool compute_tail_strategy(const HostPlan* hp, int esize, int nwarps, std::vecto
     memset(&S, 0, sizeof(S));
     if (C.nvals == 0 || C.size == 0) { S.tau = 0; S.gt = 1; S.Rt = 1; S.mu = 1; S.tbl_n = 1; S.seg = 1; continue; }
     if (C.size <= g_small_class && g_variant != 2) { S.tau = 0; S.gt = 1; S.Rt = 1; S.mu = 1; S.tbl_n = 1; S.seg = C.size; continue; }
+    // classes cut into very short segments (one per assignment of the earlier runs: a table rebuild and an unrank
+    // each) are cheaper one component per thread from the per-component directory, up to 8 M components
+    if (reserve > 0 && g_variant != 2 && C.nruns > 1 && C.radix[C.nruns - 1] < g_short_segment && C.size <= ((int64_t)8 << 20)) {
+      S.tau = 0; S.gt = 1; S.Rt = 1; S.mu = 1; S.tbl_n = 1; S.seg = C.size; continue;
+    }
     const int t = C.nruns - 1;
     S.gt = C.run_len[t];
     S.nE = C.nvals - S.gt;
@@ -1290,6 +1309,14 @@ int64_t st_contract_vec_workspace_bytes(void) { return (int64_t)sizeof(double) *
 int st_set_tuning(const char* key, int64_t value) {
   if (!key) { set_error("null key"); return ST_ERR_INVALID; }
   const std::string k(key);
+  if (k == "mat_dmma" && (value == 0 || value == 1)) { g_mat_dmma = (int)value; return ST_OK; }
+  if (k == "outer_fast" && (value == 0 || value == 1)) { g_outer_fast = (int)value; return ST_OK; }
+  if (k == "vec_short_segment" && value >= 0) {
+    g_short_segment = value;
+    std::lock_guard<std::mutex> lk(g_smu);
+    g_strats.clear();
+    return ST_OK;
+  }
   if (k == "vec_small_class" && value >= 0) {
     g_small_class = value;
     std::lock_guard<std::mutex> lk(g_smu);

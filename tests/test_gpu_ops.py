@@ -235,3 +235,44 @@ def test_matrix_identity_at_config4_shape():
     # W = identity returns the tensor itself, bit for bit (index maps of the whole chain)
     I = st.contract_all_indices_with_matrix(A, np.eye(dim))
     assert torch.equal(I.packed, A.packed)
+
+
+def test_matrix_tensor_pipe_and_register_tile_paths_agree():
+    """fp64 mode chain: the FP64-tensor-pipe kernels (gather maps, row strips, last-step kernel) against the DFMA
+    register-tile kernel on the same inputs -- same index maps, results to rounding."""
+    from symtensor_b200._cabi import c_i64, check, lib
+    for rank, dim in [(4, 70), (5, 20), (6, 9), (3, 130)]:
+        rng = np.random.default_rng(rank * 100 + dim)
+        A = rand_packed(rank, dim, rng, "pos")
+        W = rng.uniform(0.5, 1.5, (dim, dim)) / dim
+        TA = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=A, device=DEV)
+        try:
+            check(lib.st_set_tuning(b"mat_dmma", c_i64(0)))
+            C0 = st.contract_all_indices_with_matrix(TA, W).packed.clone()
+        finally:
+            check(lib.st_set_tuning(b"mat_dmma", c_i64(1)))
+        C1 = st.contract_all_indices_with_matrix(TA, W).packed
+        assert torch.allclose(C0, C1, rtol=1e-13, atol=0)
+
+
+def test_outer_compile_time_rank_and_run_time_rank_kernels_agree():
+    """multiply.outer: the compile-time-rank kernels (shared-memory rank terms, unrolled subsets) against the
+    run-time-rank kernel on the same inputs, both operand orders, and the fused outer->vector path."""
+    from symtensor_b200 import ops
+    from symtensor_b200._cabi import c_i64, check, lib
+    for ra, rb, dim in [(4, 4, 7), (2, 4, 9), (3, 3, 11), (3, 1, 40), (1, 1, 50), (4, 3, 6), (2, 2, 70)]:
+        rng = np.random.default_rng(ra * 100 + rb * 10 + dim)
+        A, B = rand_packed(ra, dim, rng, "pos"), rand_packed(rb, dim, rng, "pos")
+        x = rng.uniform(0.5, 1.5, dim)
+        TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=A, device=DEV)
+        TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=B, device=DEV)
+        try:
+            check(lib.st_set_tuning(b"outer_fast", c_i64(0)))
+            C0 = st.multiply.outer(TA, TB).packed.clone()
+            v0 = float(ops.outer_then_contract_vec(TA, TB, x))
+        finally:
+            check(lib.st_set_tuning(b"outer_fast", c_i64(1)))
+        C1 = st.multiply.outer(TA, TB).packed
+        v1 = float(ops.outer_then_contract_vec(TA, TB, x))
+        assert torch.allclose(C0, C1, rtol=1e-13, atol=0), (ra, rb, dim)
+        assert abs(v0 - v1) <= 1e-12 * abs(v0)
