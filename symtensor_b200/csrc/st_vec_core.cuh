@@ -520,7 +520,7 @@ struct RingSrc {
   int64_t ptk, pk0, pk1, plo, phi;  // tile being copied, the class's tiles, class range
   int64_t pdbase, pntail, pn;       // dynamic deal: deal index of claim 0, tiles of the costly tail, deal index of the current tile
   unsigned long long pend;          // dynamic deal: the next claim of this class (valid in lane 0)
-  bool pdyn, pahead;                // the current class is dealt dynamically / with claims one tile ahead
+  bool pdyn, pahead, pstatic_only;  // the current class is dealt dynamically / with claims one tile ahead / entirely by the static first deal
   const T* pcbase;                  // first component of the class
   const T* pbase;                   // first component of the tile being copied
   int plen, poff;                   // its length, offset of the next sub-chunk
@@ -603,10 +603,13 @@ struct RingSrc {
       pahead = (r.k1 - r.k0) >= 4 * step;
       pdbase = r.ns;
       pntail = r.ntail;
+      pstatic_only = r.ns >= r.k1 - r.k0;
       const int64_t gw = (int64_t)cta * NW + warp;
       if (gw >= r.s0 && gw < r.s0 + r.ns) {
         tk = deal_tile(gw - r.s0);  // this warp's statically dealt tile of the class
         if (pahead) pend = claim(ci);
+      } else if (pstatic_only) {
+        return false;  // every tile of the class went out with the static first deal: nothing to claim
       } else {
         const unsigned long long first = claim(ci);
         if (pahead) pend = claim(ci);
@@ -635,6 +638,8 @@ struct RingSrc {
           if ((pk1 - pk0) - pn > 2 * step) pend = claim(pci);
           else pahead = false;
         }
+      } else if (pstatic_only) {
+        ptk = pk1;
       } else {
         ptk = claimed(claim(pci));
       }
@@ -665,6 +670,7 @@ struct RingSrc {
     pn = 0;
     pdyn = false;
     pahead = false;
+    pstatic_only = false;
     cslot = 0;
     cpar = 0;
     held = false;
