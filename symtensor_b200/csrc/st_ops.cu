@@ -219,6 +219,44 @@ __global__ void __launch_bounds__(256) outer_fast_kernel(PlanView P, const T* __
   }
 }
 
+// tensordot epilogue with compile-time free ranks: C_K = inv_count * sum_S G[rank(K_S)][rank(K_S^c)] (same scheme as
+// outer_fast_kernel: rank terms from shared memory, subsets unrolled)
+template <typename T, int NA, int NB>
+__global__ void __launch_bounds__(256) gram_gather_fast_kernel(PlanView P, const T* __restrict__ G, int64_t ncols, T* __restrict__ out, int64_t begin,
+                                                               int64_t end, double inv_count) {
+  constexpr int N = NA + NB, TM = NA > NB ? NA : NB;
+  extern __shared__ int32_t Fs[];  // [TM][d]
+  const int d = (int)P.dim;
+  for (int e = threadIdx.x; e < TM * d; e += blockDim.x) {
+    const int tt = e / d, v = e % d;
+    Fs[e] = (int32_t)binom_at(P.binom, P.rank, d - 1 + tt - v, tt + 1);
+  }
+  __syncthreads();
+  const int base_a = (int)(binom_at(P.binom, P.rank, d + NA - 1, NA) - 1), base_b = (int)(binom_at(P.binom, P.rank, d + NB - 1, NB) - 1);
+  for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
+    int32_t K[ST_MAX_RANK];
+    if (!permcls_coord_sorted(P, c, K)) { out[c - begin] = T(0); continue; }
+    int32_t Gt[TM][N];
+#pragma unroll
+    for (int tt = 0; tt < TM; ++tt)
+#pragma unroll
+      for (int p = 0; p < N; ++p) Gt[tt][p] = Fs[tt * d + K[p]];
+    double acc = 0.0;
+#pragma unroll
+    for (unsigned mask = 0; mask < (1u << N); ++mask) {
+      if (popc_const(mask) != NA) continue;
+      int sa = 0, sb = 0, ia = 0, ib = 0;
+#pragma unroll
+      for (int p = 0; p < N; ++p) {
+        if ((mask >> p) & 1u) { sa += Gt[NA - 1 - ia][p]; ++ia; }
+        else { sb += Gt[NB - 1 - ib][p]; ++ib; }
+      }
+      acc += (double)G[(int64_t)(base_a - sa) * ncols + (base_b - sb)];
+    }
+    out[c - begin] = (T)(acc * inv_count);
+  }
+}
+
 __global__ void sum_partials_kernel(const double* __restrict__ partials, int n, double* out64, float* out32) {
   __shared__ double red[32];
   double s = 0.0;
@@ -305,6 +343,164 @@ __global__ void __launch_bounds__(256) gemm_nt_kernel(const T* __restrict__ A, c
       const int64_t m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
       if (m < M && n < N) C[m * N + n] = acc[i][j];
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fp32 Gram matrix on the 5th-generation tensor cores: C[M x N] = A[M x K] * B[N x K]^T with tcgen05.mma kind::tf32
+// (SASS UTCHMMA), accumulator in TMEM, fp32 accuracy through the 3xTF32 split
+//     a = a_hi + a_lo (a_hi: the 19 bits the tensor core reads, a_lo: the exact remainder),
+//     a b ~ a_hi b_hi + a_hi b_lo + a_lo b_hi                       (relative error ~2^-21 per product)
+// and two-level accumulation: the tensor core adds into its fp32 accumulator with truncation (measured: the error
+// grows with the chain length, 1.4e-5 of sum|terms| at K = 1024), so a chain is at most 256 long and the chains are
+// added in registers with round-to-nearest.  One CTA (4 warps) per 128 x 128 tile; the operand chunks (32 along K)
+// are split and laid out by the CTA's threads in the canonical K-major no-swizzle layout (core matrices of 8 rows x
+// 16 bytes; cute::UMMA::SmemDescriptor / InstrDescriptor bit layouts), one elected thread issues the MMAs and
+// commits them to an mbarrier.  Three CTAs share an SM (66 KB of shared memory, 128 TMEM columns each), which is
+// what overlaps one CTA's staging with another's MMAs in this first version (tools/membench/umma_probe.cu:
+// 38.6 TFLOP/s at 4096 x 4096 x 1024 with the split, 4x the CUDA-core kernel it replaces).
+// ------------------------------------------------------------------------------------------------------
+namespace umma {
+constexpr int BM = 128, BN = 128, BK = 32, CHAIN = 256;
+constexpr uint32_t LBO = 128, SBO = (BK / 4) * 128;  // bytes: next 16-byte K chunk, next 8-row group
+constexpr int TILE_BYTES = (BM / 8) * SBO;           // 16 KB
+constexpr size_t SMEM_BYTES = 4 * TILE_BYTES + 1024;
+
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t a) {
+  return (uint64_t)((a & 0x3FFFF) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | ((uint64_t)1 << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {  // D = F32, A = B = TF32, K-major, M x N
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_c),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool wait_bounded(uint32_t bar, uint32_t parity) {
+  for (int it = 0; it < (1 << 26); ++it) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+}  // namespace umma
+
+__global__ void __launch_bounds__(128) gram_umma_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int64_t M,
+                                                        int64_t N, int64_t K) {
+  using namespace umma;
+  extern __shared__ __align__(1024) unsigned char smem_umma[];
+  unsigned char* tiles = smem_umma;  // A hi, A lo, B hi, B lo
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(&bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_base_s)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t idesc = make_idesc(BM, BN);
+  const bool vec4 = (K & 3) == 0;
+  float acc[BN];  // this thread's row of the tile: the chains are added here with round-to-nearest
+#pragma unroll
+  for (int j = 0; j < BN; ++j) acc[j] = 0.f;
+  uint32_t phase = 0;
+  bool ok = true;
+  // drain the TMEM accumulator into the registers (warp w owns TMEM lanes 32 w .. 32 w + 31 = rows of the tile)
+  auto drain = [&]() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 8) {
+      uint32_t v[8];
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                   : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+  int in_chain = 0;  // K elements accumulated in TMEM since the last drain
+  for (int64_t k0 = 0; k0 < K; k0 += BK) {
+    // stage: 16-byte chunks (row r, chunk kc) of the A and B operand chunks, split into hi / lo
+    for (int e = tid; e < BM * (BK / 4); e += 128) {
+      const int r = e / (BK / 4), kc = e % (BK / 4);
+      const int64_t kk = k0 + kc * 4;
+      float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+      if (vec4) {
+        if (m0 + r < M && kk < K) { const float4 v = *reinterpret_cast<const float4*>(A + (m0 + r) * K + kk); a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+        if (n0 + r < N && kk < K) { const float4 v = *reinterpret_cast<const float4*>(B + (n0 + r) * K + kk); b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w; }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (m0 + r < M && kk + q < K) a[q] = A[(m0 + r) * K + kk + q];
+          if (n0 + r < N && kk + q < K) b[q] = B[(n0 + r) * K + kk + q];
+        }
+      }
+      float4 ah, al, bh, bl;
+      ah.x = tf32_hi(a[0]); ah.y = tf32_hi(a[1]); ah.z = tf32_hi(a[2]); ah.w = tf32_hi(a[3]);
+      bh.x = tf32_hi(b[0]); bh.y = tf32_hi(b[1]); bh.z = tf32_hi(b[2]); bh.w = tf32_hi(b[3]);
+      al.x = a[0] - ah.x; al.y = a[1] - ah.y; al.z = a[2] - ah.z; al.w = a[3] - ah.w;
+      bl.x = b[0] - bh.x; bl.y = b[1] - bh.y; bl.z = b[2] - bh.z; bl.w = b[3] - bh.w;
+      const uint32_t off = (uint32_t)(r >> 3) * SBO + (uint32_t)kc * LBO + (uint32_t)(r & 7) * 16;
+      *reinterpret_cast<float4*>(tiles + 0 * TILE_BYTES + off) = ah;
+      *reinterpret_cast<float4*>(tiles + 1 * TILE_BYTES + off) = al;
+      *reinterpret_cast<float4*>(tiles + 2 * TILE_BYTES + off) = bh;
+      *reinterpret_cast<float4*>(tiles + 3 * TILE_BYTES + off) = bl;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> tensor-core (async proxy) reads
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t base = saddr(tiles);
+#pragma unroll
+      for (int ks = 0; ks < BK / 8; ++ks) {  // one MMA = 8 tf32 along K = two 16-byte chunks
+        const uint32_t koff = ks * 2 * LBO;
+        const uint64_t dAh = make_desc(base + 0 * TILE_BYTES + koff), dAl = make_desc(base + 1 * TILE_BYTES + koff);
+        const uint64_t dBh = make_desc(base + 2 * TILE_BYTES + koff), dBl = make_desc(base + 3 * TILE_BYTES + koff);
+        mma_tf32(tmem_base, dAh, dBh, idesc, (in_chain > 0 || ks > 0) ? 1u : 0u);
+        mma_tf32(tmem_base, dAh, dBl, idesc, 1u);
+        mma_tf32(tmem_base, dAl, dBh, idesc, 1u);
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(saddr(&bar)) : "memory");
+    }
+    in_chain += BK;
+    // the tiles are overwritten by the next stage: wait for the MMAs of this one
+    if (!wait_bounded(saddr(&bar), phase)) { ok = false; break; }
+    phase ^= 1;
+    if (in_chain >= CHAIN || k0 + BK >= K) {
+      drain();
+      in_chain = 0;
+    }
+    __syncthreads();
+  }
+  const int64_t row = m0 + warp * 32 + lane;
+  if (row < M) {
+    const float poison = __uint_as_float(0x7fc00000u);  // a timed-out barrier must not pass as a result
+#pragma unroll
+    for (int j = 0; j < BN; ++j)
+      if (n0 + j < N) C[row * N + n0 + j] = ok ? acc[j] : poison;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
 }
 
 // epilogue: C_K = inv_count * sum_S G[rank(K_S)][rank(K_S^c)], written in the permcls layout of rank n
@@ -695,6 +891,7 @@ static int flat_to_permcls(int rank, int64_t dim, const T* d_in, T* d_out, int64
   return check_cuda(cudaGetLastError(), "flat_to_permcls_kernel");
 }
 
+int g_gram_umma = 1;   // fp32 tensordot Gram matrix on tcgen05 (0: the CUDA-core kernel; test hook)
 int g_outer_fast = 1;  // compile-time-rank outer kernels (0: the run-time-rank kernel; test hook)
 
 // launch the compile-time-rank kernel for (ra, rb) if there is one (ra >= rb; the symmetrized product commutes, so the
@@ -803,10 +1000,36 @@ static int tensordot(int ra, int rb, int k, int64_t dim, const T* d_a_flat, cons
   expand_kernel<T><<<grid_1d(s.N * s.K, 256), 256, 0, stream>>>(P, s.nb, k, d_b_flat, bex, s.N, s.K, 0);
   const dim3 grid((unsigned)((s.N + 63) / 64), (unsigned)((s.M + 63) / 64));
   if (grid.y > 65535) { set_error("Gram matrix with %lld rows needs the tiled (non-materialising) kernel", (long long)s.M); return ST_ERR_UNSUPPORTED; }
-  gemm_nt_kernel<T><<<grid, 256, 0, stream>>>(aex, bex, G, s.M, s.N, s.K);
+  if (sizeof(T) == 4 && g_gram_umma) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      rc = check_cuda(cudaFuncSetAttribute(gram_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES), "cudaFuncSetAttribute");
+      if (rc) return rc;
+      attr_set = true;
+    }
+    const dim3 ugrid((unsigned)((s.N + umma::BN - 1) / umma::BN), (unsigned)((s.M + umma::BM - 1) / umma::BM));
+    if (ugrid.y > 65535) { set_error("Gram matrix with %lld rows needs the tiled (non-materialising) kernel", (long long)s.M); return ST_ERR_UNSUPPORTED; }
+    gram_umma_kernel<<<ugrid, 128, umma::SMEM_BYTES, stream>>>(reinterpret_cast<const float*>(aex), reinterpret_cast<const float*>(bex),
+                                                              reinterpret_cast<float*>(G), s.M, s.N, s.K);
+  } else {
+    gemm_nt_kernel<T><<<grid, 256, 0, stream>>>(aex, bex, G, s.M, s.N, s.K);
+  }
   // the gather runs on the plan of the output rank; sub-tuple ranks only need binomials up to rank n there
-  gram_gather_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(Pn, s.na, s.nb, G, s.N, d_out, begin, end,
-                                                                        1.0 / binom_double(s.n, s.na));
+  {
+    const double inv = 1.0 / binom_double(s.n, s.na);
+    const int tm = std::max(s.na, s.nb);
+    const size_t fsm = (size_t)tm * dim * sizeof(int32_t);
+    const int gg = grid_1d(end - begin, 256);
+    bool done = false;
+    if (g_outer_fast && s.na >= 1 && s.nb >= 1 && tm <= 3 && fsm <= 40 * 1024 && s.M < 2147483647LL && s.N < 2147483647LL) {
+#define ST_GRAM_CASE(NA, NB) \
+  if (s.na == NA && s.nb == NB) { gram_gather_fast_kernel<T, NA, NB><<<gg, 256, fsm, stream>>>(Pn, G, s.N, d_out, begin, end, inv); done = true; }
+      ST_GRAM_CASE(1, 1) ST_GRAM_CASE(1, 2) ST_GRAM_CASE(2, 1) ST_GRAM_CASE(2, 2) ST_GRAM_CASE(1, 3) ST_GRAM_CASE(3, 1)
+      ST_GRAM_CASE(2, 3) ST_GRAM_CASE(3, 2) ST_GRAM_CASE(3, 3)
+#undef ST_GRAM_CASE
+    }
+    if (!done) gram_gather_kernel<T><<<gg, 256, 0, stream>>>(Pn, s.na, s.nb, G, s.N, d_out, begin, end, inv);
+  }
   count_launch(4);
   return check_cuda(cudaGetLastError(), "tensordot kernels");
 }

@@ -693,7 +693,7 @@ unsigned long long* g_timeline = nullptr;  // debug: device buffer of kTimelineS
 static const size_t kTimelineSlots = 148 * 16 + 4096 + 4096 * 8;
 int g_ring_direct = 1;                 // ring kernel: allow the table-free pair walk (2: with vec_force_tau 2, force it)
 int64_t g_ring_table_max = 72 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
-extern int g_mat_dmma, g_outer_fast;  // st_ops.cu
+extern int g_mat_dmma, g_outer_fast, g_gram_umma;  // st_ops.cu
 int64_t g_short_segment = 1024;  // classes whose segments are shorter than this take the per-component phase (tuning knob)
 int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
@@ -1311,6 +1311,7 @@ int st_set_tuning(const char* key, int64_t value) {
   const std::string k(key);
   if (k == "mat_dmma" && (value == 0 || value == 1)) { g_mat_dmma = (int)value; return ST_OK; }
   if (k == "outer_fast" && (value == 0 || value == 1)) { g_outer_fast = (int)value; return ST_OK; }
+  if (k == "gram_umma" && (value == 0 || value == 1)) { g_gram_umma = (int)value; return ST_OK; }
   if (k == "vec_short_segment" && value >= 0) {
     g_short_segment = value;
     std::lock_guard<std::mutex> lk(g_smu);

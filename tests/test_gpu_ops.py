@@ -276,3 +276,28 @@ def test_outer_compile_time_rank_and_run_time_rank_kernels_agree():
         v1 = float(ops.outer_then_contract_vec(TA, TB, x))
         assert torch.allclose(C0, C1, rtol=1e-13, atol=0), (ra, rb, dim)
         assert abs(v0 - v1) <= 1e-12 * abs(v0)
+
+
+def test_tensordot_fp32_tensor_core_gram_matches_cuda_core_gram_and_oracle():
+    """fp32 tensordot: the tcgen05 (3xTF32, two-level accumulation) Gram kernel against the CUDA-core kernel and the
+    fp64 oracle, including contraction lengths beyond one accumulation chain (K > 256) and K not a multiple of 4."""
+    from symtensor_b200._cabi import c_i64, check, lib
+    for ra, rb, k, dim in [(2, 2, 1, 600), (3, 2, 1, 70), (2, 2, 1, 301), (3, 3, 2, 24), (2, 1, 1, 1000)]:
+        rng = np.random.default_rng(ra * 1000 + rb * 100 + k * 10 + dim)
+        A, B = rand_packed(ra, dim, rng, "normal"), rand_packed(rb, dim, rng, "normal")
+        TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=A, device=DEV).astype(np.float32)
+        TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=B, device=DEV).astype(np.float32)
+        A32 = {q: v.astype(np.float32).astype(np.float64) for q, v in A.items()}
+        B32 = {q: v.astype(np.float32).astype(np.float64) for q, v in B.items()}
+        ref, n = po.tensordot(A32, ra, B32, rb, dim, k)
+        scale, _ = po.tensordot(absd(A32), ra, absd(B32), rb, dim, k)
+        try:  # the CUDA-core Gram kernel and the run-time-rank epilogue
+            check(lib.st_set_tuning(b"gram_umma", c_i64(0)))
+            check(lib.st_set_tuning(b"outer_fast", c_i64(0)))
+            C0 = st.tensordot(TA, TB, axes=k)
+            assert_classes_close(C0, ref, scale, RTOL32)
+        finally:
+            check(lib.st_set_tuning(b"gram_umma", c_i64(1)))
+            check(lib.st_set_tuning(b"outer_fast", c_i64(1)))
+        C1 = st.tensordot(TA, TB, axes=k)
+        assert_classes_close(C1, ref, scale, RTOL32)
