@@ -140,6 +140,25 @@ int st_flat_to_permcls_f64(int rank, int64_t dim, const double* d_flat, double* 
 int st_flat_to_permcls_f32(int rank, int64_t dim, const float* d_flat, float* d_permcls, int64_t begin, int64_t end, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Dense <-> packed (the constructor / todense step either side of the ops).  d_dense is the row-major
+ * dim^rank array.  st_pack_dense_* fills the packed coordinates [begin, end) (d_packed points at `begin`;
+ * permcls padding is written as zeros): symmetrize = 0 takes the representative entry of every component
+ * and checks the symmetry of the dense array with numpy.allclose(rtol, atol) semantics over all
+ * permutations, setting *d_flag (device int, caller-zeroed) to 1 on a violation -- the reference raises
+ * ValueError("Data array is not symmetric.") then (PermClsSymmetricTensor._validate_data,
+ * symtensor/permcls_symtensor.py:599-618; utils.is_symmetric, symtensor/utils.py:563-578); symmetrize = 1
+ * stores the mean over all axis permutations (utils.symmetrize, symtensor/utils.py:507-532).
+ * st_unpack_dense_* is todense (symtensor/permcls_symtensor.py:883-887, torch_symtensor.py:564-568,
+ * flat_symtensor.py:251-256).
+ * ------------------------------------------------------------------------------------------------ */
+int st_pack_dense_f64(int layout, int rank, int64_t dim, const double* d_dense, double* d_packed, int64_t begin, int64_t end,
+                      int symmetrize, double rtol, double atol, int* d_flag, void* stream);
+int st_pack_dense_f32(int layout, int rank, int64_t dim, const float* d_dense, float* d_packed, int64_t begin, int64_t end,
+                      int symmetrize, double rtol, double atol, int* d_flag, void* stream);
+int st_unpack_dense_f64(int layout, int rank, int64_t dim, const double* d_packed, double* d_dense, void* stream);
+int st_unpack_dense_f32(int layout, int rank, int64_t dim, const float* d_packed, float* d_dense, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * multiply.outer, symmetrized  (symtensor/symalg.py:294-316 via symmetrized_op :206-283):
  *     C_K = C(ra+rb, ra)^-1 * sum over position subsets S, |S| = ra, of A[K_S] * B[K_S^c]
  * Operands in ST_LAYOUT_FLAT (rank ra / rb, same dim); the output is the ST_LAYOUT_PERMCLS buffer of rank

@@ -47,6 +47,10 @@ SIGNATURES = {
     "st_permcls_to_flat_f32": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp]),
     "st_flat_to_permcls_f64": (c_int, [c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_flat_to_permcls_f32": (c_int, [c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_pack_dense_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, ctypes.c_double, ctypes.c_double, c_vp, c_vp]),
+    "st_pack_dense_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_i64, c_i64, c_int, ctypes.c_double, ctypes.c_double, c_vp, c_vp]),
+    "st_unpack_dense_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "st_unpack_dense_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "st_outer_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_outer_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_outer_vec_workspace_bytes": (c_i64, []),

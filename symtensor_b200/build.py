@@ -38,12 +38,32 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libsymtensor_b200.so")
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    headers = [d for d in deps if not d.endswith(".cu")]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs = []
+    objs = []
+    for src in sources():  # one translation unit per file, compiled in parallel; only the stale ones
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + headers):
+            cmd = [nvcc] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            jobs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for src, proc in jobs:
+        out, _ = proc.communicate()
+        log.append(out)
+        if proc.returncode != 0:
+            for _, other in jobs:
+                if other.poll() is None:
+                    other.kill()
+            raise RuntimeError(f"nvcc failed on {src}:\n" + out)
+    res = subprocess.run([nvcc, "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc (link) failed:\n" + res.stdout + res.stderr)
     if verbose:
-        print(res.stderr)
+        print("\n".join(log))
     return LIB
 
 

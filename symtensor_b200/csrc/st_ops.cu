@@ -35,25 +35,6 @@ ST_HD void flat_unrank_r(const PlanView& P, int64_t pos, int r, int32_t* s) {
   for (int k = 0; k < r; ++k) s[k] -= k;
 }
 
-// packed coordinate of the permcls layout -> sorted multi-index (false for alignment padding)
-ST_HD bool permcls_coord_sorted(const PlanView& P, int64_t c, int32_t* K) {
-  const int ci = class_of_coord(P, c);
-  const ClassDesc& C = P.cls[ci];
-  const int64_t pos = c - C.offset;
-  if (pos >= C.size) return false;
-  int32_t vals[ST_MAX_RANK];
-  permcls_unrank_vals(P, C, pos, vals);
-  int n = 0;
-  for (int v = 0; v < C.nvals; ++v)
-    for (int m = 0; m < C.mult[v]; ++m) {
-      const int32_t x = vals[v];
-      int u = n++;
-      while (u > 0 && K[u - 1] > x) { K[u] = K[u - 1]; --u; }
-      K[u] = x;
-    }
-  return true;
-}
-
 // ------------------------------------------------------------------------------------------------------
 // layout converters (also the "pack / unpack" step either side of the ops: permcls <-> flat re-ordering)
 // ------------------------------------------------------------------------------------------------------

@@ -62,6 +62,7 @@ struct VecArgs {
   int32_t cdesc_smem;  // copy the class descriptors to shared memory
   double* sum_out;     // vec_ring_kernel: where the launch's sum goes (fp64)
   int32_t dynamic;     // vec_ring_kernel: deal the tiles of mode-A classes dynamically (per-class counters behind `counter`)
+  int32_t ondemand;    // vec_ring_kernel: rounds at the end of a class whose entries are claimed on demand
   unsigned long long* tl;  // debug timeline (nullptr: off): [cta][16] phase stamps, then [warp of the grid] finish stamps
   int32_t priv_cap;    // vec_ring_kernel: entries of the per-warp xr tables (nwarps * dim, or 0)
   int32_t ring_slots;  // vec_ring_kernel: slots per warp (R)
@@ -303,6 +304,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   src.queue = reinterpret_cast<TileQ*>(smem_raw + L.queue) + (size_t)warp * (a.ring_slots + 2);
   src.begin = a.begin;
   src.tile = tile;
+  src.ondemand = a.ondemand;
   src.ncls = P.ncls;
   src.NW = nwarps;
   src.G = G;
@@ -421,8 +423,10 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
         if (a.tl != nullptr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin));
         const TileQ& tq = src.pop();
         const int64_t tk = tq.tk;
+        int32_t tn;
+        const int64_t dn = tile_to_deal(rr, tk, tn);  // deal entry (its slot) and tile count (grouped deal)
         int64_t w0 = tk * tile;
-        int64_t w1 = w0 + tile;
+        int64_t w1 = w0 + tn * tile;
         const bool have_dir = a.dir != nullptr && w0 >= lo;  // the tile starts inside the launch range
         if (w0 < lo) w0 = lo;
         if (w1 > hi) w1 = hi;
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
           }
         }
         src.close_tile();
-        store_tile(dbase + tk, tsum);
+        store_tile(dbase + k0 + dn, tsum);
         if (a.tl != nullptr) {
           unsigned long long t_end;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -651,7 +655,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
           if (!run[c].mode) continue;
           ctl->red_start[n] = pos;
           ctl->red_ptr[n] = tile_part + 4 * (cls_s[c].tile_base + run[c].k0);
-          pos += run[c].k1 - run[c].k0;
+          pos += run[c].nd;  // one slot per deal entry (mode B: per tile)
           ++n;
         }
         ctl->red_start[n] = pos;
@@ -729,6 +733,9 @@ static int g_ring_slots = 2;           // ring slots per warp
 static int g_ring_bytes = 4096;        // preferred bytes per slot (shrunk to 1536 / 1024 when the table needs the room)
 static int g_ring_bytes_max = 4096;    // slots grow up to this when shared memory is left over
 static int g_ring_tile_bytes = 49152;    // bytes per tile (directory granularity; rounded to whole slots)
+static int g_ring_group = 4;             // dynamic deal: tiles per group at the start of a class (1: every tile on its own)
+static int g_ring_ondemand = 2;          // dynamic deal: rounds at the end of an ungrouped class claimed on demand
+static int g_ring_fine = 2;              // dynamic deal: single tiles per warp of the grid that close a grouped class
 static std::map<StratKey, StratEntry> g_strats;
 
 static double dbinom(const HostPlan* hp, int64_t n, int k) {
@@ -1067,6 +1074,7 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
     if (rc) return rc;
   }
   a.dynamic = (g_ring_dynamic && hp->ncls <= kMaxCounters - 2) ? 1 : 0;
+  a.ondemand = g_ring_ondemand;
   RingSched sched;
   sched.n = 0;
   sched.pad_ = 0;
@@ -1078,14 +1086,10 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
       sched.cls[c].sbase = se.h_sbase.empty() ? 0 : se.h_sbase[c];
       sched.cls[c].S = se.h_strat[c];
     }
-    make_runs(sched.cls, hp->ncls, a.begin, a.end, se.tile_elems, nwarps, (int)grid, sched.run);
-    for (int c = 0; c < hp->ncls; ++c) {  // the costly tail is dealt first when the launch covers the end of the class
-      ClsRun& r = sched.run[c];
-      if (r.mode == 1 && a.dynamic && r.hi == hp->h_cls[c].size) {
-        r.ntail = std::min<int64_t>(se.h_ntail[c], r.k1 - r.k0);
-        if (r.ntail > r.ns) r.ntail = r.ntail;  // (the static first deal follows the same order)
-      }
-    }
+    // dynamic deal: the costly tail first when the launch covers the end of the class, then groups of tiles, single
+    // tiles last (the static first deal follows the same order)
+    make_runs(sched.cls, hp->ncls, a.begin, a.end, se.tile_elems, nwarps, (int)grid, sched.run, a.dynamic ? se.h_ntail.data() : nullptr,
+              a.dynamic ? g_ring_group : 1, g_ring_fine);
     sched.n = hp->ncls;
   }
   vec_ring_kernel<T><<<(int)grid, nwarps * 32, se.smem_bytes, stream>>>(a, sched);
@@ -1131,6 +1135,7 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   a.ring_elems = 0;
   a.priv_cap = 0;
   a.dynamic = 0;
+  a.ondemand = 2;
   a.sum_out = partials;
   a.tl = g_timeline;
   *grid_out = 1;
@@ -1353,6 +1358,9 @@ int st_set_tuning(const char* key, int64_t value) {
       g_strats.clear();
       return ST_OK;
     }
+    if (k == "vec_ring_group" && value >= 0 && value <= 64) { g_ring_group = (int)value; return ST_OK; }
+    if (k == "vec_ring_fine" && value >= 0 && value <= 64) { g_ring_fine = (int)value; return ST_OK; }
+    if (k == "vec_ring_ondemand" && value >= 0 && value <= 64) { g_ring_ondemand = (int)value; return ST_OK; }
     int* knob = k == "vec_ring_warps" ? &g_ring_warps : k == "vec_ring_slots" ? &g_ring_slots : k == "vec_ring_bytes" ? &g_ring_bytes :
                 k == "vec_ring_bytes_max" ? &g_ring_bytes_max : k == "vec_ring_tile_bytes" ? &g_ring_tile_bytes : nullptr;
     if (knob) {

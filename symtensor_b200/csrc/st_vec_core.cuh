@@ -392,13 +392,47 @@ struct ClsRun {
   int64_t k0, k1;    // tiles k0 .. k1-1 (tile k = positions [k * tile, (k + 1) * tile))
   int64_t ch0, ch1;  // chunks ch0 .. ch1-1 (chunk c = tiles [c * NW, (c + 1) * NW))
   int64_t ntail;     // dynamic deal: the class's last ntail tiles (many tiny blocks: the costly ones) are dealt FIRST, last tile first
-  int64_t s0, ns;    // dynamic deal: the class's first ns tiles go to the warps s0 .. s0 + ns - 1 of the grid without a claim
+  int64_t s0, ns;    // dynamic deal: the class's first ns deal entries go to the warps s0 .. s0 + ns - 1 of the grid without a claim
+  int64_t nd;        // deal entries of the class (== k1 - k0 unless tiles are grouped)
+  int64_t kf;        // grouped deal: tiles k0 .. kf-1 are dealt in groups of m consecutive tiles, kf .. k1-ntail-1 one by one
+  int32_t m;         // group size (1: no grouping; then kf == k0)
   int32_t rot;       // chunks of the earlier classes, mod G
   int32_t mode;      // 0: not walked (small class / empty range); 1: tiles per warp (mode A); 2: chunks per CTA (mode B)
+  int32_t pad_;
 };
 
+// Deal order of a mode-A class (guided: the big pieces first, the small ones last, so that the launch's tail is made of
+// short pieces).  Entry n: n < ntail -> the costly tail tiles, last tile first; then the groups of m tiles from k0;
+// then the single tiles kf .. k1-ntail-1.  Returns the first tile of the entry (>= k1: exhausted), its tile count in tn.
+ST_HD int64_t deal_to_tile(const ClsRun& r, int64_t n, int32_t& tn) {
+  tn = 1;
+  if (n < r.ntail) return r.k1 - 1 - n;
+  n -= r.ntail;
+  const int64_t nc = (r.kf - r.k0 + r.m - 1) / r.m;
+  if (n < nc) {
+    const int64_t t = r.k0 + n * r.m;
+    tn = (int32_t)(r.kf - t < r.m ? r.kf - t : r.m);
+    return t;
+  }
+  const int64_t t = r.kf + (n - nc);
+  return t < r.k1 - r.ntail ? t : r.k1;
+}
+// inverse: deal entry whose first tile is tk (the slot of the entry's sum), and its tile count
+ST_HD int64_t tile_to_deal(const ClsRun& r, int64_t tk, int32_t& tn) {
+  tn = 1;
+  if (tk >= r.k1 - r.ntail) return r.k1 - 1 - tk;
+  if (tk < r.kf) {
+    tn = (int32_t)(r.kf - tk < r.m ? r.kf - tk : r.m);
+    return r.ntail + (tk - r.k0) / r.m;
+  }
+  return r.ntail + (r.kf - r.k0 + r.m - 1) / r.m + (tk - r.kf);
+}
+
 // the launch's schedule: one record per class (serial)
-ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, int64_t tile, int nwarps, int G, ClsRun* run) {
+// `ntail_in` (per class, may be null), `group`, `fine`: the dynamic deal's shape -- costly tail tiles, tiles per group,
+// and how many single tiles per warp of the grid close the class (see deal_to_tile); only the host passes them.
+ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, int64_t tile, int nwarps, int G, ClsRun* run,
+                     const int64_t* ntail_in = nullptr, int group = 1, int64_t fine = 0) {
   int64_t rot = 0, wused = 0;
   const int64_t W = (int64_t)G * nwarps;
   for (int ci = 0; ci < ncls; ++ci) {
@@ -417,9 +451,31 @@ ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, i
     if (r.mode) rot += r.ch1 - r.ch0;
     // the first tiles of the stream are dealt statically, one per warp, so that no warp starts with an atomic
     r.ntail = 0;
+    r.m = 1;
+    r.kf = r.k0;
+    r.nd = r.k1 - r.k0;
+    r.pad_ = 0;
+    if (r.mode == 1 && ntail_in != nullptr && r.hi == csize) r.ntail = ntail_in[ci] < r.k1 - r.k0 ? ntail_in[ci] : r.k1 - r.k0;
+    if (r.mode == 1 && (group > 1 || group == 0)) {
+      const int64_t body = r.k1 - r.ntail - r.k0;
+      int64_t f = fine * W < body ? fine * W : body;
+      int g = group;
+      if (g == 0) {
+        // one group per warp still without a tile (dealt statically, no claim), the rest of the class in single tiles
+        const int64_t navail = W - wused - r.ntail > 0 ? W - wused - r.ntail : 0;
+        int64_t m = navail > 0 ? (body - f) / navail : 1;
+        if (m < 1) m = 1;
+        if (m > 64) m = 64;
+        g = (int)m;
+        if (m > 1) f = body - m * navail;
+      }
+      r.m = g;
+      r.kf = r.k1 - r.ntail - f;
+      r.nd = r.ntail + (r.kf - r.k0 + r.m - 1) / r.m + f;
+    }
     r.s0 = wused;
     r.ns = 0;
-    if (r.mode == 1) { r.ns = r.k1 - r.k0 < W - wused ? r.k1 - r.k0 : W - wused; wused += r.ns; }
+    if (r.mode == 1) { r.ns = r.nd < W - wused ? r.nd : W - wused; wused += r.ns; }
     run[ci] = r;
   }
 }
@@ -515,10 +571,12 @@ struct RingSrc {
   int64_t begin, tile;
   int ncls, NW, G, warp, cta;
   int64_t step;    // G * NW: distance between two tiles of this warp inside a class (static deal)
+  int ondemand;    // dynamic deal, ungrouped classes: the last `ondemand` entries per warp of the grid are claimed on demand, not one ahead
   // producer cursor
   int pci;
   int64_t ptk, pk0, pk1, plo, phi;  // tile being copied, the class's tiles, class range
-  int64_t pdbase, pntail, pn;       // dynamic deal: deal index of claim 0, tiles of the costly tail, deal index of the current tile
+  int64_t pdbase, pn;               // dynamic deal: deal index of claim 0, deal index of the current tile
+  int32_t ptn;                      // tiles in the current deal entry (grouped deal)
   unsigned long long pend;          // dynamic deal: the next claim of this class (valid in lane 0)
   bool pdyn, pahead, pstatic_only;  // the current class is dealt dynamically / with claims one tile ahead / entirely by the static first deal
   const T* pcbase;                  // first component of the class
@@ -548,17 +606,14 @@ struct RingSrc {
     if (lane == 0) r = atomicAdd(ctr + ci, 1ULL);
     return r;
 #else
-    (void)ci;
-    return 0;
+    return ctr[ci]++;  // emulation: the warps run one after the other, every claim takes the next entry
 #endif
   }
   // n-th tile of the class in deal order: the costly tail first (from the end), then the rest in address order;
   // >= pk1 when the class is exhausted
   ST_HD int64_t deal_tile(int64_t n) {
     pn = n;
-    if (n < pntail) return pk1 - 1 - n;
-    const int64_t t = pk0 + (n - pntail);
-    return t < pk1 - pntail ? t : pk1;
+    return deal_to_tile(run[pci], n, ptn);
   }
   ST_HD int64_t claimed(unsigned long long raw) {
 #ifdef __CUDA_ARCH__
@@ -569,7 +624,7 @@ struct RingSrc {
   }
   // enter the tile ptk of class pci: source range, queue entry, directory entry
   ST_HD void set_tile() {
-    int64_t w0 = ptk * tile, w1 = w0 + tile;
+    int64_t w0 = ptk * tile, w1 = w0 + ptn * tile;
     if (w0 < plo) w0 = plo;
     if (w1 > phi) w1 = phi;
     pbase = pcbase + w0;
@@ -596,14 +651,14 @@ struct RingSrc {
     pk0 = r.k0;
     pk1 = r.k1;
     pdyn = ctr != nullptr && r.mode == 1;
+    ptn = 1;
     int64_t tk;
     if (pdyn) {
       // classes with many tiles per warp claim one tile ahead (the atomic's latency is never waited for); small
       // classes claim on demand, or the first warps to arrive would take two tiles each and leave none
-      pahead = (r.k1 - r.k0) >= 4 * step;
+      pahead = r.nd >= 4 * step;
       pdbase = r.ns;
-      pntail = r.ntail;
-      pstatic_only = r.ns >= r.k1 - r.k0;
+      pstatic_only = r.ns >= r.nd;
       const int64_t gw = (int64_t)cta * NW + warp;
       if (gw >= r.s0 && gw < r.s0 + r.ns) {
         tk = deal_tile(gw - r.s0);  // this warp's statically dealt tile of the class
@@ -635,7 +690,8 @@ struct RingSrc {
         // the last 2 * step tiles (two per warp of the grid) are claimed on demand: a warp sitting on a claimed but
         // unstarted tile while others have run dry is what the tail of the launch is made of
         if (ptk < pk1) {
-          if ((pk1 - pk0) - pn > 2 * step) pend = claim(pci);
+          // (a grouped class ends in single tiles -- short pieces -- and keeps claiming ahead to the end)
+          if (run[pci].nd - pn > (run[pci].m > 1 ? 0 : (int64_t)ondemand * step)) pend = claim(pci);
           else pahead = false;
         }
       } else if (pstatic_only) {
@@ -666,7 +722,7 @@ struct RingSrc {
     qtail_i = qhead_i = 0;
     pend = 0;
     pdbase = 0;
-    pntail = 0;
+    ptn = 1;
     pn = 0;
     pdyn = false;
     pahead = false;

@@ -15,7 +15,7 @@ import torch
 from . import combinatorics as comb
 from ._cabi import LAYOUT_FLAT, c_i64, check, lib
 from .base import SymmetricTensor
-from .permcls import _TORCH2NP, _is_host, _stream_ptr, to_torch_dtype
+from .permcls import _TORCH2NP, _is_host, _kernel_dtype, _stream_ptr, pack_dense_device, to_torch_dtype, unpack_dense_device
 
 
 class CudaFlatSymmetricTensor(SymmetricTensor):
@@ -45,8 +45,12 @@ class CudaFlatSymmetricTensor(SymmetricTensor):
         if tuple(t.shape) != self.shape:
             raise RuntimeError(f"data must be scalar or array of shape {(n,)} or {self.shape}")
         dense = t.to(self.device, self._tdtype)
-        idx = self._rep_index_tensor()
         self._buf = self._empty(n)
+        if self.rank and not self._host and _kernel_dtype(self._tdtype):  # CUDA pack kernel
+            if not pack_dense_device(LAYOUT_FLAT, self.rank, self.dim, dense, self._buf, symmetrize):
+                raise RuntimeError("data is not symmetric")
+            return
+        idx = self._rep_index_tensor()
         if symmetrize:
             perms = list(itertools.permutations(range(self.rank)))
             acc = torch.zeros(n, dtype=self._tdtype, device=self.device)
@@ -125,6 +129,8 @@ class CudaFlatSymmetricTensor(SymmetricTensor):
     def todense(self) -> torch.Tensor:
         if self.rank == 0:
             return self._buf.reshape(()).clone()
+        if not self._host and _kernel_dtype(self._tdtype):
+            return unpack_dense_device(LAYOUT_FLAT, self.rank, self.dim, self._buf)
         dense = torch.zeros(self.shape, dtype=self._tdtype, device=self.device)
         idx = self._rep_index_tensor()
         for p in itertools.permutations(range(self.rank)):

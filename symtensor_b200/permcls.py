@@ -64,6 +64,32 @@ def _parse_class_key(key) -> Cls:
     return tuple(int(k) for k in key)
 
 
+def pack_dense_device(layout: int, rank: int, dim: int, dense: torch.Tensor, buf: torch.Tensor, symmetrize: bool) -> bool:
+    """Fill the packed buffer ``buf`` from the dense ``dim**rank`` device tensor with ``pack_dense_kernel``; returns whether the
+    dense array passed the reference's symmetry check (``utils.is_symmetric``, symtensor/utils.py:563-578; always True with
+    ``symmetrize``, which averages over the axis permutations instead, symtensor/utils.py:507-532)."""
+    fn = lib.st_pack_dense_f64 if buf.dtype == torch.float64 else lib.st_pack_dense_f32
+    dense = dense.contiguous()
+    flag = torch.zeros(1, dtype=torch.int32, device=buf.device)
+    with torch.cuda.device(buf.device):
+        check(fn(layout, rank, c_i64(dim), dense.data_ptr(), buf.data_ptr(), c_i64(0), c_i64(buf.numel()), int(bool(symmetrize)),
+                 1e-5, 1e-8, flag.data_ptr(), _stream_ptr(buf.device)))
+    return symmetrize or int(flag.item()) == 0
+
+
+def unpack_dense_device(layout: int, rank: int, dim: int, buf: torch.Tensor) -> torch.Tensor:
+    """``todense`` with ``unpack_dense_kernel`` (one thread per dense element)."""
+    fn = lib.st_unpack_dense_f64 if buf.dtype == torch.float64 else lib.st_unpack_dense_f32
+    dense = torch.empty((dim,) * rank, dtype=buf.dtype, device=buf.device)
+    with torch.cuda.device(buf.device):
+        check(fn(layout, rank, c_i64(dim), buf.data_ptr(), dense.data_ptr(), _stream_ptr(buf.device)))
+    return dense
+
+
+def _kernel_dtype(tdt: torch.dtype) -> bool:
+    return tdt in (torch.float32, torch.float64)
+
+
 class CudaPermClsSymmetricTensor(SymmetricTensor):
     """On creation, defaults to a zero tensor (like the reference)."""
 
@@ -184,6 +210,10 @@ class CudaPermClsSymmetricTensor(SymmetricTensor):
         if self.rank == 0:
             self._data[()].copy_(dense)
             return
+        if not self._host and _kernel_dtype(self._tdtype):  # CUDA pack kernel: gather + symmetry check / symmetrization fused
+            if not pack_dense_device(LAYOUT_PERMCLS, self.rank, self.dim, dense, self._buf, symmetrize):
+                raise ValueError("Data array is not symmetric.")
+            return
         perms = list(itertools.permutations(range(self.rank)))
         for c in self._table.classes:
             if len(c) > self.dim:
@@ -279,6 +309,8 @@ class CudaPermClsSymmetricTensor(SymmetricTensor):
         """Dense ``dim**rank`` tensor on the same device (small tensors / tests only)."""
         if self.rank == 0:
             return self._data[()].clone()
+        if not self._host and _kernel_dtype(self._tdtype):
+            return unpack_dense_device(LAYOUT_PERMCLS, self.rank, self.dim, self._buf)
         dense = torch.zeros(self.shape, dtype=self._tdtype, device=self.device)
         perms = list(itertools.permutations(range(self.rank)))
         for c in self._table.classes:

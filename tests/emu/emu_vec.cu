@@ -67,8 +67,32 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
       tb += (P.cls[c].size + tile - 1) / tile;
     }
   }
+  // use_dir bit 0: tile directory; the bits above: g >= 1 -> the DYNAMIC deal (claims served in replay order), groups of g
+  // tiles, one round of single tiles, a costly tail of 2 tiles per class
+  const int group = use_dir >> 1;
+  use_dir &= 1;
   std::vector<ClsRun> run(P.ncls);
-  make_runs(cls.data(), P.ncls, begin, end, tile, nwarps, G, run.data());
+  std::vector<int64_t> ntail(P.ncls, 2);
+  std::vector<unsigned long long> counters(P.ncls, 0ULL);
+  if (group >= 1) make_runs(cls.data(), P.ncls, begin, end, tile, nwarps, G, run.data(), ntail.data(), group == 99 ? 0 : group, 1);  // 99: automatic group size
+  else make_runs(cls.data(), P.ncls, begin, end, tile, nwarps, G, run.data());
+  if (group >= 1) {  // the deal is a bijection: every tile of the class range belongs to exactly one entry, and the inverse agrees
+    for (int c = 0; c < P.ncls; ++c) {
+      const ClsRun& r = run[c];
+      if (r.mode != 1) continue;
+      std::vector<int> seen(r.k1 - r.k0, 0);
+      for (int64_t n = 0; n < r.nd; ++n) {
+        int32_t tn = 0, tn2 = 0;
+        const int64_t t = deal_to_tile(r, n, tn);
+        if (t < r.k0 || t + tn > r.k1 || tn < 1) return 10;
+        if (tile_to_deal(r, t, tn2) != n || tn2 != tn) return 11;
+        for (int i = 0; i < tn; ++i) if (seen[t - r.k0 + i]++) return 12;
+      }
+      for (int v : seen) if (v != 1) return 13;
+      int32_t tn = 0;
+      if (deal_to_tile(r, r.nd, tn) < r.k1) return 14;
+    }
+  }
   // what vec_dir_kernel stores for the tile that starts at class position `pos`
   auto make_entry = [&](const ClassDesc& C, int64_t pos) {
     DirEntry e;
@@ -111,10 +135,13 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
   std::vector<TileQ> queue(R + 2);
   std::vector<T> tbl(tbl_cap), xr(dim + 1), priv(dim + 1), ring((size_t)R * Bel);
   std::vector<int32_t> blen(dim + 1);
+  std::vector<unsigned long long> counters_at_warp_start;
   for (int cta = 0; cta < G; ++cta)
     for (int warp = 0; warp < nwarps; ++warp)
       for (int lane = 0; lane < 32; ++lane) {
-        // one thread's program, start to end
+        // one thread's program, start to end (the 32 lanes of a warp see the same claims)
+        if (lane == 0) counters_at_warp_start = counters;
+        else counters = counters_at_warp_start;
         WarpScratch ws;
         int cur_cls = -1;
         int64_t cur_seg = -1;
@@ -159,11 +186,12 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
         src.cls = cls.data();
         src.A = A;
         src.dir = use_dir ? dir.data() : nullptr;
-        src.ctr = nullptr;
+        src.ctr = group >= 1 ? counters.data() : nullptr;
         src.queue = queue.data();
         src.QD = R + 2;
         src.begin = begin;
         src.tile = tile;
+        src.ondemand = 2;
         src.ncls = P.ncls;
         src.NW = nwarps;
         src.G = G;
@@ -188,7 +216,9 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
             while (src.head_is(ci)) {
               const TileQ& tq = src.pop();
               const int64_t tk = tq.tk;
-              int64_t w0 = tk * tile, w1 = w0 + tile;
+              int32_t tn;
+              (void)tile_to_deal(rr, tk, tn);
+              int64_t w0 = tk * tile, w1 = w0 + tn * tile;
               const bool have_dir = use_dir && w0 >= lo;
               if (w0 < lo) w0 = lo;
               if (w1 > hi) w1 = hi;

@@ -200,7 +200,17 @@ def test_tail_kernel_index_walk_emulated_on_cpu(emu_lib):
                     assert abs(got - ref) <= 1e-12 * abs(ref), (rank, dim, tau, nw, grid, item, bel, slots, use_dir)
         for small in (100, 10 ** 9):  # some / all classes through the per-component phase
             assert abs(emu(rank, dim, buf, x, small=small) - ref) <= 1e-12 * abs(ref)
+        # dynamic deal (claims served in replay order): costly tail first, groups of g tiles, single tiles last;
+        # use_dir = 2 * g + directory bit (the emulation also checks that the deal is a bijection onto the tiles)
+        for g in (1, 3, 4, 99):  # 99: one group per warp (automatic size)
+            for tau in (0, 2, -3):
+                for nw, grid, item, bel, slots in [(4, 3, 64, 16, 2), (2, 7, 32, 32, 3)]:
+                    got = emu(rank, dim, buf, x, nwarps=nw, grid=grid, item=item, bel=bel, slots=slots, tau=tau, use_dir=2 * g + 1)
+                    assert abs(got - ref) <= 1e-12 * abs(ref), (rank, dim, tau, nw, grid, item, bel, slots, g)
         tot = len(buf)
+        cut0 = (tot // 2) // 32 * 32
+        s = emu(rank, dim, buf, x, begin=0, end=cut0, use_dir=2 * 3 + 1) + emu(rank, dim, buf, x, begin=cut0, end=tot, use_dir=2 * 3 + 1)
+        assert abs(s - ref) <= 1e-12 * abs(ref)
         cut = (tot // 3) // 32 * 32
         s = sum(emu(rank, dim, buf, x, begin=b, end=e, small=sm) for sm, (b, e) in zip((0, 50, 0), [(0, cut), (cut, 2 * cut), (2 * cut, tot)]))
         assert abs(s - ref) <= 1e-12 * abs(ref)
