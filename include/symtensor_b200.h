@@ -43,6 +43,11 @@ extern "C" {
 #define ST_LAYOUT_PERMCLS 0
 #define ST_LAYOUT_FLAT 1
 
+/* combiner of the symmetrized outer ops (st_outer_op_*): symalg.multiply / add / subtract (symtensor/symalg.py:193-195) */
+#define ST_OUTER_MULTIPLY 0
+#define ST_OUTER_ADD 1
+#define ST_OUTER_SUBTRACT 2
+
 typedef enum {
   ST_OK = 0,
   ST_ERR_INVALID = 1,     /* bad argument (maps to ValueError in the Python mixin) */
@@ -170,6 +175,13 @@ int st_outer_f64(int ra, int rb, int64_t dim, const double* d_a_flat, const doub
                  int64_t end, void* stream);
 int st_outer_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin,
                  int64_t end, void* stream);
+/* add.outer / subtract.outer / multiply.outer with an explicit combiner `op` (ST_OUTER_*): the reference registers the
+ * same symmetrized outer for the three ufunc wrappers (symtensor/symalg.py:294-316):
+ *     C_K = C(ra+rb, ra)^-1 * sum over position subsets S of  A[K_S] (op) B[K_S^c]                                   */
+int st_outer_op_f64(int op, int ra, int rb, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out,
+                    int64_t begin, int64_t end, void* stream);
+int st_outer_op_f32(int op, int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out,
+                    int64_t begin, int64_t end, void* stream);
 int64_t st_outer_vec_workspace_bytes(void);
 int st_outer_vec_f64(int ra, int rb, int64_t dim, const double* d_a_flat, const double* d_b_flat, const double* d_x,
                      double* d_out, void* d_workspace, int64_t begin, int64_t end, void* stream);

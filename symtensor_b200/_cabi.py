@@ -53,6 +53,8 @@ SIGNATURES = {
     "st_unpack_dense_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
     "st_outer_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_outer_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_outer_op_f64": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "st_outer_op_f32": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_outer_vec_workspace_bytes": (c_i64, []),
     "st_outer_vec_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_outer_vec_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
@@ -75,6 +77,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 
 ST_OK, ST_ERR_INVALID, ST_ERR_CUDA, ST_ERR_UNSUPPORTED, ST_ERR_OVERFLOW = range(5)
 LAYOUT_PERMCLS, LAYOUT_FLAT = 0, 1
+OUTER_MULTIPLY, OUTER_ADD, OUTER_SUBTRACT = 0, 1, 2
 MAX_RANK = 16
 CLASS_ALIGN = 32
 

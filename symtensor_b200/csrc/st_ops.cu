@@ -61,7 +61,7 @@ __global__ void flat_to_permcls_kernel(PlanView P, const T* __restrict__ in, T* 
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) outer_kernel(PlanView P, int ra, int rb, const T* __restrict__ af, const T* __restrict__ bf,
-                                                    T* __restrict__ out, int64_t begin, int64_t end, double inv_count) {
+                                                    T* __restrict__ out, int64_t begin, int64_t end, double inv_count, int op) {
   const int n = ra + rb;
   for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
     int32_t K[ST_MAX_RANK];
@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(256) outer_kernel(PlanView P, int ra, int rb, 
       for (int p = 0; p < n; ++p) {
         if ((mask >> p) & 1u) sa[ia++] = K[p]; else sb[ib++] = K[p];
       }
-      acc += (double)af[flat_rank_r(P, sa, ra)] * (double)bf[flat_rank_r(P, sb, rb)];
+      const double va = (double)af[flat_rank_r(P, sa, ra)], vb = (double)bf[flat_rank_r(P, sb, rb)];
+      acc += op == ST_OUTER_MULTIPLY ? va * vb : op == ST_OUTER_ADD ? va + vb : va - vb;  // (warp-uniform)
       if (ra == 0) break;
       const uint32_t lo = mask & (0u - mask), hi = mask + lo;
       mask = (((mask ^ hi) >> 2) / lo) | hi;
@@ -894,8 +895,10 @@ static bool launch_outer_fast(const HostPlan* hp, const PlanView& P, int ra, int
 }
 
 template <typename T>
-static int outer(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_b_flat, T* d_out, int64_t begin, int64_t end, cudaStream_t stream) {
+static int outer(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_b_flat, T* d_out, int64_t begin, int64_t end, cudaStream_t stream,
+                 int op = ST_OUTER_MULTIPLY) {
   if (ra < 0 || rb < 0 || ra + rb > ST_MAX_RANK) { set_error("ranks %d + %d exceed %d", ra, rb, ST_MAX_RANK); return ST_ERR_INVALID; }
+  if (op != ST_OUTER_MULTIPLY && op != ST_OUTER_ADD && op != ST_OUTER_SUBTRACT) { set_error("unknown outer op %d", op); return ST_ERR_INVALID; }
   PlanView P;
   int rc = get_device_plan(ra + rb, dim, &P);
   if (rc) return rc;
@@ -905,10 +908,10 @@ static int outer(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_b_fl
   {
     const HostPlan* hp = get_host_plan(ra + rb, dim);
     const bool sw = ra < rb;  // A (x) B symmetrized == B (x) A symmetrized
-    if (!hp || !launch_outer_fast<T, false>(hp, P, sw ? rb : ra, sw ? ra : rb, sw ? d_b_flat : d_a_flat, sw ? d_a_flat : d_b_flat, d_out, nullptr,
+    if (op != ST_OUTER_MULTIPLY || !hp || !launch_outer_fast<T, false>(hp, P, sw ? rb : ra, sw ? ra : rb, sw ? d_b_flat : d_a_flat, sw ? d_a_flat : d_b_flat, d_out, nullptr,
                                             nullptr, begin, end, grid_1d(end - begin, 256), stream))
       outer_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_out, begin, end,
-                                                                      1.0 / binom_double(ra + rb, ra));
+                                                                      1.0 / binom_double(ra + rb, ra), op);
   }
   count_launch();
   return check_cuda(cudaGetLastError(), "outer_kernel");
@@ -1091,6 +1094,15 @@ int st_outer_f64(int ra, int rb, int64_t dim, const double* d_a_flat, const doub
 int st_outer_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin, int64_t end,
                  void* stream) {
   return outer<float>(ra, rb, dim, d_a_flat, d_b_flat, d_out, begin, end, (cudaStream_t)stream);
+}
+
+int st_outer_op_f64(int op, int ra, int rb, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out, int64_t begin, int64_t end,
+                    void* stream) {
+  return outer<double>(ra, rb, dim, d_a_flat, d_b_flat, d_out, begin, end, (cudaStream_t)stream, op);
+}
+int st_outer_op_f32(int op, int ra, int rb, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin, int64_t end,
+                    void* stream) {
+  return outer<float>(ra, rb, dim, d_a_flat, d_b_flat, d_out, begin, end, (cudaStream_t)stream, op);
 }
 
 int64_t st_outer_vec_workspace_bytes(void) { return (int64_t)sizeof(double) * kOuterVecCtas; }

@@ -735,6 +735,7 @@ static int g_ring_bytes_max = 4096;    // slots grow up to this when shared memo
 static int g_ring_tile_bytes = 49152;    // bytes per tile (directory granularity; rounded to whole slots)
 static int g_ring_group = 4;             // dynamic deal: tiles per group at the start of a class (1: every tile on its own)
 static int g_ring_ondemand = 2;          // dynamic deal: rounds at the end of an ungrouped class claimed on demand
+static int g_ring_fine_pos = 70;         // dynamic deal: where the single tiles sit inside a grouped class (percent of its length)
 static int g_ring_fine = 2;              // dynamic deal: single tiles per warp of the grid that close a grouped class
 static std::map<StratKey, StratEntry> g_strats;
 
@@ -1089,7 +1090,7 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
     // dynamic deal: the costly tail first when the launch covers the end of the class, then groups of tiles, single
     // tiles last (the static first deal follows the same order)
     make_runs(sched.cls, hp->ncls, a.begin, a.end, se.tile_elems, nwarps, (int)grid, sched.run, a.dynamic ? se.h_ntail.data() : nullptr,
-              a.dynamic ? g_ring_group : 1, g_ring_fine);
+              a.dynamic ? g_ring_group : 1, g_ring_fine, g_ring_fine_pos);
     sched.n = hp->ncls;
   }
   vec_ring_kernel<T><<<(int)grid, nwarps * 32, se.smem_bytes, stream>>>(a, sched);
@@ -1358,8 +1359,9 @@ int st_set_tuning(const char* key, int64_t value) {
       g_strats.clear();
       return ST_OK;
     }
-    if (k == "vec_ring_group" && value >= 0 && value <= 64) { g_ring_group = (int)value; return ST_OK; }
+    if (k == "vec_ring_group" && value >= 1 && value <= 64) { g_ring_group = (int)value; return ST_OK; }
     if (k == "vec_ring_fine" && value >= 0 && value <= 64) { g_ring_fine = (int)value; return ST_OK; }
+    if (k == "vec_ring_fine_pos" && value >= 0 && value <= 100) { g_ring_fine_pos = (int)value; return ST_OK; }
     if (k == "vec_ring_ondemand" && value >= 0 && value <= 64) { g_ring_ondemand = (int)value; return ST_OK; }
     int* knob = k == "vec_ring_warps" ? &g_ring_warps : k == "vec_ring_slots" ? &g_ring_slots : k == "vec_ring_bytes" ? &g_ring_bytes :
                 k == "vec_ring_bytes_max" ? &g_ring_bytes_max : k == "vec_ring_tile_bytes" ? &g_ring_tile_bytes : nullptr;

@@ -394,45 +394,63 @@ struct ClsRun {
   int64_t ntail;     // dynamic deal: the class's last ntail tiles (many tiny blocks: the costly ones) are dealt FIRST, last tile first
   int64_t s0, ns;    // dynamic deal: the class's first ns deal entries go to the warps s0 .. s0 + ns - 1 of the grid without a claim
   int64_t nd;        // deal entries of the class (== k1 - k0 unless tiles are grouped)
-  int64_t kf;        // grouped deal: tiles k0 .. kf-1 are dealt in groups of m consecutive tiles, kf .. k1-ntail-1 one by one
-  int32_t m;         // group size (1: no grouping; then kf == k0)
+  int64_t kf, ke;    // grouped deal: tiles kf .. ke-1 are dealt one by one (last), the tiles on either side in groups of m
+  int32_t m;         // group size (1: no grouping)
   int32_t rot;       // chunks of the earlier classes, mod G
   int32_t mode;      // 0: not walked (small class / empty range); 1: tiles per warp (mode A); 2: chunks per CTA (mode B)
   int32_t pad_;
 };
 
-// Deal order of a mode-A class (guided: the big pieces first, the small ones last, so that the launch's tail is made of
-// short pieces).  Entry n: n < ntail -> the costly tail tiles, last tile first; then the groups of m tiles from k0;
-// then the single tiles kf .. k1-ntail-1.  Returns the first tile of the entry (>= k1: exhausted), its tile count in tn.
+// Deal order of a mode-A class (guided, costly pieces first).  A tile's cost is highest at the START of a class (long
+// rows below the suffix table: row walk) and at its END (short blocks: many pieces per tile), and lowest and most even in
+// between.  Entry n < ntail -> the costly tail tiles, last tile first; then GROUPS of m consecutive tiles over [k0, kf),
+// ascending; then groups over [ke, k1 - ntail), last group first; then the single tiles kf .. ke-1 -- the cheap, even
+// ones -- which make the launch's tail short.  Returns the first tile of the entry (>= k1: exhausted), its tile count in tn.
 ST_HD int64_t deal_to_tile(const ClsRun& r, int64_t n, int32_t& tn) {
   tn = 1;
   if (n < r.ntail) return r.k1 - 1 - n;
   n -= r.ntail;
-  const int64_t nc = (r.kf - r.k0 + r.m - 1) / r.m;
-  if (n < nc) {
+  const int64_t nl = (r.kf - r.k0 + r.m - 1) / r.m;
+  if (n < nl) {
     const int64_t t = r.k0 + n * r.m;
     tn = (int32_t)(r.kf - t < r.m ? r.kf - t : r.m);
     return t;
   }
-  const int64_t t = r.kf + (n - nc);
-  return t < r.k1 - r.ntail ? t : r.k1;
+  n -= nl;
+  const int64_t E = r.k1 - r.ntail;
+  const int64_t nu = (E - r.ke + r.m - 1) / r.m;
+  if (n < nu) {
+    const int64_t hi = E - n * r.m;
+    const int64_t lo = hi - r.m > r.ke ? hi - r.m : r.ke;
+    tn = (int32_t)(hi - lo);
+    return lo;
+  }
+  const int64_t t = r.kf + (n - nu);
+  return t < r.ke ? t : r.k1;
 }
 // inverse: deal entry whose first tile is tk (the slot of the entry's sum), and its tile count
 ST_HD int64_t tile_to_deal(const ClsRun& r, int64_t tk, int32_t& tn) {
   tn = 1;
-  if (tk >= r.k1 - r.ntail) return r.k1 - 1 - tk;
+  const int64_t E = r.k1 - r.ntail;
+  if (tk >= E) return r.k1 - 1 - tk;
+  const int64_t nl = (r.kf - r.k0 + r.m - 1) / r.m;
   if (tk < r.kf) {
     tn = (int32_t)(r.kf - tk < r.m ? r.kf - tk : r.m);
     return r.ntail + (tk - r.k0) / r.m;
   }
-  return r.ntail + (r.kf - r.k0 + r.m - 1) / r.m + (tk - r.kf);
+  if (tk >= r.ke) {
+    const int64_t g = (E - 1 - tk) / r.m;
+    tn = (int32_t)(E - g * r.m - tk);
+    return r.ntail + nl + g;
+  }
+  return r.ntail + nl + (E - r.ke + r.m - 1) / r.m + (tk - r.kf);
 }
 
 // the launch's schedule: one record per class (serial)
 // `ntail_in` (per class, may be null), `group`, `fine`: the dynamic deal's shape -- costly tail tiles, tiles per group,
 // and how many single tiles per warp of the grid close the class (see deal_to_tile); only the host passes them.
 ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, int64_t tile, int nwarps, int G, ClsRun* run,
-                     const int64_t* ntail_in = nullptr, int group = 1, int64_t fine = 0) {
+                     const int64_t* ntail_in = nullptr, int group = 1, int64_t fine = 0, int fine_pos = 70) {
   int64_t rot = 0, wused = 0;
   const int64_t W = (int64_t)G * nwarps;
   for (int ci = 0; ci < ncls; ++ci) {
@@ -453,25 +471,24 @@ ST_HD void make_runs(const ClsInfo* cls, int ncls, int64_t begin, int64_t end, i
     r.ntail = 0;
     r.m = 1;
     r.kf = r.k0;
+    r.ke = r.k0;
     r.nd = r.k1 - r.k0;
     r.pad_ = 0;
     if (r.mode == 1 && ntail_in != nullptr && r.hi == csize) r.ntail = ntail_in[ci] < r.k1 - r.k0 ? ntail_in[ci] : r.k1 - r.k0;
-    if (r.mode == 1 && (group > 1 || group == 0)) {
+    if (r.mode == 1 && S.nE == 0 && group > 1) {  // (classes with earlier runs: uneven tiles, never grouped)
+      // Groups cut the number of tile starts (each costs ~2 us of warp time), but a group must stay below a warp's fair
+      // share of the class, or the deal cannot even out: m = a warp's share of what is left of the class after `fine`
+      // single tiles per warp of the grid, capped at `group` (measured: rank 6 dim 64 wants 3, rank 8 dim 40 none).
       const int64_t body = r.k1 - r.ntail - r.k0;
-      int64_t f = fine * W < body ? fine * W : body;
-      int g = group;
-      if (g == 0) {
-        // one group per warp still without a tile (dealt statically, no claim), the rest of the class in single tiles
-        const int64_t navail = W - wused - r.ntail > 0 ? W - wused - r.ntail : 0;
-        int64_t m = navail > 0 ? (body - f) / navail : 1;
-        if (m < 1) m = 1;
-        if (m > 64) m = 64;
-        g = (int)m;
-        if (m > 1) f = body - m * navail;
+      const int64_t f = fine * W < body ? fine * W : body;
+      int64_t m = ((body - f) * 4 / W + 3) / 4;  // floor(share + 0.75)
+      if (m > group) m = group;
+      if (m > 1) {
+        r.m = (int32_t)m;
+        r.kf = r.k0 + (body - f) * fine_pos / 100 / m * m;  // whole groups below the single tiles
+        r.ke = r.kf + f;
+        r.nd = r.ntail + (r.kf - r.k0) / m + (r.k1 - r.ntail - r.ke + m - 1) / m + f;
       }
-      r.m = g;
-      r.kf = r.k1 - r.ntail - f;
-      r.nd = r.ntail + (r.kf - r.k0 + r.m - 1) / r.m + f;
     }
     r.s0 = wused;
     r.ns = 0;

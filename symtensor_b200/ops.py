@@ -154,20 +154,27 @@ def _result_dtype(a, b) -> torch.dtype:
     return _NP2TORCH[res]
 
 
-def outer_device(a, b, out_rank_buf: torch.Tensor, begin: int, end: int, tdt: torch.dtype, af=None, bf=None):
+def outer_device(a, b, out_rank_buf: torch.Tensor, begin: int, end: int, tdt: torch.dtype, af=None, bf=None, op: int = 0):
     """Raw launch: coordinates [begin, end) of the permcls buffer of a (x)_s b into ``out_rank_buf`` (which starts at
-    coordinate ``begin``) -- the output range is the sharding axis for multi-GPU runs."""
+    coordinate ``begin``) -- the output range is the sharding axis for multi-GPU runs.  ``op``: 0 multiply (the
+    compile-time-rank kernels), 1 add, 2 subtract (``st_outer_op_*``)."""
     af = _flat_buffer(a, tdt) if af is None else af
     bf = _flat_buffer(b, tdt) if bf is None else bf
     with torch.cuda.device(af.device):
-        check(_fn("st_outer", tdt)(a.rank, b.rank, c_i64(a.dim), af.data_ptr(), bf.data_ptr(), out_rank_buf.data_ptr(),
-                                   c_i64(begin), c_i64(end), _stream_ptr(af.device)))
+        if op == 0:
+            check(_fn("st_outer", tdt)(a.rank, b.rank, c_i64(a.dim), af.data_ptr(), bf.data_ptr(), out_rank_buf.data_ptr(),
+                                       c_i64(begin), c_i64(end), _stream_ptr(af.device)))
+        else:
+            check(_fn("st_outer_op", tdt)(op, a.rank, b.rank, c_i64(a.dim), af.data_ptr(), bf.data_ptr(), out_rank_buf.data_ptr(),
+                                          c_i64(begin), c_i64(end), _stream_ptr(af.device)))
 
 
 def _outer(ufunc, a, b, **kwargs):
-    """symtensor/symalg.py:294-316 for ``multiply``: C_K = mean over the C(n, ra) position splits of A[K_S] B[K_S^c]."""
-    if ufunc is not symalg.multiply:
-        return NotImplemented  # add.outer / subtract.outer: "next" row of the scope table
+    """symtensor/symalg.py:294-316 (registered there for add, subtract and multiply alike):
+    C_K = mean over the C(n, ra) position splits of A[K_S] (op) B[K_S^c]."""
+    op = {symalg.multiply: 0, symalg.add: 1, symalg.subtract: 2}.get(ufunc)
+    if op is None:
+        return NotImplemented
     like = a if isinstance(a, _SYM) else b
     ranka, rankb = np.ndim(a) if not isinstance(a, _SYM) else a.rank, np.ndim(b) if not isinstance(b, _SYM) else b.rank
     dima = a.dim if isinstance(a, _SYM) else (*np.shape(a), 1)[0]
@@ -181,22 +188,28 @@ def _outer(ufunc, a, b, **kwargs):
     tdt = _result_dtype(a, b) if out is None else out.torch_dtype
     n = a.rank + b.rank
     dim = a.dim if a.rank else b.dim
-    if a.rank == 0 or b.rank == 0:  # scalar times tensor
+    if a.rank == 0 or b.rank == 0:  # scalar (op) tensor: one split, elementwise on the packed buffer
         s, t = (a, b) if a.rank == 0 else (b, a)
-        res = cls.from_packed(t.rank, t.dim, (t._buf.to(tdt) * s._buf.to(tdt).reshape(-1)[0]))
+        sv, tv = s._buf.to(tdt).reshape(-1)[0], t._buf.to(tdt)
+        val = tv * sv if op == 0 else tv + sv if op == 1 else (sv - tv if a.rank == 0 else tv - sv)
+        if op and isinstance(t, CudaPermClsSymmetricTensor):  # keep the alignment padding at zero
+            tab = t.class_table
+            for size, off, nxt in zip(tab.sizes, tab.offsets, list(tab.offsets[1:]) + [tab.total]):
+                val[off + size:nxt] = 0
+        res = cls.from_packed(t.rank, t.dim, val)
         if out is not None:
             out._buf.copy_(res._buf)
             return out
         return res
     if issubclass(cls, CudaFlatSymmetricTensor):
         tmp = torch.empty(comb_total(n, dim), dtype=tdt, device=a.device)
-        outer_device(a, b, tmp, 0, tmp.numel(), tdt)
+        outer_device(a, b, tmp, 0, tmp.numel(), tdt, op=op)
         res_p = CudaPermClsSymmetricTensor.from_packed(n, dim, tmp)
         res = cls.from_packed(n, dim, _flat_buffer(res_p, tdt))
     else:
         buf = out._buf if (out is not None and isinstance(out, CudaPermClsSymmetricTensor)) else \
             torch.empty(comb_total(n, dim), dtype=tdt, device=a.device)
-        outer_device(a, b, buf, 0, buf.numel(), tdt)
+        outer_device(a, b, buf, 0, buf.numel(), tdt, op=op)
         res = out if buf is getattr(out, "_buf", None) else cls.from_packed(n, dim, buf)
     if out is not None and res is not out:
         out._buf.copy_(res._buf)
@@ -298,4 +311,4 @@ def outer_then_contract_vec(a, b, x):
 for _cls in _SYM:
     _cls.implements(symalg.tensordot)(_tensordot)
     _cls.implements(symalg.contract_all_indices_with_matrix)(_contract_all_indices_with_matrix)
-    _cls.implements_ufunc.outer(symalg.multiply)(_outer)
+    _cls.implements_ufunc.outer(symalg.add, symalg.subtract, symalg.multiply)(_outer)

@@ -74,7 +74,7 @@ static int emu(int rank, int64_t dim, const T* A, int64_t begin, int64_t end, co
   std::vector<ClsRun> run(P.ncls);
   std::vector<int64_t> ntail(P.ncls, 2);
   std::vector<unsigned long long> counters(P.ncls, 0ULL);
-  if (group >= 1) make_runs(cls.data(), P.ncls, begin, end, tile, nwarps, G, run.data(), ntail.data(), group == 99 ? 0 : group, 1);  // 99: automatic group size
+  if (group >= 1) make_runs(cls.data(), P.ncls, begin, end, tile, nwarps, G, run.data(), ntail.data(), group, 1, 37);
   else make_runs(cls.data(), P.ncls, begin, end, tile, nwarps, G, run.data());
   if (group >= 1) {  // the deal is a bijection: every tile of the class range belongs to exactly one entry, and the inverse agrees
     for (int c = 0; c < P.ncls; ++c) {

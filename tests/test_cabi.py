@@ -202,7 +202,7 @@ def test_tail_kernel_index_walk_emulated_on_cpu(emu_lib):
             assert abs(emu(rank, dim, buf, x, small=small) - ref) <= 1e-12 * abs(ref)
         # dynamic deal (claims served in replay order): costly tail first, groups of g tiles, single tiles last;
         # use_dir = 2 * g + directory bit (the emulation also checks that the deal is a bijection onto the tiles)
-        for g in (1, 3, 4, 99):  # 99: one group per warp (automatic size)
+        for g in (1, 2, 3, 4):
             for tau in (0, 2, -3):
                 for nw, grid, item, bel, slots in [(4, 3, 64, 16, 2), (2, 7, 32, 32, 3)]:
                     got = emu(rank, dim, buf, x, nwarps=nw, grid=grid, item=item, bel=bel, slots=slots, tau=tau, use_dir=2 * g + 1)

@@ -28,14 +28,16 @@ def main():
             combos = [tuple(int(v) for v in c.split(":")) for c in a[len("--combos="):].split(",")]
     if "--short" in sys.argv:
         combos = [c for c in combos if c[0] in (49152, 24576)]
-    for tile, group, fine, od in combos:
+    combos = [c if len(c) > 4 else tuple(c) + (60,) for c in combos]
+    for tile, group, fine, od, pos in combos:
+        check(lib.st_set_tuning(b"vec_ring_fine_pos", c_i64(pos)))
         check(lib.st_set_tuning(b"vec_ring_tile_bytes", c_i64(tile)))
         check(lib.st_set_tuning(b"vec_ring_group", c_i64(group)))
         check(lib.st_set_tuning(b"vec_ring_fine", c_i64(fine)))
         check(lib.st_set_tuning(b"vec_ring_ondemand", c_i64(od)))
         try:
             ms, gbs, val = bench(rank, dim, tdt, reps=50)
-            print(f"r{rank} d{dim} {str(tdt)[6:]} tile={tile:6d} group={group:2d} fine={fine:2d} ondemand={od}: {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s  val={val:.15g}", flush=True)
+            print(f"r{rank} d{dim} {str(tdt)[6:]} tile={tile:6d} group={group:2d} fine={fine:2d} ondemand={od} pos={pos:3d}: {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s  val={val:.15g}", flush=True)
         except Exception as exc:  # noqa: BLE001
             print(f"r{rank} d{dim} tile={tile} group={group} fine={fine}: FAILED {exc}", flush=True)
 
