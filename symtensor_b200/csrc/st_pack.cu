@@ -31,7 +31,8 @@ ST_HD bool next_perm(int32_t* a, int n) {
   return true;
 }
 
-// packed -> dense: one thread per dense element (coalesced stores); its multi-index is sorted / classified and ranked
+// packed -> dense: one thread per dense element (coalesced stores); its multi-index is sorted / classified and ranked.
+// Run-time-rank form (any rank, both layouts): the index arrays live in local memory.
 template <typename T>
 __global__ void __launch_bounds__(256) unpack_dense_kernel(PlanView P, int layout, const T* __restrict__ packed, T* __restrict__ dense, int64_t n_dense) {
   const int r = P.rank;
@@ -57,6 +58,46 @@ __global__ void __launch_bounds__(256) unpack_dense_kernel(PlanView P, int layou
       pos = flat_rank_sorted(P, idx);
     }
     dense[e] = packed[pos];
+  }
+}
+
+// Compile-time-rank form for the flat layout (ranks 1..8, dim^rank < 2^32): everything in registers.  One thread per
+// dense element; the flat rank of the sorted index is a sum of R per-position terms
+// F[t][v] = C(dim - 1 + t - v, t + 1) (t-th position from the end holding value v), kept in shared memory, and the sort is
+// a fully unrolled odd-even transposition network.  HBM-bound on the dense store (the packed gather hits L2: the packed
+// tensor is R! times smaller).
+template <typename T, int R>
+__global__ void __launch_bounds__(256) unpack_flat_fast_kernel(PlanView P, const T* __restrict__ packed, T* __restrict__ dense, uint32_t n_dense) {
+  extern __shared__ uint32_t F_s[];  // [R][dim]
+  const uint32_t dim = (uint32_t)P.dim;
+  for (uint32_t i = threadIdx.x; i < R * dim; i += blockDim.x) {
+    const uint32_t t = i / dim, v = i - t * dim;
+    F_s[i] = (uint32_t)binom_at(P.binom, P.rank, (int64_t)dim - 1 + t - v, (int)t + 1);
+  }
+  __syncthreads();
+  const uint32_t last = (uint32_t)(P.flat_size - 1);
+  for (uint64_t e0 = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; e0 < n_dense; e0 += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t q = (uint32_t)e0;
+    uint32_t s[R];
+#pragma unroll
+    for (int k = R - 1; k >= 0; --k) {
+      const uint32_t d = q / dim;
+      s[k] = q - d * dim;
+      q = d;
+    }
+#pragma unroll
+    for (int pass = 0; pass < R; ++pass) {
+#pragma unroll
+      for (int k = pass & 1; k + 1 < R; k += 2) {
+        const uint32_t lo = min(s[k], s[k + 1]), hi = max(s[k], s[k + 1]);
+        s[k] = lo;
+        s[k + 1] = hi;
+      }
+    }
+    uint32_t pos = last;
+#pragma unroll
+    for (int t = 0; t < R; ++t) pos -= F_s[t * dim + s[R - 1 - t]];
+    dense[e0] = packed[pos];
   }
 }
 
@@ -130,7 +171,24 @@ static int unpack_dense(int layout, int rank, int64_t dim, const T* d_packed, T*
   if (rc) return rc;
   if (n == 0) return ST_OK;
   if (!d_packed || !d_dense) { set_error("null pointer"); return ST_ERR_INVALID; }
-  unpack_dense_kernel<T><<<grid_for_pack(n, 256), 256, 0, stream>>>(P, layout, d_packed, d_dense, n);
+  const size_t smem = (size_t)rank * dim * sizeof(uint32_t);
+  bool fast = false;
+  if (layout == ST_LAYOUT_FLAT && rank >= 1 && rank <= 8 && n < 4294967296LL && smem <= 40 * 1024) {
+    const int grid = grid_for_pack(n, 256);
+    const uint32_t nn = (uint32_t)n;
+    fast = true;
+    switch (rank) {
+      case 1: unpack_flat_fast_kernel<T, 1><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+      case 2: unpack_flat_fast_kernel<T, 2><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+      case 3: unpack_flat_fast_kernel<T, 3><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+      case 4: unpack_flat_fast_kernel<T, 4><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+      case 5: unpack_flat_fast_kernel<T, 5><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+      case 6: unpack_flat_fast_kernel<T, 6><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+      case 7: unpack_flat_fast_kernel<T, 7><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+      default: unpack_flat_fast_kernel<T, 8><<<grid, 256, smem, stream>>>(P, d_packed, d_dense, nn); break;
+    }
+  }
+  if (!fast) unpack_dense_kernel<T><<<grid_for_pack(n, 256), 256, 0, stream>>>(P, layout, d_packed, d_dense, n);
   count_launch();
   return check_cuda(cudaGetLastError(), "unpack_dense_kernel");
 }

@@ -310,6 +310,13 @@ class CudaPermClsSymmetricTensor(SymmetricTensor):
         if self.rank == 0:
             return self._data[()].clone()
         if not self._host and _kernel_dtype(self._tdtype):
+            if self.rank <= 8 and self.dim ** self.rank < 2 ** 32 and self.rank * self.dim * 4 <= 40 * 1024:
+                # re-order to the flat layout (N components), then the compile-time-rank unpack kernel (dim^rank elements)
+                flat = torch.empty(comb.indep_size(self.rank, self.dim), dtype=self._tdtype, device=self.device)
+                fn = lib.st_permcls_to_flat_f64 if self._tdtype == torch.float64 else lib.st_permcls_to_flat_f32
+                with torch.cuda.device(self.device):
+                    check(fn(self.rank, c_i64(self.dim), self._buf.data_ptr(), flat.data_ptr(), _stream_ptr(self.device)))
+                return unpack_dense_device(1, self.rank, self.dim, flat)
             return unpack_dense_device(LAYOUT_PERMCLS, self.rank, self.dim, self._buf)
         dense = torch.zeros(self.shape, dtype=self._tdtype, device=self.device)
         perms = list(itertools.permutations(range(self.rank)))

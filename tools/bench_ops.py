@@ -72,7 +72,7 @@ def bench_mat():
 
 def bench_tdot():
     # config 3 is rank 3 dim 1000 fp32, k = 1 (output 167 GB): beyond one GPU; largest materialised-Gram size here
-    for ra, rb, k, dim in [(3, 3, 1, 160), (3, 2, 1, 400)]:
+    for ra, rb, k, dim in [(3, 3, 1, 160), (3, 2, 1, 400), (3, 2, 1, 1000)]:  # the last: SURVEY.md 8d fallback ladder for config 3
         A, B = rand_tensor(ra, dim, torch.float32, 5), rand_tensor(rb, dim, torch.float32, 6)
         n = comb.indep_size(ra + rb - 2 * k, dim)
         flops = 2 * dim * comb.indep_size(ra - k, dim) * comb.indep_size(rb - k, dim)
@@ -81,8 +81,29 @@ def bench_tdot():
               f"{flops / ms / 1e9:6.2f} TFLOP/s")
 
 
+def bench_pack():
+    # dense <-> packed: HBM-bound on the dense side, dim^rank elements written / read once
+    for rank, dim, tdt in [(4, 128, torch.float64), (3, 800, torch.float32), (6, 24, torch.float64)]:
+        A = rand_tensor(rank, dim, tdt, 7)
+        es = A.packed.element_size()
+        nd = dim ** rank
+        ms, dense = timeit(lambda: A.todense(), reps=5)
+        print(f"todense r{rank} d{dim} {str(tdt)[6:]}: {ms:8.3f} ms  {nd * es / ms / 1e6:7.1f} GB/s of dense bytes written ({nd * es / 1e9:.2f} GB)")
+        ms2, B = timeit(lambda: st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=dense, device=DEV), reps=5)
+        print(f"  pack + symmetry check:      {ms2:8.3f} ms  {nd * es / ms2 / 1e6:7.1f} GB/s of dense bytes read   round trip exact: "
+              f"{bool(torch.equal(B.packed, A.packed))}")
+        ms3, _ = timeit(lambda: st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=dense, symmetrize=True, device=DEV), reps=5)
+        print(f"  pack with symmetrize:       {ms3:8.3f} ms  {nd * es / ms3 / 1e6:7.1f} GB/s")
+    A, B = rand_tensor(3, 100, torch.float64, 8), rand_tensor(3, 100, torch.float64, 9)
+    n = comb.indep_size(6, 100)
+    ms, _ = timeit(lambda: st.symalg.add.outer(A, B), reps=2)
+    print(f"add.outer r3 (+) r3 dim 100 fp64 -> rank 6 ({n} comps): {ms:8.2f} ms  {n / ms / 1e6:7.3f} G comps/s")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("pack", "all"):
+        bench_pack()
     if what in ("outer", "all"):
         bench_outer()
     if what in ("mat", "all"):
