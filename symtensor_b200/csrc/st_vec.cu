@@ -479,7 +479,10 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
           }
         }
         src.close_tile();
-        store_tile(dbase + k0 + dn, tsum);
+        // a statically dealt entry belongs to this warp whatever happens: its sum needs no slot of its own (the last CTA
+        // reads one 32-byte sector per slot, ~0.8 ns each on its one SM) and goes into the warp's sum
+        if (a.dynamic && dn < rr.ns) total += tsum;
+        else store_tile(dbase + k0 + dn, tsum);
         if (a.tl != nullptr) {
           unsigned long long t_end;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
@@ -661,8 +664,9 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
         for (; c < P.ncls && n < ST_MAX_RED; ++c) {
           if (!run[c].mode) continue;
           ctl->red_start[n] = pos;
-          ctl->red_ptr[n] = tile_part + 4 * (cls_s[c].tile_base + run[c].k0);
-          pos += run[c].nd;  // one slot per deal entry (mode B: per tile)
+          const int64_t skip = (a.dynamic && run[c].mode == 1) ? run[c].ns : 0;  // statically dealt entries: in the per-warp sums
+          ctl->red_ptr[n] = tile_part + 4 * (cls_s[c].tile_base + run[c].k0 + skip);
+          pos += run[c].nd - skip;  // one slot per deal entry (mode B: per tile)
           ++n;
         }
         ctl->red_start[n] = pos;
