@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
   for (int ci = 0; ci < P.ncls; ++ci) {
     const ClsRun rr = run[ci];
     if (!rr.mode) continue;
-    if (ci < 5) stamp(5 + ci);
+    if (ci < 5 && ci != 1) stamp(5 + ci);  // (slot 6 is the end of the last CTA's reduce_slots)
     const TailStrategy S = cls_s[ci].S;
     const ClassDesc& C = P.cls[ci];
     const int64_t coff = cls_s[ci].offset, csize = cls_s[ci].size;

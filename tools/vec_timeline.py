@@ -45,7 +45,8 @@ ph = raw[:148 * 16].reshape(148, 16).astype(np.int64)
 live = ph[:, 0] > 0
 ph = ph[live]
 t0 = ph[:, 0].min()
-names = ["start", "cls+bars+runs", "stream started", "x/binom/cdesc+table", "small classes done (warp 0)"] + [f"class {i} begins" for i in range(5)] + \
+names = ["start", "cls+bars+runs", "stream started", "x/binom/cdesc+table", "small classes done (warp 0)"] + \
+        ["class 0 begins", "last CTA: reduce_slots done", "class 2 begins", "class 3 begins", "class 4 begins"] + \
         ["all warps of the CTA done", "ticket taken", "last CTA: counters reset", "last CTA: ranges built", "last CTA: slots added", "end"]
 print(f"{live.sum()} CTAs; times in us after the first CTA start")
 for s, name in enumerate(names):
