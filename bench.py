@@ -186,6 +186,11 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL_DEBUG=VERSION makes NCCL printf "NCCL version ..." to stdout: keep stdout for the ONE JSON line of the contract
+        # (any other level the caller set -- e.g. INFO to see NVLS -- is left alone and goes where NCCL_DEBUG_FILE says)
+        # (WARN prints the version line as well -- NCCL's showVersion() -- so the variable is dropped, not lowered)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=dev)
 
     dim = WEAK_DIMS.get(world, DIM)
