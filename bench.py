@@ -227,7 +227,8 @@ def run_gpu(args):
     desc.dim = dim
     desc._buf = shard
     out = torch.zeros(1, dtype=torch.float64, device=dev)
-    ws = torch.empty(int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
+    # ST_VEC_OVERLAP launches alternate between the two halves of a double-size workspace
+    ws = torch.empty(2 * int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
 
     rebalanced = None
     if world > 1:
@@ -265,12 +266,14 @@ def run_gpu(args):
         # local streaming kernel over this rank's slice, then (N > 1) the all-reduce of one fp64
         i = counter[0] & 1
         counter[0] += 1
+        # the steps contract RESIDENT operands: every launch is flagged ST_VEC_OVERLAP (programmatic dependent launch), so
+        # the ramp-up of step i + 1 overlaps the tail of step i (one kernel launch per step either way)
         if world == 1:
-            sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, out, ws)
+            sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, out, ws, overlap=True)
             return
         if pending[i] is not None:
             pending[i].wait()
-        pending[i] = sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, outs[i], wss[i], async_op=True)
+        pending[i] = sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, outs[i], wss[i], async_op=True, overlap=True)
 
     def drain():
         for i in range(2):
@@ -304,6 +307,23 @@ def run_gpu(args):
         ms, launches = timed(args.steps)
     ms_per_step = ms / args.steps
     value = n_comps / (ms_per_step * 1e-3)
+    # the same launches WITHOUT the overlap (each launch starts after the previous one has completely finished): the
+    # latency of one isolated contraction, reported next to the pipelined figure
+    isolated = None
+    if world == 1:
+        for _ in range(3):
+            sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, out, ws)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, out, ws)
+        e1.record()
+        torch.cuda.synchronize()
+        iso_ms = e0.elapsed_time(e1) / args.steps
+        isolated = {"ms_per_step": iso_ms, "value": n_comps / (iso_ms * 1e-3), "unit": "packed components/s",
+                    "hbm_gbs": n_comps * 8 / (iso_ms * 1e-3) / 1e9,
+                    "note": "back-to-back launches without ST_VEC_OVERLAP: launch i + 1 starts when launch i has completely finished"}
     result = float(outs[(counter[0] - 1) & 1][0]) if world > 1 else float(out[0])
     serial = None
     if world > 1:
@@ -435,7 +455,7 @@ def run_gpu(args):
                        "l2": "input (549 MB per GPU) is larger than the 126 MB L2: no flush needed", "result": result},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n_comps), "peak_source": peak_src,
-                         "kernel": "vec_ring_kernel<double> (one launch per step: per-warp cp.async.bulk rings, dynamic tile deal, per-tile partial sums added in index order by the last CTA)",
+                         "kernel": "vec_ring_kernel<double> (one launch per step: per-warp cp.async.bulk rings, dynamic tile deal, per-tile partial sums added in index order by the last CTA; launches chained by programmatic dependent launch -- ST_VEC_OVERLAP -- so that consecutive steps overlap ramp-up and tail)",
                          "algorithmic_bytes_per_launch": alg_bytes},
             "clocks": clocks.summary(),
             "gpu_launches": int(launches),
@@ -444,6 +464,8 @@ def run_gpu(args):
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
             line["cpu_packed_oracle"] = cpu_packed
+        if isolated is not None:
+            line["isolated"] = isolated
         if strong is not None:
             line["strong"] = strong
         if serial is not None:

@@ -124,6 +124,18 @@ int st_contract_vec_f64(int layout, int rank, int64_t dim, const double* d_packe
                         const double* d_x, double* d_out, void* d_workspace, void* stream);
 int st_contract_vec_f32(int layout, int rank, int64_t dim, const float* d_packed, int64_t begin, int64_t end,
                         const float* d_x, float* d_out, void* d_workspace, void* stream);
+/* The same launch with `flags`.  ST_VEC_OVERLAP: the call is one of a BATCH of contractions of operands that were complete
+ * before the previous operation on `stream` was enqueued (e.g. one resident tensor contracted with many vectors, or the
+ * steps of a loop over resident tensors): the kernel is then launched as a programmatic dependent of the previous launch
+ * on the stream and starts streaming while that one -- another vector contraction -- drains its tail (ramp-up and tail
+ * of consecutive launches overlap; at most two launches are in flight).  With the flag d_workspace holds
+ * 2 * st_contract_vec_workspace_bytes() bytes (the library alternates between the halves), and d_out is written in
+ * stream order as always.  Without the promise the flag must not be set (the kernel reads d_x / d_packed early). */
+#define ST_VEC_OVERLAP 1
+int st_contract_vec_ex_f64(int layout, int rank, int64_t dim, const double* d_packed, int64_t begin, int64_t end,
+                           const double* d_x, double* d_out, void* d_workspace, int flags, void* stream);
+int st_contract_vec_ex_f32(int layout, int rank, int64_t dim, const float* d_packed, int64_t begin, int64_t end,
+                           const float* d_x, float* d_out, void* d_workspace, int flags, void* stream);
 /* Same op with HOST buffers: streams the packed range through pinned staging buffers in chunks, overlapping
  * the host->device copies with the kernel, and returns the value on the host (synchronises). */
 int st_contract_vec_host_f64(int layout, int rank, int64_t dim, const double* h_packed, int64_t total,

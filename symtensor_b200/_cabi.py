@@ -41,6 +41,8 @@ SIGNATURES = {
     "st_contract_vec_workspace_bytes": (c_i64, []),
     "st_contract_vec_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "st_contract_vec_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "st_contract_vec_ex_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "st_contract_vec_ex_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_vp]),
     "st_contract_vec_host_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "st_contract_vec_host_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_i64, c_vp, c_vp]),
     "st_permcls_to_flat_f64": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp]),
@@ -78,6 +80,7 @@ for _name, (_res, _args) in SIGNATURES.items():
 ST_OK, ST_ERR_INVALID, ST_ERR_CUDA, ST_ERR_UNSUPPORTED, ST_ERR_OVERFLOW = range(5)
 LAYOUT_PERMCLS, LAYOUT_FLAT = 0, 1
 OUTER_MULTIPLY, OUTER_ADD, OUTER_SUBTRACT = 0, 1, 2
+VEC_OVERLAP = 1
 MAX_RANK = 16
 CLASS_ALIGN = 32
 

@@ -233,5 +233,7 @@ int get_device_plan(int rank, int64_t dim, PlanView* out);
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_cuda(cudaError_t e, const char* what);
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (device, kernel) -- the attribute is per device (st_vec.cu)
+int set_max_dynamic_smem(const void* func, int bytes);
 
 }  // namespace st

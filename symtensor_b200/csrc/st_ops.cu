@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(128) gram_umma_kernel(const float* __restrict_
     }
     in_chain += BK;
     // the tiles are overwritten by the next stage: wait for the MMAs of this one
-    if (!wait_bounded(saddr(&bar), phase)) { ok = false; break; }
+    // (the decision to give up is taken by the whole block: a per-thread exit would leave the barriers below divergent)
+    if (!__syncthreads_and(wait_bounded(saddr(&bar), phase) ? 1 : 0)) { ok = false; break; }
     phase ^= 1;
     if (in_chain >= CHAIN || k0 + BK >= K) {
       drain();
@@ -985,12 +986,8 @@ static int tensordot(int ra, int rb, int k, int64_t dim, const T* d_a_flat, cons
   const dim3 grid((unsigned)((s.N + 63) / 64), (unsigned)((s.M + 63) / 64));
   if (grid.y > 65535) { set_error("Gram matrix with %lld rows needs the tiled (non-materialising) kernel", (long long)s.M); return ST_ERR_UNSUPPORTED; }
   if (sizeof(T) == 4 && g_gram_umma) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      rc = check_cuda(cudaFuncSetAttribute(gram_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)umma::SMEM_BYTES), "cudaFuncSetAttribute");
-      if (rc) return rc;
-      attr_set = true;
-    }
+    rc = set_max_dynamic_smem(reinterpret_cast<const void*>(gram_umma_kernel), (int)umma::SMEM_BYTES);
+    if (rc) return rc;
     const dim3 ugrid((unsigned)((s.N + umma::BN - 1) / umma::BN), (unsigned)((s.M + umma::BM - 1) / umma::BM));
     if (ugrid.y > 65535) { set_error("Gram matrix with %lld rows needs the tiled (non-materialising) kernel", (long long)s.M); return ST_ERR_UNSUPPORTED; }
     gram_umma_kernel<<<ugrid, 128, umma::SMEM_BYTES, stream>>>(reinterpret_cast<const float*>(aex), reinterpret_cast<const float*>(bex),

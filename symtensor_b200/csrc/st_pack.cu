@@ -104,7 +104,8 @@ __global__ void __launch_bounds__(256) unpack_flat_fast_kernel(PlanView P, const
 // dense -> packed: one thread per packed coordinate of [begin, end).  mode 0: take the representative entry and CHECK
 // the symmetry of the dense array over the component's distinct permutations, numpy.allclose semantics
 // (|a_p - a_q| <= atol + rtol |a_q| for every ordered pair; one pass: max a <= min (a + tol(a)), min a >= max (a - tol(a)));
-// a violation (or a NaN) raises *flag.  mode 1: symmetrize -- the mean over the distinct permutations, which is the
+// a violation (or a NaN facing a number; a component that is NaN in all its
+// permutations is symmetric, equal_nan=True in the reference) raises *flag.  mode 1: symmetrize -- the mean over the distinct permutations, which is the
 // reference's mean over all rank! axis permutations (every distinct one appears rank!/gamma times).
 template <typename T>
 __global__ void __launch_bounds__(256) pack_dense_kernel(PlanView P, int layout, const T* __restrict__ dense, T* __restrict__ packed, int64_t begin,
@@ -121,14 +122,13 @@ __global__ void __launch_bounds__(256) pack_dense_kernel(PlanView P, int layout,
     // K is sorted: the first of the distinct permutations
     const double rep = (double)dense[dense_offset(r, P.dim, K)];
     double sum = 0.0, mx = rep, mn = rep, minf = rep + (atol + rtol * fabs(rep)), maxg = rep - (atol + rtol * fabs(rep));
-    int64_t cnt = 0;
-    bool nan = rep != rep;
+    int64_t cnt = 0, n_nan = 0;
     do {
       const double a = (double)dense[dense_offset(r, P.dim, K)];
       const double tol = atol + rtol * fabs(a);
       sum += a;
       ++cnt;
-      nan = nan || a != a;
+      n_nan += a != a ? 1 : 0;
       mx = a > mx ? a : mx;
       mn = a < mn ? a : mn;
       minf = a + tol < minf ? a + tol : minf;
@@ -138,7 +138,8 @@ __global__ void __launch_bounds__(256) pack_dense_kernel(PlanView P, int layout,
       packed[c - begin] = (T)(sum / (double)cnt);
     } else {
       packed[c - begin] = (T)rep;
-      if (nan || !(mx <= minf && mn >= maxg)) bad = true;
+      // NaNs: numpy.allclose(..., equal_nan=True) in utils.is_symmetric accepts a component whose permutations are ALL NaN
+      if (n_nan != 0 ? n_nan != cnt : !(mx <= minf && mn >= maxg)) bad = true;
     }
   }
   if (bad && flag) atomicOr(flag, 1);

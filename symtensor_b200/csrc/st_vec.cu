@@ -67,6 +67,7 @@ struct VecArgs {
   int32_t priv_cap;    // vec_ring_kernel: entries of the per-warp xr tables (nwarps * dim, or 0)
   int32_t ring_slots;  // vec_ring_kernel: slots per warp (R)
   int32_t ring_elems;  // vec_ring_kernel: components per slot (Bel; Bel * sizeof(T) is a multiple of 16)
+  int32_t pdl;         // vec_ring_kernel: launched as a programmatic dependent of the previous launch on the stream (ST_VEC_OVERLAP)
 };
 
 // The launch's class records and tile schedule as kernel parameters (rank <= 8: at most 22 classes): computed on
@@ -271,6 +272,19 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
     }
   };
   stamp(0);
+  // Programmatic dependent launch (ST_VEC_OVERLAP): this launch may have started while the previous launch on the
+  // stream -- another vector contraction -- was still draining its tail.  Everything a launch writes before `pdl_sync`
+  // (tile slots, claim counters) lives in the half of the workspace / the counter set of ITS parity, which the launch
+  // before the previous one used; that one is complete, because a CTA lets the next launch go (launch_dependents) only
+  // after it has seen the previous launch complete (wait).  So at most two launches are ever in flight.
+  bool pdl_done = false;
+  auto pdl_sync = [&]() {
+    if (!pdl_done) {
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      pdl_done = true;
+    }
+  };
 
   // ---- 1. class records and the launch's tile schedule (from the kernel parameters when the host could put them
   // there), barriers; the stream starts at once
@@ -479,6 +493,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
           }
         }
         src.close_tile();
+        if (warp == 0) pdl_sync();  // (by now the previous launch is long complete: no stall)
         // a statically dealt entry belongs to this warp whatever happens: its sum needs no slot of its own (the last CTA
         // reads one 32-byte sector per slot, ~0.8 ns each on its one SM) and goes into the warp's sum
         if (a.dynamic && dn < rr.ns) total += tsum;
@@ -560,6 +575,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
           src.close_tile();
           store_tile(dbase + tk, tsum);
         }
+        if (warp == 0) pdl_sync();
       }
     }
     if (a.tl != nullptr && lane == 0 && ci < 8) {
@@ -626,6 +642,7 @@ __global__ void __launch_bounds__(512, 1) vec_ring_kernel(const __grid_constant_
     d[2] = dbg_maxtile;
   }
   // one partial per warp of the grid, added in index order by the last CTA to finish (deterministic)
+  if (warp == 0) pdl_sync();
   total = warp_sum(total);
   if (lane == 0) ctl->red[warp] = total;
   __syncthreads();
@@ -1049,44 +1066,68 @@ static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
 }
 
 static int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
+  static std::mutex mu;
+  static std::map<int, int> counts;  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = counts.find(dev);
+  if (it != counts.end()) return it->second;
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (n <= 0) n = 148;
+  counts[dev] = n;
   return n;
 }
 
-// one {next item, finished CTAs} counter pair per (device, stream); zeroed once, reset by the kernel itself
+// Two sets of {finished CTAs, -, one tile counter per class} per (device, stream), zeroed once and reset by the kernel
+// itself; launches alternate between the sets (and between the halves of an ST_VEC_OVERLAP workspace), so that a launch
+// overlapping the tail of the previous one never touches the previous one's counters or slots.
 static std::mutex g_cmu;
-static std::map<std::pair<int, cudaStream_t>, unsigned long long*> g_counters;
-static int get_counter(cudaStream_t stream, unsigned long long** out) {
+struct CounterSet { unsigned long long* d; int parity; };
+static std::map<std::pair<int, cudaStream_t>, CounterSet> g_counters;
+static int get_counter(cudaStream_t stream, unsigned long long** out, int* parity_out) {
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_cmu);
   auto key = std::make_pair(dev, stream);
   auto it = g_counters.find(key);
-  if (it != g_counters.end()) { *out = it->second; return ST_OK; }
-  unsigned long long* d = nullptr;
-  rc = check_cuda(cudaMalloc(&d, kMaxCounters * sizeof(unsigned long long)), "cudaMalloc(counter)");
+  if (it == g_counters.end()) {
+    unsigned long long* d = nullptr;
+    rc = check_cuda(cudaMalloc(&d, 2 * kMaxCounters * sizeof(unsigned long long)), "cudaMalloc(counter)");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemset(d, 0, 2 * kMaxCounters * sizeof(unsigned long long)), "cudaMemset(counter)");
+    if (rc) return rc;
+    it = g_counters.insert(std::make_pair(key, CounterSet{d, 0})).first;
+  }
+  it->second.parity ^= 1;
+  *parity_out = it->second.parity;
+  *out = it->second.d + (size_t)it->second.parity * kMaxCounters;
+  return ST_OK;
+}
+
+// per-device: the dynamic shared memory opt-in of a kernel and the SM count (a process may drive several devices)
+static std::mutex g_dmu;
+static std::map<std::pair<int, const void*>, bool> g_attr_set;
+int set_max_dynamic_smem(const void* func, int bytes) {
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
-  rc = check_cuda(cudaMemset(d, 0, kMaxCounters * sizeof(unsigned long long)), "cudaMemset(counter)");
+  std::lock_guard<std::mutex> lk(g_dmu);
+  auto key = std::make_pair(dev, func);
+  if (g_attr_set.count(key)) return ST_OK;
+  rc = check_cuda(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes), "cudaFuncSetAttribute");
   if (rc) return rc;
-  g_counters[key] = d;
-  *out = d;
+  g_attr_set[key] = true;
   return ST_OK;
 }
 
 template <typename T>
-static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, int64_t len, int* grid_out, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    int rc = check_cuda(cudaFuncSetAttribute(vec_ring_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024), "cudaFuncSetAttribute");
+static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, int64_t len, int* grid_out, cudaStream_t stream, int flags) {
+  {
+    int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(vec_ring_kernel<T>), 227 * 1024);
     if (rc) return rc;
-    attr_set = true;
   }
   // One resident CTA per SM; tiles are dealt to the warps by the kernel (see RingSrc).
   const int nwarps = se.nwarps;
@@ -1095,9 +1136,16 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
   grid = std::min<int64_t>(grid, (kMaxPartials - kWarpPartOff) / ((nwarps + 3) & ~3));
   grid = std::max<int64_t>(1, std::min<int64_t>(grid, (ntiles + nwarps - 1) / nwarps));
   {
-    int rc = get_counter(stream, &a.counter);
+    int parity = 0;
+    int rc = get_counter(stream, &a.counter, &parity);
     if (rc) return rc;
+    // ST_VEC_OVERLAP: the workspace is two 4 MiB halves, one per parity
+    if ((flags & ST_VEC_OVERLAP) && parity) {
+      if (a.sum_out == a.partials) a.sum_out = a.partials + kWsSlots;
+      a.partials += kWsSlots;
+    }
   }
+  a.pdl = (flags & ST_VEC_OVERLAP) ? 1 : 0;
   a.dynamic = (g_ring_dynamic && hp->ncls <= kMaxCounters - 2) ? 1 : 0;
   a.ondemand = g_ring_ondemand;
   RingSched sched;
@@ -1117,7 +1165,24 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
               a.dynamic ? g_ring_group : 1, g_ring_fine, g_ring_fine_pos);
     sched.n = hp->ncls;
   }
-  vec_ring_kernel<T><<<(int)grid, nwarps * 32, se.smem_bytes, stream>>>(a, sched);
+  if (flags & ST_VEC_OVERLAP) {
+    // programmatic dependent launch: the launch may begin once every CTA of the previous launch on the stream has let it
+    // go (griddepcontrol.launch_dependents in vec_ring_kernel), i.e. while that launch drains its tail
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)(nwarps * 32));
+    cfg.dynamicSmemBytes = se.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int rc = check_cuda(cudaLaunchKernelEx(&cfg, vec_ring_kernel<T>, a, sched), "cudaLaunchKernelEx(vec_ring_kernel)");
+    if (rc) return rc;
+  } else {
+    vec_ring_kernel<T><<<(int)grid, nwarps * 32, se.smem_bytes, stream>>>(a, sched);
+  }
   *grid_out = 1;  // the kernel leaves the launch's sum in partials[0]
   return ST_OK;
 }
@@ -1126,7 +1191,7 @@ static int launch_ring(VecArgs<T>& a, const StratEntry& se, const HostPlan* hp, 
 // tail kernel also reduces them (`*fused` = true); otherwise (or on the generic path) the caller finalizes.
 template <typename T>
 static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, int64_t begin, int64_t end, const T* d_x,
-                        double* partials, int* grid_out, T* d_out, bool* fused, cudaStream_t stream, double* ring_ws = nullptr) {
+                        double* partials, int* grid_out, T* d_out, bool* fused, cudaStream_t stream, double* ring_ws = nullptr, int flags = 0) {
   // `ring_ws`: separate workspace (kWsSlots) for vec_ring_kernel, whose only output is then partials[0]
   if (fused) *fused = false;
   if (layout != ST_LAYOUT_PERMCLS && layout != ST_LAYOUT_FLAT) { set_error("unknown layout %d", layout); return ST_ERR_INVALID; }
@@ -1162,6 +1227,7 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   a.dynamic = 0;
   a.ondemand = 2;
   a.sum_out = partials;
+  a.pdl = 0;
   a.tl = g_timeline;
   *grid_out = 1;
   if (end == begin) return check_cuda(cudaMemsetAsync(partials, 0, sizeof(double), stream), "cudaMemsetAsync");
@@ -1187,7 +1253,7 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
     a.priv_cap = se.priv_cap;
     a.tile_elems = se.tile_elems;
     if (ring_ws) a.partials = ring_ws;
-    rc = launch_ring<T>(a, se, get_host_plan(rank, dim), end - begin, grid_out, stream);
+    rc = launch_ring<T>(a, se, get_host_plan(rank, dim), end - begin, grid_out, stream, flags);
     if (rc) return rc;
     count_launch();
     if (fused) *fused = d_out != nullptr;
@@ -1213,12 +1279,13 @@ static int vec_finalize(const double* partials, int n, T* d_out, cudaStream_t st
 
 template <typename T>
 static int contract_vec(int layout, int rank, int64_t dim, const T* d_packed, int64_t begin, int64_t end, const T* d_x,
-                        T* d_out, void* d_ws, cudaStream_t stream) {
+                        T* d_out, void* d_ws, cudaStream_t stream, int flags = 0) {
   if (!d_out || !d_ws) { set_error("null pointer"); return ST_ERR_INVALID; }
+  if (flags & ~ST_VEC_OVERLAP) { set_error("unknown flags 0x%x", flags); return ST_ERR_INVALID; }
   double* partials = reinterpret_cast<double*>(d_ws);
   int grid = 1;
   bool fused = false;
-  int rc = vec_partials<T>(layout, rank, dim, d_packed, begin, end, d_x, partials, &grid, d_out, &fused, stream);
+  int rc = vec_partials<T>(layout, rank, dim, d_packed, begin, end, d_x, partials, &grid, d_out, &fused, stream, nullptr, flags);
   if (rc) return rc;
   if (fused) return ST_OK;
   return vec_finalize<T>(partials, grid, d_out, stream);
@@ -1438,6 +1505,16 @@ int st_contract_vec_f64(int layout, int rank, int64_t dim, const double* d_packe
 int st_contract_vec_f32(int layout, int rank, int64_t dim, const float* d_packed, int64_t begin, int64_t end,
                         const float* d_x, float* d_out, void* d_workspace, void* stream) {
   return contract_vec<float>(layout, rank, dim, d_packed, begin, end, d_x, d_out, d_workspace, (cudaStream_t)stream);
+}
+
+int st_contract_vec_ex_f64(int layout, int rank, int64_t dim, const double* d_packed, int64_t begin, int64_t end,
+                           const double* d_x, double* d_out, void* d_workspace, int flags, void* stream) {
+  return contract_vec<double>(layout, rank, dim, d_packed, begin, end, d_x, d_out, d_workspace, (cudaStream_t)stream, flags);
+}
+
+int st_contract_vec_ex_f32(int layout, int rank, int64_t dim, const float* d_packed, int64_t begin, int64_t end,
+                           const float* d_x, float* d_out, void* d_workspace, int flags, void* stream) {
+  return contract_vec<float>(layout, rank, dim, d_packed, begin, end, d_x, d_out, d_workspace, (cudaStream_t)stream, flags);
 }
 
 int st_contract_vec_host_f64(int layout, int rank, int64_t dim, const double* h_packed, int64_t total, const double* h_x,

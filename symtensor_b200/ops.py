@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import symalg
-from ._cabi import c_i64, check, lib
+from ._cabi import VEC_OVERLAP, c_i64, check, lib
 from .flat import CudaFlatSymmetricTensor
 from .permcls import _NP2TORCH, _TORCH2NP, CudaPermClsSymmetricTensor, _stream_ptr
 
@@ -42,14 +42,49 @@ def _all_close_to_zero(x) -> bool:
 
 
 def contract_vec_device(A, x_dev: torch.Tensor, out: torch.Tensor, ws: torch.Tensor, begin: int = 0, end: int = None,
-                        packed: torch.Tensor = None) -> None:
+                        packed: torch.Tensor = None, overlap: bool = False) -> None:
     """Raw launch: partial sum of packed coordinates [begin, end) into the 0-d/1-element ``out``.
-    ``packed`` is the local shard starting at coordinate ``begin`` (default: the whole buffer)."""
+    ``packed`` is the local shard starting at coordinate ``begin`` (default: the whole buffer).
+    ``overlap`` (``ST_VEC_OVERLAP``): the call belongs to a batch of contractions of resident operands -- the launch starts
+    while the previous one on the stream drains its tail; ``ws`` then holds ``2 * st_contract_vec_workspace_bytes()``."""
     packed = A._buf if packed is None else packed
     total = A._buf.numel() if (end is None and packed is A._buf) else end
-    fn = lib.st_contract_vec_f64 if packed.dtype == torch.float64 else lib.st_contract_vec_f32
+    f64 = packed.dtype == torch.float64
+    if overlap:
+        if ws.numel() * ws.element_size() < 2 * _WS_BYTES:
+            raise ValueError("overlapping launches need a workspace of 2 * st_contract_vec_workspace_bytes()")
+        fn = lib.st_contract_vec_ex_f64 if f64 else lib.st_contract_vec_ex_f32
+        check(fn(A.layout, A.rank, c_i64(A.dim), packed.data_ptr(), c_i64(begin), c_i64(total), x_dev.data_ptr(),
+                 out.data_ptr(), ws.data_ptr(), VEC_OVERLAP, _stream_ptr(packed.device)))
+        return
+    fn = lib.st_contract_vec_f64 if f64 else lib.st_contract_vec_f32
     check(fn(A.layout, A.rank, c_i64(A.dim), packed.data_ptr(), c_i64(begin), c_i64(total), x_dev.data_ptr(),
              out.data_ptr(), ws.data_ptr(), _stream_ptr(packed.device)))
+
+
+def contract_all_indices_with_vectors(symtensor, X):
+    """Batch form of ``contract_all_indices_with_vector`` (symtensor/symalg.py:505-527): one resident tensor contracted
+    with every row of ``X`` (``n x dim``) -- the polynomial evaluated at n points.  One kernel launch per row, chained with
+    ``ST_VEC_OVERLAP`` so that consecutive launches overlap their ramp-up and tail.  Returns a length-n torch tensor."""
+    _need_device(symtensor)
+    dev = symtensor.device
+    Xt = X if isinstance(X, torch.Tensor) else torch.as_tensor(np.asarray(X))
+    if Xt.ndim != 2 or Xt.shape[1] != symtensor.dim:
+        raise ValueError(f"X must have shape (n, {symtensor.dim}); received {tuple(Xt.shape)}")
+    tdt = _promote(symtensor.dtype, Xt)
+    buf = symtensor._buf if symtensor._buf.dtype == tdt else symtensor._buf.to(tdt)
+    n = Xt.shape[0]
+    with torch.cuda.device(dev):
+        Xd = Xt.to(device=dev, dtype=tdt).contiguous()
+        out = torch.zeros(max(n, 1), dtype=tdt, device=dev)
+        ws = torch.empty(2 * _WS_BYTES // 8, dtype=torch.float64, device=dev)
+        torch.cuda.current_stream(dev).synchronize()  # the operands are complete: the launches below may start early
+        fn = lib.st_contract_vec_ex_f64 if tdt == torch.float64 else lib.st_contract_vec_ex_f32
+        sp = _stream_ptr(dev)
+        for i in range(n):
+            check(fn(type(symtensor).layout, symtensor.rank, c_i64(symtensor.dim), buf.data_ptr(), c_i64(0), c_i64(buf.numel()),
+                     Xd[i].data_ptr(), out[i:].data_ptr(), ws.data_ptr(), VEC_OVERLAP, sp))
+    return out[:n]
 
 
 def _contract_all_indices_with_vector(symtensor, x):

@@ -241,3 +241,33 @@ def test_large_rank_configs_via_identities(rank, dim, dtype):
     check(lib.st_set_vec_variant(1))
     b = float(st.contract_all_indices_with_vector(A, x))
     assert abs(a - b) <= tol * abs(b)
+
+
+@pytest.mark.parametrize("rank,dim,dtype", [(4, 200, np.float64), (4, 50, np.float64), (6, 30, np.float64), (3, 400, np.float32), (5, 9, np.float64)])
+def test_overlapped_batch_equals_single_launches(rank, dim, dtype):
+    """ST_VEC_OVERLAP (programmatic dependent launch: launch i + 1 starts while launch i drains its tail, alternating
+    workspace halves and claim-counter sets): a batch of contractions of one resident tensor with n vectors gives, bit for
+    bit, the results of n isolated launches -- the result does not depend on the tile deal -- and matches the oracle."""
+    t = comb.class_table(rank, dim)
+    g = torch.Generator(device=DEV)
+    g.manual_seed(rank * 1000 + dim)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    buf = (torch.rand(t.total, generator=g, dtype=torch.float64, device=DEV) + 0.5).to(tdt)
+    for i in range(t.ncls):
+        buf[t.offsets[i] + t.sizes[i]:t.offsets[i + 1]] = 0
+    A = st.PermClsTorchSymmetricTensor.from_packed(rank, dim, buf)
+    rng = np.random.default_rng(dim)
+    n = 9
+    X = (rng.uniform(0.5, 1.5, (n, dim)) / np.sqrt(dim)).astype(dtype)
+    batch = ops.contract_all_indices_with_vectors(A, X).cpu().numpy()
+    single = np.array([float(st.contract_all_indices_with_vector(A, X[i])) for i in range(n)], dtype=dtype)
+    assert np.array_equal(batch, single)
+    batch2 = ops.contract_all_indices_with_vectors(A, X).cpu().numpy()  # and is reproducible run to run
+    assert np.array_equal(batch, batch2)
+    if t.total <= 2_000_000:
+        host = {c: A._data[c].cpu().numpy().astype(np.float64) for c in t.classes}
+        for i in (0, n - 1):
+            ref = po.contract_all_indices_with_vector(host, rank, dim, X[i].astype(np.float64))
+            assert abs(float(batch[i]) - ref) <= (RTOL64 if dtype == np.float64 else RTOL32) * abs(ref)
+    with pytest.raises(ValueError):
+        ops.contract_all_indices_with_vectors(A, X[:, :-1])
