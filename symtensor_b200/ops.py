@@ -168,18 +168,31 @@ def comb_total(rank: int, dim: int) -> int:
 
 
 def _as_symtensor_operand(x, like):
-    """ndarray / torch operands of tensordot and outer: vectors and scalars are symmetric tensors already; a
-    higher-rank dense array must be symmetric (it is packed through the class constructor, which checks)."""
+    """ndarray / torch / scalar operands of tensordot and outer.  Vectors and scalars are symmetric tensors already.  A
+    dense array of rank >= 2 must be symmetric: the reference accepts ARBITRARY dense operands there and symmetrizes only
+    the result (``Sym(np.tensordot(a.todense(), b, axes))``, symtensor/symalg.py:427-459, 294-316), which for a
+    non-symmetric operand is a partially symmetric contraction the packed kernels do not implement -- that case raises
+    ``NotImplementedError`` (documented deviation; ``symtensor_b200.plugin`` hands it to the reference's own default).
+    Python scalars are weakly typed like in NumPy (fp32 tensor * 2.0 stays fp32)."""
     if isinstance(x, _SYM):
         return x
+    if isinstance(x, (bool, int, float)):
+        x = torch.tensor(x, dtype=like.torch_dtype)
     arr = x if isinstance(x, torch.Tensor) else np.asarray(x)
     nd = arr.ndim
     if nd == 0:
         return type(like)(rank=0, dim=1, data={(): arr} if isinstance(like, CudaPermClsSymmetricTensor) else arr, device=like.device)
-    if isinstance(like, CudaPermClsSymmetricTensor):
-        return CudaPermClsSymmetricTensor(data=arr, device=like.device) if nd > 1 else \
-            CudaPermClsSymmetricTensor(rank=1, dim=arr.shape[0], data={(1,): arr}, device=like.device)
-    return CudaFlatSymmetricTensor(nd, arr.shape[0], arr, device=like.device)
+    try:
+        if isinstance(like, CudaPermClsSymmetricTensor):
+            return CudaPermClsSymmetricTensor(data=arr, device=like.device) if nd > 1 else \
+                CudaPermClsSymmetricTensor(rank=1, dim=arr.shape[0], data={(1,): arr}, device=like.device)
+        return CudaFlatSymmetricTensor(nd, arr.shape[0], arr, device=like.device)
+    except ValueError as e:
+        if "not symmetric" in str(e):
+            raise NotImplementedError("symtensor_b200: tensordot / outer with a NON-symmetric dense operand of rank >= 2 is not "
+                                      "implemented on the packed kernels (the reference symmetrizes only the result); symmetrize the "
+                                      "operand or use the reference default") from e
+        raise
 
 
 def _result_dtype(a, b) -> torch.dtype:

@@ -53,8 +53,15 @@ def flat_host(T, dtype=np.float64):
     return ops._flat_buffer(T, T.torch_dtype).cpu().numpy().astype(dtype)
 
 
+def rep_index(cls, dim, pos):
+    """Representative multi-index of component `pos` of class `cls`: the distinct values (class order) repeated by their
+    multiplicities (get_index_representative, symtensor/permcls_symtensor.py:375-381)."""
+    vals = io.permcls_unrank(cls, dim, int(pos))
+    return tuple(v for v, m in zip(vals, cls) for _ in range(m))
+
+
 def sorted_indices(cls, dim, positions):
-    return np.array([sorted(io.permcls_unrank(cls, dim, int(p))) for p in positions], dtype=np.int64).reshape(len(positions), sum(cls))
+    return np.array([sorted(rep_index(cls, dim, p)) for p in positions], dtype=np.int64).reshape(len(positions), sum(cls))
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -94,7 +101,7 @@ def test_config4_identity_and_permutation_are_bit_exact(c4_tensor):
     for cls in table.classes:
         ci = table.index(cls)
         pos = sample_positions(table.sizes[ci], 150, rng)
-        J = np.array([io.permcls_unrank(cls, dim, int(q)) for q in pos], dtype=np.int64)
+        J = np.array([rep_index(cls, dim, q) for q in pos], dtype=np.int64)
         want = _gather_components(a_host, table, dim, p[J])
         got = c_host[table.offsets[ci] + pos]
         assert np.array_equal(got, want), cls
@@ -124,7 +131,7 @@ def test_config4_windows_against_the_packed_direct_form(c4_tensor):
         ci = table.index(cls)
         pos = sample_positions(table.sizes[ci], 40, rng)
         for q in pos:
-            J = io.permcls_unrank(cls, dim, int(q))
+            J = rep_index(cls, dim, q)
             terms = []
             for ch in choices:
                 I = [rows[b, j] for b, j in zip(ch, J)]

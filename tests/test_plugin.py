@@ -1,0 +1,114 @@
+"""The drop-in claim, exercised: ``symtensor_b200.plugin.bind()`` registers the CUDA implementations on a subclass of the
+REAL reference class ``PermClsTorchSymmetricTensor`` through the reference's own ``@Cls.implements`` /
+``@Cls.implements_ufunc.outer`` decorators (symtensor/base.py:259-322, 1057-1063), and the reference's own generic API suite
+(symtensor/testing/api.py, bound with its one-fixture pattern as in symtensor/tests/test_permcls_torch.py) runs against it.
+
+The unmodified reference package is imported from ``baseline/_ref`` (staged by ``__graft_entry__.build()`` in the build
+container; it travels to the GPU box) through the stand-ins of ``oracle/ref_shim`` for its four uninstallable
+dependencies; every test here is skipped when that copy is absent.
+
+  * not gpu: the class is created, the registries hold OUR implementations, dispatch through ``symalg`` reaches them (without a
+    CUDA device they raise this backend's RuntimeError -- there is no CPU fallback to land on);
+  * gpu: the hot-path tests of the reference's API suite (outer product, tensordot, matrix and vector contractions) with
+    ``SymTensor`` = the bound class, plus the rest of the suite to show the class is otherwise the reference's own.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+SHIM = os.path.join(ROOT, "oracle", "ref_shim")
+
+if not os.path.isdir(os.path.join(REF, "symtensor")):
+    pytest.skip("baseline/_ref (the staged reference) is absent", allow_module_level=True)
+
+warnings.filterwarnings("ignore")
+for p in (REF, SHIM):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import symtensor  # noqa: E402  (the unmodified reference)
+from symtensor import symalg, utils  # noqa: E402
+from symtensor.torch_symtensor import PermClsTorchSymmetricTensor  # noqa: E402
+from symtensor.tests.test_permcls_torch import TestPermClsTorchSymtensorAPI as _RefTorchAPI  # noqa: E402
+
+from symtensor_b200 import plugin  # noqa: E402
+
+B200 = plugin.bind()
+HAS_GPU = torch.cuda.is_available()
+
+
+def test_bound_class_is_a_reference_subclass_with_our_registrations():
+    assert issubclass(B200, PermClsTorchSymmetricTensor) and B200.data_format == "PermCls"
+    impls = B200.b200_impls
+    # the subclass registries shadow the parents' entries, which stay untouched (symtensor/base.py:682-698)
+    for f, name in [(symalg.contract_all_indices_with_vector, "contract_all_indices_with_vector"),
+                    (symalg.contract_all_indices_with_matrix, "contract_all_indices_with_matrix"),
+                    (symalg.tensordot, "tensordot")]:
+        assert B200._HANDLED_FUNCTIONS[f] is impls[name]
+        assert PermClsTorchSymmetricTensor._HANDLED_FUNCTIONS[f] is not impls[name]
+    for uf in (symalg.add, symalg.subtract, symalg.multiply):
+        assert B200._HANDLED_UFUNCS["outer"][uf].func is impls["outer"]
+        assert PermClsTorchSymmetricTensor._HANDLED_UFUNCS["outer"][uf].func is not impls["outer"]
+    assert plugin.bind() is B200  # idempotent
+    # the rest of the class is the reference's own: construction, indexing, σ-class storage
+    A = B200(rank=3, dim=3)
+    A[0, 0, 1] = -12.0
+    assert float(A["iij"][0]) == -12.0 and list(A.perm_classes) == ["iii", "iij", "ijk"]
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-CUDA behaviour")
+def test_dispatch_reaches_the_backend_and_there_is_no_cpu_fallback():
+    A = B200(rank=3, dim=3, data=1.0)
+    x = np.ones(3)
+    for call in (lambda: symalg.contract_all_indices_with_vector(A, x),
+                 lambda: symalg.contract_all_indices_with_matrix(A, np.eye(3)),
+                 lambda: symalg.tensordot(A, A, axes=1),
+                 lambda: symalg.multiply.outer(A, A)):
+        with pytest.raises(RuntimeError, match="CUDA device"):
+            call()
+    # the reference's early exits are mirrored before any device work
+    assert symalg.contract_all_indices_with_vector(A, np.zeros(3)) == 0
+    with pytest.raises(ValueError):
+        symalg.contract_all_indices_with_vector(A, np.ones(4))
+
+
+@pytest.mark.gpu
+class TestB200AgainstTheReferenceAPISuite(_RefTorchAPI):
+    """symtensor/testing/api.py with ``SymTensor`` = the bound class: the reference's own tests of the hot path
+    (test_outer_product :474-512, test_tensordot :556-566, test_contract_all_indices_with_matrix :576-611,
+    test_contract_all_indices :657-672) now run on the CUDA kernels, everything else on the reference's own code."""
+
+    @pytest.fixture
+    def SymTensor(self):
+        return B200
+
+    def test_serialization(self, SymTensor):
+        pytest.skip("needs the real scityping.Serializable (the stand-in of oracle/ref_shim does not serialise); not on the hot path")
+
+    def test_hot_path_results_come_from_the_cuda_library(self, SymTensor):
+        """The four ops on the bound class launch this library's kernels (st_launch_count grows) and agree with the
+        reference's dense defaults computed by the PARENT class on the same data."""
+        from symtensor_b200._cabi import lib
+        rng = np.random.default_rng(7)
+        d = 4
+        A = SymTensor(rank=3, dim=d)
+        A["iii"] = rng.normal(size=utils._get_permclass_size((3,), d))
+        A["iij"] = rng.normal(size=utils._get_permclass_size((2, 1), d))
+        A["ijk"] = rng.normal(size=utils._get_permclass_size((1, 1, 1), d))
+        P = PermClsTorchSymmetricTensor(rank=3, dim=d, data={k: v.clone() for k, v in A._data.items()})
+        x, W = rng.normal(size=d), rng.normal(size=(d, d))
+        n0 = lib.st_launch_count()
+        got = [symalg.contract_all_indices_with_vector(A, x), symalg.contract_all_indices_with_matrix(A, W),
+               symalg.tensordot(A, A, axes=1), symalg.multiply.outer(A, A)]
+        assert lib.st_launch_count() > n0
+        want = [symalg.contract_all_indices_with_vector(P, x), symalg.contract_all_indices_with_matrix(P, W),
+                symalg.tensordot(P, P, axes=1), symalg.multiply.outer(P, P)]
+        for g, w in zip(got, want):
+            assert type(g) is SymTensor
+            assert np.allclose(np.asarray(g.todense()), np.asarray(w.todense()), rtol=1e-10, atol=1e-12)
