@@ -209,6 +209,12 @@ int st_outer_vec_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const f
  * the reference returns dim 1).  d_workspace: st_tensordot_workspace_bytes() bytes.
  * ------------------------------------------------------------------------------------------------ */
 int st_tensordot_workspace_bytes(int ra, int rb, int k, int64_t dim, int elem_size, int64_t* out_bytes);
+/* 1 when st_tensordot_* serves (ra, rb, k, dim, elem_size) with the tiled NON-MATERIALISING kernel (fp32, two free indices on
+ * each side: BASELINE config 3): the six Gram terms of an 8 x 16 x 16 x 16 output tile are three 128 x 256 tcgen05 GEMMs over
+ * TMA-staged operand boxes, added straight into the packed output (which is zeroed first); the workspace then holds the
+ * expanded, hi/lo-split pair matrices (16 dim^2 Kp bytes) and its first int is an error flag the kernel raises if a
+ * bounded barrier wait expired (read it after synchronising the stream). */
+int st_tensordot_is_tiled(int ra, int rb, int k, int64_t dim, int elem_size);
 int st_tensordot_f64(int ra, int rb, int k, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out,
                      int64_t begin, int64_t end, void* d_workspace, void* stream);
 int st_tensordot_f32(int ra, int rb, int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out,

@@ -61,6 +61,7 @@ SIGNATURES = {
     "st_outer_vec_f64": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_outer_vec_f32": (c_int, [c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "st_tensordot_workspace_bytes": (c_int, [c_int, c_int, c_int, c_i64, c_int, c_i64p]),
+    "st_tensordot_is_tiled": (c_int, [c_int, c_int, c_int, c_i64, c_int]),
     "st_tensordot_f64": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "st_tensordot_f32": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "st_contract_mat_workspace_bytes": (c_int, [c_int, c_i64, c_int, c_i64p]),

@@ -177,6 +177,18 @@ ST_HD void flat_unrank_sorted(const PlanView& P, int64_t pos, int32_t* s) {
   for (int k = 0; k < P.rank; ++k) s[k] -= k;
 }
 
+// flat position of the sorted r-tuple s (r <= plan rank), using the plan's binomial table
+ST_HD int64_t flat_rank_r(const PlanView& P, const int32_t* s, int r) {
+  int64_t pos = binom_at(P.binom, P.rank, P.dim + r - 1, r) - 1;
+  for (int k = 0; k < r; ++k) pos -= binom_at(P.binom, P.rank, P.dim - 1 + k - s[r - 1 - k], k + 1);
+  return pos;
+}
+
+ST_HD void flat_unrank_r(const PlanView& P, int64_t pos, int r, int32_t* s) {
+  comb_unrank(P.binom, P.rank, pos, P.dim + r - 1, r, s);
+  for (int k = 0; k < r; ++k) s[k] -= k;
+}
+
 // class containing the packed coordinate c (offsets ascending); padding belongs to the class before it
 ST_HD int class_of_coord(const PlanView& P, int64_t c) {
   int lo = 0, hi = P.ncls - 1;

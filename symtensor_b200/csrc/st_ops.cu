@@ -23,18 +23,6 @@
 
 namespace st {
 
-// flat position of the sorted r-tuple s (r <= plan rank), using the plan's binomial table
-ST_HD int64_t flat_rank_r(const PlanView& P, const int32_t* s, int r) {
-  int64_t pos = binom_at(P.binom, P.rank, P.dim + r - 1, r) - 1;
-  for (int k = 0; k < r; ++k) pos -= binom_at(P.binom, P.rank, P.dim - 1 + k - s[r - 1 - k], k + 1);
-  return pos;
-}
-
-ST_HD void flat_unrank_r(const PlanView& P, int64_t pos, int r, int32_t* s) {
-  comb_unrank(P.binom, P.rank, pos, P.dim + r - 1, r, s);
-  for (int k = 0; k < r; ++k) s[k] -= k;
-}
-
 // ------------------------------------------------------------------------------------------------------
 // layout converters (also the "pack / unpack" step either side of the ops: permcls <-> flat re-ordering)
 // ------------------------------------------------------------------------------------------------------
@@ -943,6 +931,18 @@ static int outer_vec(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_
   return check_cuda(cudaGetLastError(), "outer_vec_kernel");
 }
 
+// st_sym22.cu: non-materialising tcgen05 kernel for two free indices on each side (fp32)
+namespace s22 {
+int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin, int64_t end, void* d_ws,
+                    cudaStream_t stream);
+int workspace_bytes(int k, int64_t dim, int64_t* out);
+}
+int g_sym22 = 1;             // fp32 tensordot with 2 + 2 free indices through the tiled kernel (0: always the materialised Gram matrix)
+int64_t g_sym22_min_dim = 96;  // ... from this dimension on (tuning key "sym22_min_dim": tests lower it to reach the kernel at small sizes)
+static bool use_sym22(int ra, int rb, int k, int64_t dim, int elem_size) {
+  return g_sym22 && elem_size == 4 && k >= 1 && ra - k == 2 && rb - k == 2 && dim >= g_sym22_min_dim;
+}
+
 struct TdotShape {
   int na, nb, n, R;
   int64_t M, N, K;
@@ -978,6 +978,9 @@ static int tensordot(int ra, int rb, int k, int64_t dim, const T* d_a_flat, cons
   if (begin < 0 || end < begin || end > Pn.total) { set_error("range outside the packed output"); return ST_ERR_INVALID; }
   if (end == begin) return ST_OK;
   if (!d_a_flat || !d_b_flat || !d_out || !d_ws) { set_error("null pointer"); return ST_ERR_INVALID; }
+  if (use_sym22(ra, rb, k, dim, (int)sizeof(T)))
+    return s22::tensordot_sym22(k, dim, reinterpret_cast<const float*>(d_a_flat), reinterpret_cast<const float*>(d_b_flat),
+                                reinterpret_cast<float*>(d_out), begin, end, d_ws, stream);
   T* aex = reinterpret_cast<T*>(d_ws);
   T* bex = aex + s.M * s.K;
   T* G = bex + s.N * s.K;
@@ -1117,11 +1120,13 @@ int st_tensordot_workspace_bytes(int ra, int rb, int k, int64_t dim, int elem_si
   int rc = tdot_shape(ra, rb, k, dim, &s);
   if (rc) return rc;
   if (!out_bytes) { set_error("null pointer"); return ST_ERR_INVALID; }
+  if (use_sym22(ra, rb, k, dim, elem_size)) return s22::workspace_bytes(k, dim, out_bytes);
   const __int128 elems = k == 0 ? 0 : (__int128)s.M * s.K + (__int128)s.N * s.K + (__int128)s.M * s.N;
   if (elems * elem_size > (__int128)INT64_MAX) { set_error("workspace does not fit int64"); return ST_ERR_OVERFLOW; }
   *out_bytes = (int64_t)elems * elem_size;
   return ST_OK;
 }
+int st_tensordot_is_tiled(int ra, int rb, int k, int64_t dim, int elem_size) { return use_sym22(ra, rb, k, dim, elem_size) ? 1 : 0; }
 int st_tensordot_f64(int ra, int rb, int k, int64_t dim, const double* d_a_flat, const double* d_b_flat, double* d_out, int64_t begin,
                      int64_t end, void* d_workspace, void* stream) {
   return tensordot<double>(ra, rb, k, dim, d_a_flat, d_b_flat, d_out, begin, end, d_workspace, (cudaStream_t)stream);

@@ -295,22 +295,38 @@ def _tensordot(a, b, axes=2):
     dim = a.dim
     n = a.rank + b.rank - 2 * k
     out_dim = dim if n else 1
-    af, bf = _flat_buffer(a, tdt), _flat_buffer(b, tdt)
-    nbytes = c_i64(0)
-    check(lib.st_tensordot_workspace_bytes(a.rank, b.rank, k, c_i64(dim), af.element_size(), ctypes.byref(nbytes)))
-    if nbytes.value > 64 << 30:
-        raise NotImplementedError(f"symtensor_b200.tensordot: the pair-packed Gram matrix needs {nbytes.value / 2 ** 30:.0f} GiB; "
-                                  "sizes beyond one GPU need the tiled kernel (not in this build)")
     total = comb_total(n, out_dim)
-    with torch.cuda.device(af.device):
-        ws = torch.empty(max(1, nbytes.value // af.element_size()), dtype=tdt, device=af.device)
-        buf = torch.empty(total, dtype=tdt, device=af.device)
-        check(_fn("st_tensordot", tdt)(a.rank, b.rank, k, c_i64(dim), af.data_ptr(), bf.data_ptr(), buf.data_ptr(), c_i64(0),
-                                       c_i64(total), ws.data_ptr(), _stream_ptr(af.device)))
+    with torch.cuda.device(a.device):
+        buf = torch.empty(total, dtype=tdt, device=a.device)
+    tensordot_device(a, b, k, buf, 0, total, tdt)
     res = CudaPermClsSymmetricTensor.from_packed(n, out_dim, buf)
     if issubclass(cls, CudaFlatSymmetricTensor):
         return cls.from_packed(n, out_dim, _flat_buffer(res, tdt))
     return res if cls is CudaPermClsSymmetricTensor else cls.from_packed(n, out_dim, buf)
+
+
+def tensordot_device(a, b, k: int, out_range_buf: torch.Tensor, begin: int, end: int, tdt: torch.dtype, af=None, bf=None, ws=None,
+                     check_flag: bool = True):
+    """Raw launch: coordinates [begin, end) of the permcls buffer of ``tensordot(a, b, axes=k)`` into ``out_range_buf`` (which starts
+    at coordinate ``begin``) -- the output range is the sharding axis for multi-GPU runs (BASELINE config 3's 168 GB output only
+    exists sharded).  fp32 with two free indices on each side runs the tiled tcgen05 kernel (``st_tensordot_is_tiled``), everything
+    else the materialised Gram matrix."""
+    af = _flat_buffer(a, tdt) if af is None else af
+    bf = _flat_buffer(b, tdt) if bf is None else bf
+    nbytes = c_i64(0)
+    check(lib.st_tensordot_workspace_bytes(a.rank, b.rank, k, c_i64(a.dim), af.element_size(), ctypes.byref(nbytes)))
+    tiled = bool(lib.st_tensordot_is_tiled(a.rank, b.rank, k, c_i64(a.dim), af.element_size()))
+    if nbytes.value > 150 << 30:
+        raise NotImplementedError(f"symtensor_b200.tensordot: the workspace of this shape needs {nbytes.value / 2 ** 30:.0f} GiB "
+                                  "(the materialised pair-packed Gram matrix; only fp32 with two free indices per side has the tiled kernel)")
+    with torch.cuda.device(af.device):
+        if ws is None:
+            ws = torch.empty(max(1, (nbytes.value + af.element_size() - 1) // af.element_size()), dtype=tdt, device=af.device)
+        check(_fn("st_tensordot", tdt)(a.rank, b.rank, k, c_i64(a.dim), af.data_ptr(), bf.data_ptr(), out_range_buf.data_ptr(), c_i64(begin),
+                                       c_i64(end), ws.data_ptr(), _stream_ptr(af.device)))
+        if tiled and check_flag and int(ws[:1].view(torch.int32)[0].item()) != 0:
+            raise RuntimeError("symtensor_b200.tensordot: the tiled tcgen05 kernel gave up on a barrier (internal error; the result is invalid)")
+    return ws
 
 
 def _contract_all_indices_with_matrix(symtensor, W):

@@ -249,3 +249,42 @@ def test_config3_ladder_rung_windows(c3_operands):
         want, mag = _tensordot_components(af, bf, 3, 2, dim, K)
         got = c_host[table.offsets[ci] + pos].astype(np.float64)
         assert np.all(np.abs(got - want) <= 1e-5 * mag), (cls, np.max(np.abs(got - want) / mag))
+
+
+def test_config3_full_operands_output_ranges_windows(c3_operands):
+    """BASELINE config 3 itself -- rank 3 . rank 3 over one index at dim 1000 (output rank 4, 41,917,125,250 components =
+    167.7 GB, which only exists sharded): the tiled tcgen05 kernel computes RANGES of the packed output from the full-size
+    operands, exactly what one GPU of an 8-GPU run does for its slice; random windows of every range against the packed
+    formula in fp64 (1e-5 of the sum of |terms|).  Ranges: the start of the buffer (the four small classes and the first
+    components of class (1,1,1,1)), a slice from the middle, and the very end."""
+    from symtensor_b200._cabi import c_i64, lib
+    A, B = c3_operands
+    dim = 1000
+    assert lib.st_tensordot_is_tiled(3, 3, 1, c_i64(dim), 4) == 1
+    table = comb.class_table(4, dim)
+    total = table.total
+    af_d, bf_d = ops._flat_buffer(A, torch.float32), ops._flat_buffer(B, torch.float32)
+    af, bf = af_d.cpu().numpy().astype(np.float64), bf_d.cpu().numpy().astype(np.float64)
+    rng = np.random.default_rng(333)
+    n_small = table.offsets[4]                      # start of class (1,1,1,1)
+    span = 200_000_000 // 32 * 32                   # 0.8 GB of output per range
+    mid = (total // 2) // 32 * 32
+    ws = None
+    for begin, end in [(0, n_small + span), (mid, mid + span), (total - span, total)]:
+        out = torch.empty(end - begin, dtype=torch.float32, device=DEV)
+        ws = ops.tensordot_device(A, B, 1, out, begin, end, torch.float32, af=af_d, bf=bf_d, ws=ws)
+        for ci, cls in enumerate(table.classes):
+            lo, hi = max(begin, table.offsets[ci]), min(end, table.offsets[ci] + table.sizes[ci])
+            if lo >= hi:
+                continue
+            pos = np.unique(np.concatenate([np.arange(lo, min(hi, lo + 4)), np.arange(max(lo, hi - 4), hi), rng.integers(lo, hi, 24)]))
+            K = sorted_indices(cls, dim, pos - table.offsets[ci])
+            want, mag = _tensordot_components(af, bf, 3, 3, dim, K)
+            got = out[torch.as_tensor(pos - begin, device=DEV)].cpu().numpy().astype(np.float64)
+            assert np.all(np.abs(got - want) <= 1e-5 * mag), (begin, cls, np.max(np.abs(got - want) / mag))
+        # alignment padding of the packed layout stays zero
+        for ci in range(table.ncls):
+            lo, hi = max(begin, table.offsets[ci] + table.sizes[ci]), min(end, table.offsets[ci + 1])
+            if lo < hi:
+                assert float(out[lo - begin:hi - begin].abs().max()) == 0.0
+        del out

@@ -301,3 +301,40 @@ def test_tensordot_fp32_tensor_core_gram_matches_cuda_core_gram_and_oracle():
             check(lib.st_set_tuning(b"outer_fast", c_i64(1)))
         C1 = st.tensordot(TA, TB, axes=k)
         assert_classes_close(C1, ref, scale, RTOL32)
+
+
+@pytest.mark.parametrize("kch", [16, 32])
+@pytest.mark.parametrize("ra,rb,k,dim", [(3, 3, 1, 11), (3, 3, 1, 24), (3, 3, 1, 40), (4, 4, 2, 9), (3, 3, 1, 70)])
+def test_tensordot_tiled_tcgen05_kernel_against_packed_oracle(ra, rb, k, dim, kch):
+    """fp32 tensordot with two free indices on each side (BASELINE config 3's shape family) through the NON-MATERIALISING
+    kernel (st_sym22.cu: TMA-staged operand boxes, three 128 x 256 tcgen05 GEMMs per 8 x 16 x 16 x 16 output tile, chains of
+    256 added in registers, red.global.add into the packed output): the whole output against the fp64 packed oracle on the
+    up-cast inputs (1e-5 of the component's sum of |terms|), both stage geometries, and [begin, end) output ranges -- the
+    multi-GPU partition -- concatenating bit for bit to the whole."""
+    from symtensor_b200._cabi import c_i64, check, lib
+    rng = np.random.default_rng(ra * 1000 + rb * 100 + k * 10 + dim)
+    dist = "pos" if dim % 2 else "normal"
+    A, B = rand_packed(ra, dim, rng, dist), rand_packed(rb, dim, rng, dist)
+    TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=A, device=DEV).astype(np.float32)
+    TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=B, device=DEV).astype(np.float32)
+    A32 = {q: v.astype(np.float32).astype(np.float64) for q, v in A.items()}
+    B32 = {q: v.astype(np.float32).astype(np.float64) for q, v in B.items()}
+    ref, n = po.tensordot(A32, ra, B32, rb, dim, k)
+    scale, _ = po.tensordot(absd(A32), ra, absd(B32), rb, dim, k)
+    try:
+        check(lib.st_set_tuning(b"sym22_min_dim", c_i64(1)))
+        check(lib.st_set_tuning(b"sym22_kch", c_i64(kch)))
+        assert lib.st_tensordot_is_tiled(ra, rb, k, c_i64(dim), 4) == 1 and lib.st_tensordot_is_tiled(ra, rb, k, c_i64(dim), 8) == 0
+        C = st.tensordot(TA, TB, axes=k)
+        assert n == 4 and C.rank == 4 and C.dtype == np.float32
+        assert_classes_close(C, ref, scale, RTOL32)
+        whole = C.packed
+        total = whole.numel()
+        cuts = sorted({0, total} | {min(total, int(total * f) // 32 * 32) for f in (0.013, 0.21, 0.5, 0.77)})
+        for b, e in zip(cuts[:-1], cuts[1:]):
+            part = torch.full((e - b,), float("nan"), dtype=torch.float32, device=DEV)
+            ops.tensordot_device(TA, TB, k, part, b, e, torch.float32)
+            assert torch.equal(part, whole[b:e]), (b, e)
+    finally:
+        check(lib.st_set_tuning(b"sym22_min_dim", c_i64(96)))
+        check(lib.st_set_tuning(b"sym22_kch", c_i64(16)))
