@@ -245,6 +245,9 @@ int st_set_tuning(const char* key, int64_t value);
  * boundaries ([cta][16] stamps, then one finish stamp per warp of the grid); this copies the first n stamps of
  * the last launch to the host.  Profiling aid (tools/vec_timeline.py), not part of the reference-facing surface. */
 int st_debug_vec_timeline(unsigned long long* h_out, int64_t n);
+/* debug (host only): the tile words p | q << 16 | r << 32 | s << 48 (index blocks 8 / 16 / 16 / 16) the tiled tensordot kernel
+ * runs for the output range [begin, end) of a rank-4 result; returns their number (writes at most `cap`). */
+int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end, unsigned long long* h_out, int64_t cap);
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 int64_t st_launch_count(void);
 

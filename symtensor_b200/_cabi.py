@@ -70,6 +70,7 @@ SIGNATURES = {
     "st_set_vec_variant": (c_int, [c_int]),
     "st_set_tuning": (c_int, [ctypes.c_char_p, c_i64]),
     "st_debug_vec_timeline": (c_int, [c_vp, c_i64]),
+    "st_debug_sym22_tiles": (c_i64, [c_i64, c_i64, c_i64, c_vp, c_i64]),
     "st_launch_count": (c_i64, []),
 }
 

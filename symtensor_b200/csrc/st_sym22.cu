@@ -340,6 +340,10 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
             slow_add(P, base1111, prm.begin, prm.end, prm.out, gi, gj, gk, gl, acc[c] * sixth);
           }
         }
+        // a component gets its three adds from three different threads of this CTA: keep them in pairing order (fp32 adds do
+        // not commute bit for bit) -- nobody starts the next pairing's adds before everybody's adds of this one are performed
+        __threadfence();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
       }
     }
   }
@@ -461,20 +465,15 @@ static int64_t rank1111(const HostPlan* hp, int64_t base, int64_t a, int64_t b, 
 }
 
 // tiles (p, q, r, s) that can hold components of [begin, end); s runs fastest so that the CTAs working side by side
-// share the (i, j), (i, k) and (j, k) operand boxes in L2
-static int get_tiles(const HostPlan* hp, int64_t begin, int64_t end, TileList* out) {
-  int dev = 0;
-  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
-  if (rc) return rc;
-  std::lock_guard<std::mutex> lk(g_tmu);
-  const TileKey key{dev, hp->dim, begin, end};
-  auto it = g_tiles.find(key);
-  if (it != g_tiles.end()) { *out = it->second; return ST_OK; }
+// share the (i, j), (i, k) and (j, k) operand boxes in L2.  Pure host arithmetic (tests/test_cabi.py checks it against a
+// brute-force enumeration through st_debug_sym22_tiles).
+void build_tiles(const HostPlan* hp, int64_t begin, int64_t end, std::vector<unsigned long long>& tiles) {
   const int64_t d = hp->dim;
   const int64_t off4 = hp->h_cls[hp->ncls - 1].offset;
   const int64_t base = off4 + hp->h_binom[d * 5 + 4] - 1;
   const int64_t nbi = (d + BI - 1) / BI, nbj = (d + BJ - 1) / BJ;
-  std::vector<unsigned long long> tiles;
+  tiles.clear();
+  if (end <= begin) return;
   for (int64_t p = 0; p < nbi; ++p) {
     const int64_t i0 = p * BI;
     for (int64_t q = i0 / BJ; q < nbj; ++q) {
@@ -486,11 +485,11 @@ static int get_tiles(const HostPlan* hp, int64_t begin, int64_t end, TileList* o
           const bool diag = i0 + BI - 1 >= j0 || q == r || r == s;
           bool take = diag && begin < off4;  // components with repeated indices live in the classes before (1,1,1,1)
           if (!take) {
-            // smallest / largest strictly increasing tuple of the tile
+            // smallest / largest strictly increasing tuple of the tile (componentwise bounds; lexicographic rank is monotone)
             const int64_t a0 = i0, b0 = std::max(j0, a0 + 1), c0 = std::max(k0, b0 + 1), e0 = std::max(l0, c0 + 1);
             const int64_t e1 = std::min(l0 + BJ - 1, d - 1), c1 = std::min(k0 + BJ - 1, e1 - 1), b1 = std::min(j0 + BJ - 1, c1 - 1),
                           a1 = std::min(i0 + BI - 1, b1 - 1);
-            if (a0 <= i0 + BI - 1 && b0 <= j0 + BJ - 1 && c0 <= k0 + BJ - 1 && e0 <= e1 && a1 >= a0 && b1 >= b0 && c1 >= c0 && b1 > a0) {
+            if (b0 <= j0 + BJ - 1 && c0 <= k0 + BJ - 1 && e0 <= e1 && a1 >= a0 && b1 >= b0 && c1 >= c0) {
               const int64_t lo = rank1111(hp, base, a0, b0, c0, e0), hi = rank1111(hp, base, a1, b1, c1, e1);
               take = lo < end && hi >= begin;
             }
@@ -500,6 +499,18 @@ static int get_tiles(const HostPlan* hp, int64_t begin, int64_t end, TileList* o
       }
     }
   }
+}
+
+static int get_tiles(const HostPlan* hp, int64_t begin, int64_t end, TileList* out) {
+  int dev = 0;
+  int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
+  if (rc) return rc;
+  std::lock_guard<std::mutex> lk(g_tmu);
+  const TileKey key{dev, hp->dim, begin, end};
+  auto it = g_tiles.find(key);
+  if (it != g_tiles.end()) { *out = it->second; return ST_OK; }
+  std::vector<unsigned long long> tiles;
+  build_tiles(hp, begin, end, tiles);
   TileList tl{nullptr, (int64_t)tiles.size()};
   if (tl.n) {
     rc = check_cuda(cudaMalloc(&tl.d, tiles.size() * sizeof(unsigned long long)), "cudaMalloc(tiles)");
@@ -584,3 +595,12 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
 
 }  // namespace s22
 }  // namespace st
+
+extern "C" int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end, unsigned long long* h_out, int64_t cap) {
+  const st::HostPlan* hp = st::get_host_plan(4, dim);
+  if (!hp) return -1;
+  std::vector<unsigned long long> tiles;
+  st::s22::build_tiles(hp, begin, end, tiles);
+  for (int64_t i = 0; i < (int64_t)tiles.size() && i < cap; ++i) h_out[i] = tiles[i];
+  return (int64_t)tiles.size();
+}

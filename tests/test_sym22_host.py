@@ -1,0 +1,45 @@
+"""Host logic of the tiled tensordot kernel (st_sym22.cu): the tile list of an output range [begin, end) -- the multi-GPU
+partition of BASELINE config 3 -- against a brute-force enumeration with the ORACLE's (class, position) map: every tile that
+holds a component of the range must be in the list (a missing tile is a missing part of the result)."""
+import itertools
+
+import numpy as np
+
+from oracle import index_oracle as io
+
+from symtensor_b200 import combinatorics as comb
+from symtensor_b200 import sharding
+from symtensor_b200._cabi import c_i64, lib
+
+
+def tiles_needed(dim, begin, end):
+    tab = comb.class_table(4, dim)
+    need = set()
+    for t in itertools.combinations_with_replacement(range(dim), 4):
+        cls, pos = io.rank_of_index(t, dim)
+        if begin <= tab.offsets[tab.index(cls)] + pos < end:
+            need.add((t[0] // 8, t[1] // 16, t[2] // 16, t[3] // 16))
+    return need
+
+
+def tiles_listed(dim, begin, end):
+    buf = np.zeros(1 << 16, dtype=np.uint64)
+    n = lib.st_debug_sym22_tiles(c_i64(dim), c_i64(begin), c_i64(end), buf.ctypes.data, c_i64(buf.size))
+    assert 0 <= n <= buf.size
+    words = [int(w) for w in buf[:n]]
+    assert len(set(words)) == n  # no tile twice: a component gets its three adds from ONE tile
+    return {(w & 0xffff, (w >> 16) & 0xffff, (w >> 32) & 0xffff, (w >> 48) & 0xffff) for w in words}
+
+
+def test_tile_lists_cover_every_output_range():
+    for dim in (7, 17, 33, 40):
+        total = comb.class_table(4, dim).total
+        for world in (1, 2, 3, 8):
+            cuts = sharding.shard_bounds(total, world)
+            union = set()
+            for b, e in zip(cuts[:-1], cuts[1:]):
+                need, got = tiles_needed(dim, b, e), tiles_listed(dim, b, e)
+                assert need <= got, (dim, b, e, sorted(need - got)[:5])
+                union |= got
+            assert union == tiles_listed(dim, 0, total) == tiles_needed(dim, 0, total)
+    assert tiles_listed(40, 64, 64) == set()
