@@ -210,7 +210,7 @@ int st_outer_vec_f32(int ra, int rb, int64_t dim, const float* d_a_flat, const f
  * ------------------------------------------------------------------------------------------------ */
 int st_tensordot_workspace_bytes(int ra, int rb, int k, int64_t dim, int elem_size, int64_t* out_bytes);
 /* 1 when st_tensordot_* serves (ra, rb, k, dim, elem_size) with the tiled NON-MATERIALISING kernel (fp32, two free indices on
- * each side: BASELINE config 3): the six Gram terms of an 8 x 16 x 16 x 16 output tile are three 128 x 256 tcgen05 GEMMs over
+ * each side: BASELINE config 3): the six Gram terms of a 16 x 16 x 16 x 8 output tile are three 128 x 256 tcgen05 GEMMs over
  * TMA-staged operand boxes, added straight into the packed output (which is zeroed first); the workspace then holds the
  * expanded, hi/lo-split pair matrices (16 dim^2 Kp bytes) and its first int is an error flag the kernel raises if a
  * bounded barrier wait expired (read it after synchronising the stream). */
@@ -245,7 +245,7 @@ int st_set_tuning(const char* key, int64_t value);
  * boundaries ([cta][16] stamps, then one finish stamp per warp of the grid); this copies the first n stamps of
  * the last launch to the host.  Profiling aid (tools/vec_timeline.py), not part of the reference-facing surface. */
 int st_debug_vec_timeline(unsigned long long* h_out, int64_t n);
-/* debug (host only): the tile words p | q << 16 | r << 32 | s << 48 (index blocks 8 / 16 / 16 / 16) the tiled tensordot kernel
+/* debug (host only): the tile words p | q << 16 | r << 32 | s << 48 (index blocks 16 / 16 / 16 / 8) the tiled tensordot kernel
  * runs for the output range [begin, end) of a rank-4 result; returns their number (writes at most `cap`). */
 int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end, unsigned long long* h_out, int64_t cap);
 /* number of kernel launches issued by this library since load (bench.py reports it) */

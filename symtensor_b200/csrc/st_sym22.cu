@@ -5,15 +5,18 @@
 //     G[ab|cd] = sum_J w_J A[a, b, J] B[J, c, d]          (J: the packed contracted tuples, w_J their multiplicity)
 //
 // The Gram matrix G (pair rows x pair columns, 1 TB at config 3) is never stored.  The output is cut into TILES of index
-// blocks  I x J x K x L = 8 x 16 x 16 x 16  (I: block of the smallest index).  For one tile the six terms are THREE
+// blocks  I x J x K x L = 16 x 16 x 16 x 8  (L: block of the LARGEST index).  For one tile the six terms are THREE
 // GEMMs of shape [128 x 256 x 2 Kc] -- the two orientations of a pairing share an accumulator through the concatenated
-// contraction  G[ab|cd] + G[cd|ab] = sum_J [wA | B][ab, J] . [B | wA][cd, J]  -- with rows (i, .) = 8 x 16 = 128 and
+// contraction  G[ab|cd] + G[cd|ab] = sum_J [wA | B][ab, J] . [B | wA][cd, J]  -- with rows (., l) = 16 x 8 = 128 and
 // columns 16 x 16 = 256 for every pairing, which is the full-rate tcgen05 shape (M = 128, N = 256, cta_group::1):
-//     pairing 0: rows (i, j), columns (k, l);   pairing 1: rows (i, k), columns (j, l);   pairing 2: rows (i, l), columns (j, k).
-// Operands: the expanded pair matrices X[first][second][J] (dim x dim rows of Kp floats, both triangles) of wA and B, each
+//     pairing 0: rows (k, l), columns (i, j);   pairing 1: rows (j, l), columns (i, k);   pairing 2: rows (i, l), columns (j, k).
+// l sits in the ROW index of every pairing because an epilogue thread owns a row (a TMEM lane): the 32 lanes of a warp
+// then hold 4 x 8 consecutive values of l, i.e. 4 whole 32-byte sectors of the packed output per global add (with l in the
+// columns every lane hit its own sector and the adds alone took longer than the GEMMs).
+// Operands: the expanded pair matrices X[K chunk][first][second][16 or 32 floats] (dim x dim rows, both triangles) of wA and B, each
 // pre-split into the tf32 part the tensor core reads and the exact remainder (3xTF32: hi.hi + hi.lo + lo.hi), written
-// once by expand_pairs_kernel; a tile's operand boxes (8 x 16 or 16 x 16 pair rows x 16 or 32 floats) are fetched by TMA
-// (cp.async.bulk.tensor.3d, SASS UTMALDG; hardware swizzle, out-of-range rows zero-filled) into a ring of shared-memory
+// once by expand_pairs_kernel; a tile's operand boxes (16 x 8 or 16 x 16 pair rows x 16 or 32 floats) are fetched by TMA
+// (cp.async.bulk.tensor.4d, SASS UTMALDG; hardware swizzle, out-of-range rows zero-filled) into a ring of shared-memory
 // stages guarded by full / empty mbarriers.
 //
 // Warp roles (384 threads): warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; allocates the 512 TMEM
@@ -32,6 +35,7 @@
 #include <algorithm>
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "st_common.cuh"
@@ -39,9 +43,9 @@
 namespace st {
 namespace s22 {
 
-constexpr int BI = 8, BJ = 16;
-constexpr int TM = BI * BJ;   // 128 rows
-constexpr int TN = BJ * BJ;   // 256 columns
+constexpr int BJ = 16, BL = 8;  // index blocks: i, j, k in blocks of 16, l (the LARGEST index) in blocks of 8
+constexpr int TM = BJ * BL;   // 128 rows: (one of i, j, k) x l
+constexpr int TN = BJ * BJ;   // 256 columns: the other two
 constexpr int NTHREADS = 384;
 constexpr int CHAIN_K = 256;  // products per TMEM accumulation chain
 constexpr int SMEM_STAGE_BUDGET = 192 * 1024;
@@ -57,19 +61,14 @@ struct Geo {
   static constexpr uint64_t LAYOUT = KCH == 32 ? 2ull : 4ull;   // SWIZZLE_128B : SWIZZLE_64B
 };
 
-struct Tables {
-  long long colterm[3][TN];
-  long long rowterm[3][TM];
-};
-
 struct Params {
   PlanView P;          // plan of the rank-4 output
   int64_t begin, end;  // packed output coordinates served by this launch
   float* out;          // points at coordinate `begin`
-  const unsigned long long* tiles;  // p | q << 16 | r << 32 | s << 48
+  const unsigned long long* tiles;  // block numbers p | q << 16 | r << 32 | s << 48 of i, j, k (16 wide) and l (8 wide)
   int64_t ntiles;
   int32_t nst;         // stages per K segment (Kp / KCH)
-  int32_t pad_;
+  int32_t debug;       // ablation switches (tuning key "sym22_debug"): 1 no global adds, 2 no TMEM drains, 4 no TMA loads, 8 no MMAs
   int* err;            // set to 1 when a bounded barrier wait expired
 };
 
@@ -98,10 +97,29 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatil
   *abort_flag = 1;
   return false;
 }
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
-               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+// one operand box: K chunk `c3` of the pair rows (first0 .., second0 ..) -- a 4-D tile of X[chunk][first][second][KCH]
+__device__ __forceinline__ void tma_load_box(uint32_t dst, const CUtensorMap* map, int second0, int first0, int chunk, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(second0), "r"(first0), "r"(chunk), "r"(bar), "l"(policy)
                : "memory");
+}
+// L2 policies: the operand stream must not push the output tiles out of L2 between the three pairings of a tile (a tile's
+// 128 KB of outputs are written by pairing 0 and added to by pairings 1 and 2, ~100 us apart, while ~1 GB of operands
+// streams through the 126 MB L2): operands evict-first (or evict-normal), outputs evict-last
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 template <int KCH>
 __device__ __forceinline__ uint64_t make_desc(uint32_t a) {  // K-major, hardware swizzle, 8-row groups SBO apart
@@ -123,6 +141,11 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_c, uint64_t da, uint64_t 
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+
+// binomials C(n, 2..4) for n >= 0 by exact 64-bit arithmetic (every division is exact)
+__device__ __forceinline__ int64_t c2(int64_t n) { return n * (n - 1) / 2; }
+__device__ __forceinline__ int64_t c3(int64_t n) { return c2(n) * (n - 2) / 3; }
+__device__ __forceinline__ int64_t c4(int64_t n) { return c3(n) * (n - 3) / 4; }
 
 // packed permcls coordinate of the component (a <= b <= c <= e) of the rank-4 output, or -1
 __device__ __forceinline__ int64_t element_coord(const PlanView& P, int64_t base1111, int a, int b, int c, int e) {
@@ -153,8 +176,7 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
   using G = Geo<KCH>;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* stages = smem;
-  Tables* tab = reinterpret_cast<Tables*>(smem + (size_t)G::STAGES * G::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(tab) + sizeof(Tables));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)G::STAGES * G::STAGE_BYTES);
   // bars: full[STAGES], empty[STAGES], tfull[2], tempty[2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G::STAGES + 4);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
@@ -184,25 +206,27 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
       int stage = 0;
       uint32_t ph = 0;
       bool ok = true;
+      const uint64_t pol = (prm.debug & 16) ? policy_evict_normal() : policy_evict_first();
       for (int64_t t = blockIdx.x; t < prm.ntiles && ok; t += gridDim.x) {
         const unsigned long long tw = prm.tiles[t];
-        const int i0 = (int)(tw & 0xffff) * BI, j0 = (int)((tw >> 16) & 0xffff) * BJ, k0 = (int)((tw >> 32) & 0xffff) * BJ,
-                  l0 = (int)((tw >> 48) & 0xffff) * BJ;
+        const int i0 = (int)(tw & 0xffff) * BJ, j0 = (int)((tw >> 16) & 0xffff) * BJ, k0 = (int)((tw >> 32) & 0xffff) * BJ,
+                  l0 = (int)((tw >> 48) & 0xffff) * BL;
         for (int pr = 0; pr < 3 && ok; ++pr) {
-          const int rsec = pr == 0 ? j0 : (pr == 1 ? k0 : l0);   // second index of the row pairs (first: i)
-          const int cfir = pr == 0 ? k0 : j0;                    // first index of the column pairs
-          const int csec = pr == 2 ? k0 : l0;                    // second index of the column pairs
+          const int rfir = pr == 0 ? k0 : (pr == 1 ? j0 : i0);   // first index of the row pairs (second: l)
+          const int cfir = pr == 2 ? j0 : i0;                    // first index of the column pairs
+          const int csec = pr == 0 ? j0 : k0;                    // second index of the column pairs
           for (int st = 0; st < nst_total; ++st) {
             if (!mbar_wait(bar_empty + 8 * stage, ph ^ 1, abort_flag)) { ok = false; break; }
             const uint32_t full = bar_full + 8 * stage;
+            if (prm.debug & 4) { mbar_arrive(full); if (++stage == G::STAGES) { stage = 0; ph ^= 1; } continue; }
             mbar_expect_tx(full, G::STAGE_BYTES);
             const bool seg1 = st >= nst;
-            const int kc = (seg1 ? st - nst : st) * KCH;
+            const int kc = seg1 ? st - nst : st;  // K chunk
             const uint32_t base = saddr(stages + (size_t)stage * G::STAGE_BYTES);
-            tma_load_3d(base, seg1 ? &mBhr : &mAhr, kc, rsec, i0, full);
-            tma_load_3d(base + G::ROW_BYTES, seg1 ? &mBlr : &mAlr, kc, rsec, i0, full);
-            tma_load_3d(base + 2 * G::ROW_BYTES, seg1 ? &mAhc : &mBhc, kc, csec, cfir, full);
-            tma_load_3d(base + 2 * G::ROW_BYTES + G::COL_BYTES, seg1 ? &mAlc : &mBlc, kc, csec, cfir, full);
+            tma_load_box(base, seg1 ? &mBhr : &mAhr, l0, rfir, kc, full, pol);
+            tma_load_box(base + G::ROW_BYTES, seg1 ? &mBlr : &mAlr, l0, rfir, kc, full, pol);
+            tma_load_box(base + 2 * G::ROW_BYTES, seg1 ? &mAhc : &mBhc, csec, cfir, kc, full, pol);
+            tma_load_box(base + 2 * G::ROW_BYTES + G::COL_BYTES, seg1 ? &mAlc : &mBlc, csec, cfir, kc, full, pol);
             if (++stage == G::STAGES) { stage = 0; ph ^= 1; }
           }
         }
@@ -229,7 +253,7 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const uint32_t base = saddr(stages + (size_t)stage * G::STAGE_BYTES);
 #pragma unroll
-              for (int kk = 0; kk < KCH / 8; ++kk) {  // one MMA = 8 tf32 along K = 32 bytes inside the swizzled row
+              for (int kk = 0; kk < ((prm.debug & 8) ? 0 : KCH / 8); ++kk) {  // one MMA = 8 tf32 along K = 32 bytes inside the swizzled row
                 const uint32_t ko = kk * 32;
                 const uint64_t dAh = make_desc<KCH>(base + ko), dAl = make_desc<KCH>(base + G::ROW_BYTES + ko);
                 const uint64_t dBh = make_desc<KCH>(base + 2 * G::ROW_BYTES + ko), dBl = make_desc<KCH>(base + 2 * G::ROW_BYTES + G::COL_BYTES + ko);
@@ -259,47 +283,27 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
     int buf = 0;
     uint32_t fph[2] = {0, 0};
     bool ok = true;
+    const uint64_t opol = (prm.debug & 16) ? policy_evict_normal() : policy_evict_last();
+    long long t_wait = 0, t_drain = 0, t_write = 0, t_fence = 0, t_bar = 0;  // debug 64: where an epilogue warp spends its time
     float acc[TN / 2];
     for (int64_t t = blockIdx.x; t < prm.ntiles && ok; t += gridDim.x) {
       const unsigned long long tw = prm.tiles[t];
-      const int i0 = (int)(tw & 0xffff) * BI, j0 = (int)((tw >> 16) & 0xffff) * BJ, k0 = (int)((tw >> 32) & 0xffff) * BJ,
-                l0 = (int)((tw >> 48) & 0xffff) * BJ;
-      // all indices distinct, inside the tensor and inside the launch range: positions are sums of table terms
-      bool fast = i0 + BI - 1 < j0 && j0 + BJ - 1 < k0 && k0 + BJ - 1 < l0 && l0 + BJ - 1 < P.dim;
-      if (fast) {
-        const int64_t cmin = element_coord(P, base1111, i0, j0, k0, l0);
-        const int64_t cmax = element_coord(P, base1111, i0 + BI - 1, j0 + BJ - 1, k0 + BJ - 1, l0 + BJ - 1);
-        fast = cmin >= prm.begin && cmax < prm.end;
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // everybody is done with the previous tile's tables
-      if (fast) {
-        // term of an index at output position q (0-based): C(d - 1 - g, 4 - q)
-        {
-          const int y = et >> 4, z = et & 15;  // column n = et: (first, second)
-          const long long tj = binom_at(P.binom, 4, P.dim - 1 - (j0 + y), 3), tk_f = binom_at(P.binom, 4, P.dim - 1 - (k0 + y), 2);
-          const long long tl = binom_at(P.binom, 4, P.dim - 1 - (l0 + z), 1), tk_s = binom_at(P.binom, 4, P.dim - 1 - (k0 + z), 2);
-          tab->colterm[0][et] = tk_f + tl;   // columns (k, l)
-          tab->colterm[1][et] = tj + tl;     // columns (j, l)
-          tab->colterm[2][et] = tj + tk_s;   // columns (j, k)
-        }
-        if (et < TM) {
-          const int i = et >> 4, x = et & 15;  // row m = et: (i, second)
-          const long long ti = binom_at(P.binom, 4, P.dim - 1 - (i0 + i), 4);
-          tab->rowterm[0][et] = ti + binom_at(P.binom, 4, P.dim - 1 - (j0 + x), 3);  // rows (i, j)
-          tab->rowterm[1][et] = ti + binom_at(P.binom, 4, P.dim - 1 - (k0 + x), 2);  // rows (i, k)
-          tab->rowterm[2][et] = ti + binom_at(P.binom, 4, P.dim - 1 - (l0 + x), 1);  // rows (i, l)
-        }
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const int i0 = (int)(tw & 0xffff) * BJ, j0 = (int)((tw >> 16) & 0xffff) * BJ, k0 = (int)((tw >> 32) & 0xffff) * BJ,
+                l0 = (int)((tw >> 48) & 0xffff) * BL;
+      // all indices distinct and inside the tensor: positions are sums of four per-index terms (`fast`)
+      const bool fast = i0 + BJ - 1 < j0 && j0 + BJ - 1 < k0 && k0 + BJ - 1 < l0 && l0 + BL - 1 < P.dim;
       for (int pr = 0; pr < 3 && ok; ++pr) {
 #pragma unroll
         for (int c = 0; c < TN / 2; ++c) acc[c] = 0.f;
         for (int c0 = 0; c0 < nst_total && ok; c0 += G::CHAIN_STAGES) {
+          const long long c_a = clock64();
           if (!mbar_wait(bar_tfull + 8 * buf, fph[buf], abort_flag)) { ok = false; break; }
+          const long long c_b = clock64();
+          t_wait += c_b - c_a;
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t taddr0 = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * TN + half * (TN / 2));
 #pragma unroll
-          for (int piece = 0; piece < TN / 2; piece += 16) {
+          for (int piece = 0; piece < ((prm.debug & 2) ? 0 : TN / 2); piece += 16) {
             uint32_t v[16];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -313,38 +317,75 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          t_drain += clock64() - c_b;
           fph[buf] ^= 1;
           buf ^= 1;
         }
         if (!ok) break;
         // ---- this pairing's share of the outputs: 1/6 of (G[rows|cols] + G[cols|rows])
         const float sixth = 1.0f / 6.0f;
-        if (fast) {
-          const int64_t row_off = base1111 - prm.begin - tab->rowterm[pr][m];
-          const long long* ct = tab->colterm[pr] + half * (TN / 2);
+        const long long c_w = clock64();
+        if (prm.debug & 1) {
+        } else if (fast) {
+          // positions without tables or shared memory (the tensor core and the TMA unit saturate the shared-memory pipe:
+          // an LDS of the epilogue waited ~1000 clocks there): coord = base - T4(i) - T3(j) - T2(k) - T1(l), T_r(g) = C(d-1-g, r);
+          // the row term and the term of the column's first index are computed directly, the second index steps through
+          // 16 consecutive values by finite differences.  Adds outside the launch range [begin, end) are predicated off.
+          const int x = m >> 3, z = m & 7;
+          const int64_t dm1 = P.dim - 1;
+          const int64_t rterm = (dm1 - (l0 + z)) + (pr == 0 ? c2(dm1 - (k0 + x)) : pr == 1 ? c3(dm1 - (j0 + x)) : c4(dm1 - (i0 + x)));
+          const int64_t row_off = base1111 - prm.begin - rterm;
+          const uint64_t span = (uint64_t)(prm.end - prm.begin);
+          const int64_t ns0 = dm1 - (pr == 0 ? j0 : k0);  // n = d - 1 - g of the column's second index at w = 0
 #pragma unroll
-          for (int c = 0; c < TN / 2; ++c) {
-            float* p = prm.out + (row_off - ct[c]);
-            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(acc[c] * sixth) : "memory");
+          for (int yy = 0; yy < TN / 32; ++yy) {
+            const int y = half * (TN / 32) + yy;
+            const int64_t tf = pr == 2 ? c3(dm1 - (j0 + y)) : c4(dm1 - (i0 + y));
+            int64_t off, d1, d2 = ns0 - 2;
+            if (pr == 0) { off = row_off - tf - c3(ns0); d1 = c2(ns0 - 1); }
+            else { off = row_off - tf - c2(ns0); d1 = ns0 - 1; }
+#pragma unroll
+            for (int w = 0; w < 16; ++w) {
+              if ((uint64_t)off < span)
+                asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(prm.out + off), "f"(acc[yy * 16 + w] * sixth), "l"(opol) : "memory");
+              off += d1;  // T(w + 1) = T(w) - C(n_w - 1, r - 1)
+              if (pr == 0) { d1 -= d2; d2 -= 1; }
+              else d1 -= 1;
+            }
           }
         } else {
-          const int i = m >> 4, x = m & 15;
+          const int x = m >> 3, z = m & 7;
 #pragma unroll
           for (int c = 0; c < TN / 2; ++c) {
             const int n = half * (TN / 2) + c;
-            const int y = n >> 4, z = n & 15;
-            int gi = i0 + i, gj, gk, gl;
-            if (pr == 0) { gj = j0 + x; gk = k0 + y; gl = l0 + z; }
-            else if (pr == 1) { gk = k0 + x; gj = j0 + y; gl = l0 + z; }
-            else { gl = l0 + x; gj = j0 + y; gk = k0 + z; }
+            const int y = n >> 4, w = n & 15;
+            const int gl = l0 + z;
+            int gi, gj, gk;
+            if (pr == 0) { gk = k0 + x; gi = i0 + y; gj = j0 + w; }
+            else if (pr == 1) { gj = j0 + x; gi = i0 + y; gk = k0 + w; }
+            else { gi = i0 + x; gj = j0 + y; gk = k0 + w; }
             slow_add(P, base1111, prm.begin, prm.end, prm.out, gi, gj, gk, gl, acc[c] * sixth);
           }
         }
         // a component gets its three adds from three different threads of this CTA: keep them in pairing order (fp32 adds do
         // not commute bit for bit) -- nobody starts the next pairing's adds before everybody's adds of this one are performed
+        const long long c_f = clock64();
         __threadfence();
+        const long long c_g = clock64();
         asm volatile("bar.sync 2, 256;" ::: "memory");
+        t_write += c_f - c_w;
+        t_fence += c_g - c_f;
+        t_bar += clock64() - c_g;
       }
+    }
+    if ((prm.debug & 64) && lane == 0 && prm.err) {
+      unsigned long long* dbg = reinterpret_cast<unsigned long long*>(prm.err) + 8;
+      atomicAdd(dbg + 0, (unsigned long long)t_wait);
+      atomicAdd(dbg + 1, (unsigned long long)t_drain);
+      atomicAdd(dbg + 2, (unsigned long long)t_write);
+      atomicAdd(dbg + 3, (unsigned long long)t_fence);
+      atomicAdd(dbg + 4, (unsigned long long)t_bar);
+      atomicAdd(dbg + 5, 1ULL);
     }
   }
   // ---- teardown
@@ -357,21 +398,26 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
   }
 }
 
-// X[first][second][J] for all (first, second) in dim x dim and J < Kp (zero beyond K): the tf32 part the tensor core reads
-// (the fp32 value with the low 13 mantissa bits cleared) and the exact remainder.  `weighted`: times the multiplicity of J.
+// X[chunk][first][second][kch]: for all (first, second) in dim x dim the values X[first, second, J], J = chunk * kch + e < Kp
+// (zero beyond K), stored K-chunk-major so that an operand box of the kernel -- 8 or 16 values of `first` times 16 consecutive
+// values of `second`, one chunk -- is a few contiguous runs of 16 * kch * 4 bytes (with J innermost every 64-byte piece sat in
+// its own 4 KB row: the kernel then ran at the speed of scattered HBM reads).  hi = the tf32 part the tensor core reads (the
+// fp32 value with the low 13 mantissa bits cleared), lo = the exact remainder.  `weighted`: times the multiplicity of J.
 __global__ void __launch_bounds__(256) expand_pairs_kernel(PlanView P, int k, const float* __restrict__ flat, float* __restrict__ hi,
-                                                           float* __restrict__ lo, int64_t K, int64_t Kp, int weighted) {
+                                                           float* __restrict__ lo, int64_t K, int64_t Kp, int kch, int weighted) {
   const int64_t d = P.dim;
   const int64_t total = d * d * Kp;
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = e / Kp, jj = e - row * Kp;
+    const int64_t within = e % kch, rowc = e / kch;    // rowc = (chunk * d + first) * d + second
+    const int64_t b = rowc % d, ca = rowc / d;
+    const int64_t a = ca % d, chunk = ca / d;
+    const int64_t jj = chunk * kch + within;
     float v = 0.f;
     if (jj < K) {
-      const int a = (int)(row / d), b = (int)(row - (int64_t)a * d);
       int32_t J[ST_MAX_RANK], m[ST_MAX_RANK + 2];
       flat_unrank_r(P, jj, k, J);
       int o = 0, q = 0;
-      const int f0 = a < b ? a : b, f1 = a < b ? b : a;
+      const int f0 = (int)(a < b ? a : b), f1 = (int)(a < b ? b : a);
       // merge (f0, f1) with the sorted tuple J
       int placed = 0;
       while (placed < 2 || q < k) {
@@ -415,17 +461,19 @@ static EncodeTiledFn get_encode() {
 static int make_map(CUtensorMap* map, float* base, int64_t d, int64_t Kp, int kch, int box_second, int box_first) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return ST_ERR_UNSUPPORTED; }
-  const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)d, (cuuint64_t)d};
-  const cuuint64_t strides[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)d * Kp * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)kch, (cuuint32_t)box_second, (cuuint32_t)box_first};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  // X[chunk][first][second][kch]
+  const cuuint64_t dims[4] = {(cuuint64_t)kch, (cuuint64_t)d, (cuuint64_t)d, (cuuint64_t)(Kp / kch)};
+  const cuuint64_t strides[3] = {(cuuint64_t)kch * 4, (cuuint64_t)d * kch * 4, (cuuint64_t)d * d * kch * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)kch, (cuuint32_t)box_second, (cuuint32_t)box_first, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          kch == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return ST_ERR_CUDA; }
   return ST_OK;
 }
 
+int g_debug = 0;
 int g_kch = 16;  // floats per stage row: 16 (SWIZZLE_64B, 4 stages) or 32 (SWIZZLE_128B, 2 stages); tuning key "sym22_kch"
 
 static int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
@@ -471,24 +519,24 @@ void build_tiles(const HostPlan* hp, int64_t begin, int64_t end, std::vector<uns
   const int64_t d = hp->dim;
   const int64_t off4 = hp->h_cls[hp->ncls - 1].offset;
   const int64_t base = off4 + hp->h_binom[d * 5 + 4] - 1;
-  const int64_t nbi = (d + BI - 1) / BI, nbj = (d + BJ - 1) / BJ;
+  const int64_t nbj = (d + BJ - 1) / BJ, nbl = (d + BL - 1) / BL;
   tiles.clear();
   if (end <= begin) return;
-  for (int64_t p = 0; p < nbi; ++p) {
-    const int64_t i0 = p * BI;
-    for (int64_t q = i0 / BJ; q < nbj; ++q) {
+  for (int64_t p = 0; p < nbj; ++p) {
+    const int64_t i0 = p * BJ;
+    for (int64_t q = p; q < nbj; ++q) {
       const int64_t j0 = q * BJ;
       for (int64_t r = q; r < nbj; ++r) {
         const int64_t k0 = r * BJ;
-        for (int64_t s = r; s < nbj; ++s) {
-          const int64_t l0 = s * BJ;
-          const bool diag = i0 + BI - 1 >= j0 || q == r || r == s;
+        for (int64_t s = k0 / BL; s < nbl; ++s) {
+          const int64_t l0 = s * BL;
+          const bool diag = p == q || q == r || l0 <= k0 + BJ - 1;
           bool take = diag && begin < off4;  // components with repeated indices live in the classes before (1,1,1,1)
           if (!take) {
             // smallest / largest strictly increasing tuple of the tile (componentwise bounds; lexicographic rank is monotone)
             const int64_t a0 = i0, b0 = std::max(j0, a0 + 1), c0 = std::max(k0, b0 + 1), e0 = std::max(l0, c0 + 1);
-            const int64_t e1 = std::min(l0 + BJ - 1, d - 1), c1 = std::min(k0 + BJ - 1, e1 - 1), b1 = std::min(j0 + BJ - 1, c1 - 1),
-                          a1 = std::min(i0 + BI - 1, b1 - 1);
+            const int64_t e1 = std::min(l0 + BL - 1, d - 1), c1 = std::min(k0 + BJ - 1, e1 - 1), b1 = std::min(j0 + BJ - 1, c1 - 1),
+                          a1 = std::min(i0 + BJ - 1, b1 - 1);
             if (b0 <= j0 + BJ - 1 && c0 <= k0 + BJ - 1 && e0 <= e1 && a1 >= a0 && b1 >= b0 && c1 >= c0) {
               const int64_t lo = rank1111(hp, base, a0, b0, c0, e0), hi = rank1111(hp, base, a1, b1, c1, e1);
               take = lo < end && hi >= begin;
@@ -499,6 +547,7 @@ void build_tiles(const HostPlan* hp, int64_t begin, int64_t end, std::vector<uns
       }
     }
   }
+  // (generation order: s runs fastest, so the CTAs working side by side share the three column boxes (i, j), (i, k), (j, k))
 }
 
 static int get_tiles(const HostPlan* hp, int64_t begin, int64_t end, TileList* out) {
@@ -530,7 +579,7 @@ static int get_tiles(const HostPlan* hp, int64_t begin, int64_t end, TileList* o
 template <int KCH>
 static int launch(const CUtensorMap* maps, const Params& prm, int grid, cudaStream_t stream) {
   using G = Geo<KCH>;
-  const size_t smem = (size_t)G::STAGES * G::STAGE_BYTES + sizeof(Tables) + (2 * G::STAGES + 4) * 8 + 64;
+  const size_t smem = (size_t)G::STAGES * G::STAGE_BYTES + (2 * G::STAGES + 4) * 8 + 64;
   int rc = set_max_dynamic_smem(reinterpret_cast<const void*>(sym22_umma_kernel<KCH>), (int)smem);
   if (rc) return rc;
   sym22_umma_kernel<KCH><<<grid, NTHREADS, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm);
@@ -541,7 +590,7 @@ static int launch(const CUtensorMap* maps, const Params& prm, int grid, cudaStre
 // d_ws: workspace_bytes(); layout: [0, 4096) control (error flag), then wA hi, wA lo, B hi, B lo (dim x dim x Kp floats each)
 int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin, int64_t end, void* d_ws,
                     cudaStream_t stream) {
-  if (dim >= 65536 * BI) { set_error("dim too large for the tile words"); return ST_ERR_UNSUPPORTED; }
+  if (dim >= 65536 * BL) { set_error("dim too large for the tile words"); return ST_ERR_UNSUPPORTED; }
   const int64_t K = contracted_count(k, dim);
   if (K <= 0) { set_error("nothing to contract"); return ST_ERR_INVALID; }
   const int kch = g_kch == 32 ? 32 : 16;
@@ -562,8 +611,8 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   rc = check_cuda(cudaMemsetAsync(d_out, 0, (size_t)(end - begin) * sizeof(float), stream), "cudaMemsetAsync(out)");
   if (rc) return rc;
   const int eg = (int)std::min<int64_t>((n1 + 255) / 256, 148 * 32);
-  expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_a_flat, ah, al, K, Kp, 1);
-  expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_b_flat, bh, bl, K, Kp, 0);
+  expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_a_flat, ah, al, K, Kp, kch, 1);
+  expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_b_flat, bh, bl, K, Kp, kch, 0);
   count_launch(2);
   rc = check_cuda(cudaGetLastError(), "expand_pairs_kernel");
   if (rc) return rc;
@@ -573,7 +622,7 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   if (tl.n == 0) return ST_OK;
   CUtensorMap maps[8];
   float* src[4] = {ah, al, bh, bl};
-  for (int a = 0; a < 4 && !rc; ++a) rc = make_map(&maps[a], src[a], dim, Kp, kch, BJ, BI);      // row boxes (i: 8, second: 16)
+  for (int a = 0; a < 4 && !rc; ++a) rc = make_map(&maps[a], src[a], dim, Kp, kch, BL, BJ);      // row boxes (first: 16, l: 8)
   for (int a = 0; a < 4 && !rc; ++a) rc = make_map(&maps[4 + a], src[a], dim, Kp, kch, BJ, BJ);  // column boxes (16 x 16)
   if (rc) return rc;
   Params prm;
@@ -584,7 +633,7 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   prm.tiles = tl.d;
   prm.ntiles = tl.n;
   prm.nst = (int32_t)(Kp / kch);
-  prm.pad_ = 0;
+  prm.debug = g_debug;
   prm.err = d_err;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

@@ -729,7 +729,7 @@ int g_ring_direct = 1;                 // ring kernel: allow the table-free pair
 int64_t g_ring_table_max = 72 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
 extern int g_mat_dmma, g_outer_fast, g_gram_umma, g_sym22;  // st_ops.cu
 extern int64_t g_sym22_min_dim;
-namespace s22 { extern int g_kch; }  // st_sym22.cu
+namespace s22 { extern int g_kch, g_debug; }  // st_sym22.cu
 int64_t g_short_segment = 1024;  // classes whose segments are shorter than this take the per-component phase (tuning knob)
 int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
@@ -1414,6 +1414,7 @@ int st_set_tuning(const char* key, int64_t value) {
   if (k == "sym22" && (value == 0 || value == 1)) { g_sym22 = (int)value; return ST_OK; }
   if (k == "sym22_min_dim" && value >= 1) { g_sym22_min_dim = value; return ST_OK; }
   if (k == "sym22_kch" && (value == 16 || value == 32)) { s22::g_kch = (int)value; return ST_OK; }
+  if (k == "sym22_debug" && value >= 0 && value < 128) { s22::g_debug = (int)value; return ST_OK; }
   if (k == "vec_short_segment" && value >= 0) {
     g_short_segment = value;
     std::lock_guard<std::mutex> lk(g_smu);

@@ -96,3 +96,55 @@ def contract_vec_sharded(rank_: int, dim: int, shard: torch.Tensor, x: torch.Ten
             return dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group, async_op=True)
         return None
     return all_reduce_sum(out, group)
+
+
+def tensordot22_bounds(dim: int, world: int, align: int = ALIGN) -> List[int]:
+    """Cut points of the packed rank-4 output of a tensordot with two free indices per side (BASELINE config 3) for ``world``
+    GPUs: contiguous ranges whose boundaries sit where the FIRST index enters a new block of 16 -- the tiles of the tcgen05
+    kernel (st_sym22.cu) are 16 x 16 x 16 x 8 index blocks, and a range boundary inside a block makes both neighbours run the
+    block's tiles -- balanced by the number of tiles each range has to run (``st_debug_sym22_tiles``: rank 0 also runs every
+    tile that holds components with repeated indices, which live in the small classes at the start of the buffer).  No
+    collective: the result stays sharded.  Pure host arithmetic."""
+    import ctypes
+    import math
+
+    from . import combinatorics as comb
+    from ._cabi import c_i64, lib
+
+    table = comb.class_table(4, dim)
+    total = table.total
+    if world <= 1:
+        return [0, total]
+    off4 = table.offsets[table.ncls - 1]
+    # first component whose smallest index is i0: (i0, i0+1, i0+2, i0+3) in class (1,1,1,1), lexicographic rank
+    def first_coord(i0):
+        r = math.comb(dim, 4) - 1 - (math.comb(dim - 1 - i0, 4) + math.comb(dim - 2 - i0, 3) + math.comb(dim - 3 - i0, 2) + math.comb(dim - 4 - i0, 1))
+        return off4 + r
+    cands = [0] + [min(total, first_coord(i0) // align * align) for i0 in range(16, dim - 3, 16)] + [total]
+    cands = sorted(set(cands))
+
+    def ntiles(b, e):
+        return int(lib.st_debug_sym22_tiles(c_i64(dim), c_i64(b), c_i64(e), ctypes.c_void_p(0), c_i64(0))) if e > b else 0
+
+    cuts = [0]
+    lo_idx = 0
+    for r in range(world - 1):
+        remaining = ntiles(cuts[-1], total)
+        target = remaining / (world - r)
+        # smallest candidate whose range reaches the target (tile counts grow with the end point), then the closer neighbour
+        lo, hi = lo_idx + 1, len(cands) - 1 - (world - 2 - r)
+        hi = max(hi, lo)
+        a, b = lo, hi
+        while a < b:
+            mid = (a + b) // 2
+            if ntiles(cuts[-1], cands[mid]) >= target:
+                b = mid
+            else:
+                a = mid + 1
+        best = a
+        if a > lo and abs(ntiles(cuts[-1], cands[a - 1]) - target) <= abs(ntiles(cuts[-1], cands[a]) - target):
+            best = a - 1
+        best = min(best, len(cands) - 1)
+        cuts.append(cands[best])
+        lo_idx = best
+    return cuts + [total]

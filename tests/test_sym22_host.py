@@ -18,7 +18,7 @@ def tiles_needed(dim, begin, end):
     for t in itertools.combinations_with_replacement(range(dim), 4):
         cls, pos = io.rank_of_index(t, dim)
         if begin <= tab.offsets[tab.index(cls)] + pos < end:
-            need.add((t[0] // 8, t[1] // 16, t[2] // 16, t[3] // 16))
+            need.add((t[0] // 16, t[1] // 16, t[2] // 16, t[3] // 8))
     return need
 
 
