@@ -233,6 +233,19 @@ int st_contract_mat_f64(int rank, int64_t dim, const double* d_a_flat, const dou
 int st_contract_mat_f32(int rank, int64_t dim, const float* d_a_flat, const float* d_W, float* d_out_flat, void* d_workspace,
                         void* stream);
 
+/* The same contraction restricted to the output components whose FIRST (smallest) mode j1 lies in [jlo, jhi) -- the multi-GPU
+ * partition of the matrix contraction "by output permutation classes / first output mode" (SURVEY.md 8e): with the flat
+ * (lexicographic) order these components are the contiguous range [*flat_begin, *flat_end) of the output
+ * (st_contract_mat_range_bounds), d_out_slice starts at *flat_begin, and every intermediate of the mode chain shards with
+ * it, so a GPU holds and computes only its slice of the chain (workspace: st_contract_mat_range_workspace_bytes).  A and W are
+ * replicated; no collective -- the result stays sharded (concatenate the slices for the whole tensor). */
+int st_contract_mat_range_bounds(int rank, int64_t dim, int64_t jlo, int64_t jhi, int64_t* flat_begin, int64_t* flat_end);
+int st_contract_mat_range_workspace_bytes(int rank, int64_t dim, int64_t jlo, int64_t jhi, int elem_size, int64_t* out_bytes);
+int st_contract_mat_range_f64(int rank, int64_t dim, const double* d_a_flat, const double* d_W, double* d_out_slice, int64_t jlo, int64_t jhi,
+                              void* d_workspace, void* stream);
+int st_contract_mat_range_f32(int rank, int64_t dim, const float* d_a_flat, const float* d_W, float* d_out_slice, int64_t jlo, int64_t jhi,
+                              void* d_workspace, void* stream);
+
 /* kernel variant selection for benchmarking / tests: 0 = auto (small classes per component, the rest through the
  * ring kernel), 1 = generic per-element enumerator, 2 = every class through the ring kernel.  Process-wide. */
 int st_set_vec_variant(int variant);

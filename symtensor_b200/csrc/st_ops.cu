@@ -506,7 +506,9 @@ __global__ void __launch_bounds__(256) gram_gather_kernel(PlanView P, int na, in
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256) mat_step_kernel(PlanView P, int k, int m, const T* __restrict__ Tk, const T* __restrict__ W,
-                                                       T* __restrict__ Tn, int64_t nJ, int64_t nI, int64_t nI1) {
+                                                       T* __restrict__ Tn, int64_t nJ, int64_t nI, int64_t nI1, int64_t jbase, int jlo, int jhi) {
+  // rows J = jbase + blockIdx.x / tilesI (a range of the sorted k-tuples: the multi-GPU partition by the first output mode);
+  // columns j restricted to [jlo, jhi) (step 0 of a partition; [0, d) otherwise).  Tk / Tn are indexed by GLOBAL rows.
   constexpr int TI = 64, TJ = 64, TK = 16;
   __shared__ T Ss[TK][TI + 4];
   __shared__ T Ws[TK][TJ + 4];
@@ -514,14 +516,14 @@ __global__ void __launch_bounds__(256) mat_step_kernel(PlanView P, int k, int m,
   __shared__ int32_t Js[ST_MAX_RANK];
   const int64_t d = P.dim;
   const int64_t tilesI = (nI + TI - 1) / TI;
-  const int64_t jidx = blockIdx.x / tilesI, i0 = (blockIdx.x % tilesI) * TI;
+  const int64_t jidx = jbase + blockIdx.x / tilesI, i0 = (blockIdx.x % tilesI) * TI;
   const int64_t j0 = (int64_t)blockIdx.y * TJ;
   if (threadIdx.x == 0) flat_unrank_r(P, jidx, k, Js);
   for (int r = threadIdx.x; r < TI; r += 256)
     if (i0 + r < nI) flat_unrank_r(P, i0 + r, m, Is[r]);
   __syncthreads();
-  const int jlast = k ? Js[k - 1] : 0;
-  if (j0 + TJ <= jlast) return;  // every column of this tile is below max(J): not a sorted (k+1)-tuple
+  const int jlast = max(k ? Js[k - 1] : 0, jlo);
+  if (j0 + TJ <= jlast || j0 >= jhi) return;  // every column of this tile is below max(J) (not a sorted (k+1)-tuple) or outside the range
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const T* __restrict__ row = Tk + jidx * nI1;
   T acc[4][4];
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(256) mat_step_kernel(PlanView P, int k, int m,
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int64_t jj = j0 + tx * 4 + j;
-    if (jj >= d || jj < jlast) continue;
+    if (jj >= d || jj < jlast || jj >= jhi) continue;
     Jn[k] = (int32_t)jj;
     const int64_t orow = flat_rank_r(P, Jn, k + 1);
 #pragma unroll
@@ -621,7 +623,7 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
 template <bool USE_TBL>
 __global__ void __launch_bounds__(256, 2) mat_step_dmma_kernel(PlanView P, int k, int m, const double* __restrict__ Tk, const double* __restrict__ W,
                                                             double* __restrict__ Tn, int64_t nJ, int64_t nI, int64_t nI1,
-                                                            const int32_t* __restrict__ tblI, int NT) {
+                                                            const int32_t* __restrict__ tblI, int NT, int64_t jbase, int jlo, int jhi) {
   constexpr int TI = 64, TJ = 64, TK = 32, LD = 68;  // LD = 4 mod 16: conflict-free fragment loads
   constexpr int PER = TI * TK / 256;                 // gathered components (and W entries) per thread and chunk
   __shared__ double Ss[TK][LD];
@@ -631,24 +633,24 @@ __global__ void __launch_bounds__(256, 2) mat_step_dmma_kernel(PlanView P, int k
   const int64_t d = P.dim;
   const int64_t tilesI = (nI + TI - 1) / TI;
   const int64_t strips = (tilesI + NT - 1) / NT;
-  const int64_t jidx = blockIdx.x / strips;
+  const int64_t jidx = jbase + blockIdx.x / strips;  // (a range of rows and, at step 0, of columns: see mat_step_kernel)
   const int64_t t0 = (blockIdx.x % strips) * NT;
   const int64_t t1 = t0 + NT < tilesI ? t0 + NT : tilesI;
   const int64_t j0 = (int64_t)blockIdx.y * TJ;
   if (threadIdx.x == 0) flat_unrank_r(P, jidx, k, Js);
   __syncthreads();
-  const int jlast = k ? Js[k - 1] : 0;
-  if (j0 + TJ <= jlast) return;  // every column of this tile is below max(J)
+  const int jlast = max(k ? Js[k - 1] : 0, jlo);
+  if (j0 + TJ <= jlast || j0 >= jhi) return;  // every column of this tile is below max(J) or outside the column range
   if (threadIdx.x < TJ) {        // output row of every column: flat rank of the sorted (k+1)-tuple (J, j)
     const int64_t jj = j0 + threadIdx.x;
     int32_t Jn[ST_MAX_RANK];
     for (int q = 0; q < k; ++q) Jn[q] = Js[q];
     Jn[k] = (int32_t)jj;
-    orow[threadIdx.x] = (jj < d && jj >= jlast) ? flat_rank_r(P, Jn, k + 1) : -1;
+    orow[threadIdx.x] = (jj < d && jj >= jlast && jj < jhi) ? flat_rank_r(P, Jn, k + 1) : -1;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int wr = warp & 3, wc = warp >> 2;  // 16-row block, 32-column block
-  const bool active = j0 + wc * 32 + 32 > jlast && j0 + wc * 32 < d;
+  const bool active = j0 + wc * 32 + 32 > jlast && j0 + wc * 32 < d && j0 + wc * 32 < jhi;
   const double* __restrict__ row = Tk + jidx * nI1;
   const int nchunk = (int)((d + TK - 1) / TK);
   double sreg[PER], wreg[PER];
@@ -734,7 +736,8 @@ __global__ void __launch_bounds__(256, 2) mat_step_dmma_kernel(PlanView P, int k
 // unrank and 63 successor steps), 64 columns.  The output position of (J, j) is  c_J - (d - 1 - j)  with
 // c_J = flat rank of (J, d - 1): consecutive j are consecutive output entries.
 __global__ void __launch_bounds__(256, 2) mat_last_dmma_kernel(PlanView P, int k, const double* __restrict__ Tk, const double* __restrict__ W,
-                                                               double* __restrict__ Tn, int64_t nJ) {
+                                                               double* __restrict__ Tn, int64_t nJ, int64_t rbase) {
+  // rows [rbase, nJ) of the sorted k-tuples (global row numbers; Tk / Tn indexed globally)
   constexpr int TI = 64, TJ = 64, TK = 32, LD = 68;
   __shared__ double Ss[TK][LD];
   __shared__ double Ws[TK][LD];
@@ -742,7 +745,7 @@ __global__ void __launch_bounds__(256, 2) mat_last_dmma_kernel(PlanView P, int k
   __shared__ int32_t jl[TI];
   __shared__ int32_t Jt[TI][ST_MAX_RANK];
   const int64_t d = P.dim;
-  const int64_t r0 = (int64_t)blockIdx.x * TI;
+  const int64_t r0 = rbase + (int64_t)blockIdx.x * TI;
   const int64_t j0 = (int64_t)blockIdx.y * TJ;
   if (threadIdx.x == 0) {
     flat_unrank_r(P, r0, k, Jt[0]);
@@ -1018,23 +1021,54 @@ static int tensordot(int ra, int rb, int k, int64_t dim, const T* d_a_flat, cons
   return check_cuda(cudaGetLastError(), "tensordot kernels");
 }
 
+// rows of the sorted k-tuples over range(d) whose FIRST element is below v (lexicographic = flat order)
+static int64_t rows_below(const HostPlan* hp, int k, int64_t v) {
+  if (k == 0) return v > 0 ? 1 : 0;
+  const int64_t d = hp->dim;
+  if (v >= d) return flat_size_host(hp, k);
+  if (v <= 0) return 0;
+  return flat_size_host(hp, k) - hp->h_binom[(d - v + k - 1) * (hp->rank + 1) + k];
+}
+
+// elements of one ping-pong intermediate for the output modes j1 in [jlo, jhi)
+static int64_t mat_range_elems(const HostPlan* hp, int rank, int64_t jlo, int64_t jhi) {
+  int64_t maxT = 0;
+  for (int k = 1; k <= rank; ++k) maxT = std::max(maxT, (rows_below(hp, k, jhi) - rows_below(hp, k, jlo)) * flat_size_host(hp, rank - k));
+  return maxT;
+}
+
+// C = (W^T)^{(x) r} . A restricted to the output components whose FIRST (smallest) mode j1 lies in [jlo, jhi): the flat
+// range [rows_below(r, jlo), rows_below(r, jhi)) of the output, written to d_out_slice (which starts at that position).
+// Every intermediate T_k of the chain shards with it (rows J whose first element is in the range), so a GPU of a
+// partition by j1 holds and computes only its slice of the chain: the multi-GPU scheme of SURVEY.md 8e, no collective.
 template <typename T>
-static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, T* d_out_flat, void* d_ws, cudaStream_t stream) {
+static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, T* d_out_slice, void* d_ws, cudaStream_t stream,
+                        int64_t jlo = 0, int64_t jhi = -1) {
   if (rank < 0 || rank > ST_MAX_RANK) { set_error("rank %d outside [0, %d]", rank, ST_MAX_RANK); return ST_ERR_INVALID; }
   PlanView P;
   int rc = get_device_plan(rank, dim, &P);
   if (rc) return rc;
   const HostPlan* hp = get_host_plan(rank, dim);
-  if (!d_a_flat || !d_out_flat || (rank > 0 && (!d_W || !d_ws))) { set_error("null pointer"); return ST_ERR_INVALID; }
-  if (rank == 0 || dim == 0) return check_cuda(cudaMemcpyAsync(d_out_flat, d_a_flat, sizeof(T) * (size_t)P.flat_size, cudaMemcpyDeviceToDevice, stream), "cudaMemcpyAsync");
+  if (jhi < 0) jhi = dim;
+  if (jlo < 0 || jhi < jlo || jhi > dim) { set_error("mode range [%lld, %lld) outside [0, %lld]", (long long)jlo, (long long)jhi, (long long)dim); return ST_ERR_INVALID; }
+  if (!d_a_flat || !d_out_slice || (rank > 0 && (!d_W || !d_ws))) { set_error("null pointer"); return ST_ERR_INVALID; }
+  if (rank == 0 || dim == 0) return check_cuda(cudaMemcpyAsync(d_out_slice, d_a_flat, sizeof(T) * (size_t)P.flat_size, cudaMemcpyDeviceToDevice, stream), "cudaMemcpyAsync");
+  if (jhi == jlo) return ST_OK;
+  const bool whole = jlo == 0 && jhi == dim;
   int64_t maxT = 0;
-  for (int k = 0; k <= rank; ++k) maxT = std::max(maxT, flat_size_host(hp, k) * flat_size_host(hp, rank - k));
+  if (whole) { for (int k = 0; k <= rank; ++k) maxT = std::max(maxT, flat_size_host(hp, k) * flat_size_host(hp, rank - k)); }
+  else maxT = mat_range_elems(hp, rank, jlo, jhi);
   T* buf[2] = {reinterpret_cast<T*>(d_ws), reinterpret_cast<T*>(d_ws) + maxT};
-  const T* src = d_a_flat;
+  const T* src = d_a_flat;  // global row indexing: row 0 of step 0 is the whole input
   for (int k = 0; k < rank; ++k) {
     const int m = rank - k - 1;
-    const int64_t nJ = flat_size_host(hp, k), nI = flat_size_host(hp, m), nI1 = flat_size_host(hp, m + 1);
-    T* dst = (k == rank - 1) ? d_out_flat : buf[k & 1];
+    const int64_t nI = flat_size_host(hp, m), nI1 = flat_size_host(hp, m + 1);
+    const int64_t rlo = rows_below(hp, k, jlo), rhi = k == 0 ? 1 : rows_below(hp, k, jhi);  // rows J of this step
+    const int64_t olo = rows_below(hp, k + 1, jlo);                                          // first output row
+    const int64_t nJ = rhi - rlo;
+    const int clo = k == 0 ? (int)jlo : 0, chi = k == 0 ? (int)jhi : (int)dim;               // columns j (step 0 only: the partition)
+    T* dst_slice = (k == rank - 1) ? d_out_slice : buf[k & 1];
+    T* dst = dst_slice - olo * nI;  // indexed by global output rows; only rows of the slice are touched
     const int64_t tilesI = (nI + 63) / 64;
     const int64_t gx = nJ * tilesI;
     if (gx > 2147483647LL) { set_error("mode-chain step %d needs %lld CTAs", k, (long long)gx); return ST_ERR_UNSUPPORTED; }
@@ -1049,21 +1083,21 @@ static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, 
       if (m == 0) {
         const dim3 lgrid((unsigned)((nJ + 63) / 64), (unsigned)((dim + 63) / 64));
         mat_last_dmma_kernel<<<lgrid, 256, 0, stream>>>(P, k, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
-                                                       reinterpret_cast<double*>(dst), nJ);
+                                                       reinterpret_cast<double*>(dst), rhi, rlo);
       } else if (tb > 0) {
         mat_index_kernel<<<(unsigned)((nI + 255) / 256), 256, 0, stream>>>(P, m, nI, tbl);
         count_launch();
         mat_step_dmma_kernel<true><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
-                                                              reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, NT);
+                                                              reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, NT, rlo, clo, chi);
       } else {
         mat_step_dmma_kernel<false><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
-                                                               reinterpret_cast<double*>(dst), nJ, nI, nI1, nullptr, NT);
+                                                               reinterpret_cast<double*>(dst), nJ, nI, nI1, nullptr, NT, rlo, clo, chi);
       }
     } else {
-      mat_step_kernel<T><<<grid, 256, 0, stream>>>(P, k, m, src, d_W, dst, nJ, nI, nI1);
+      mat_step_kernel<T><<<grid, 256, 0, stream>>>(P, k, m, src, d_W, dst, nJ, nI, nI1, rlo, clo, chi);
     }
     count_launch();
-    src = dst;
+    src = dst;  // (global row indexing again)
   }
   return check_cuda(cudaGetLastError(), "mat_step_kernel");
 }
@@ -1148,6 +1182,34 @@ int st_contract_mat_workspace_bytes(int rank, int64_t dim, int elem_size, int64_
   if (maxT * 2 * elem_size + tbl > (__int128)INT64_MAX) { set_error("workspace does not fit int64"); return ST_ERR_OVERFLOW; }
   *out_bytes = (int64_t)(maxT * 2 * elem_size) + tbl;
   return ST_OK;
+}
+int st_contract_mat_range_bounds(int rank, int64_t dim, int64_t jlo, int64_t jhi, int64_t* flat_begin, int64_t* flat_end) {
+  const HostPlan* hp = get_host_plan(rank, dim);
+  if (!hp) return ST_ERR_INVALID;
+  if (jlo < 0 || jhi < jlo || jhi > dim) { set_error("mode range [%lld, %lld) outside [0, %lld]", (long long)jlo, (long long)jhi, (long long)dim); return ST_ERR_INVALID; }
+  if (flat_begin) *flat_begin = rows_below(hp, rank, jlo);
+  if (flat_end) *flat_end = rows_below(hp, rank, jhi);
+  return ST_OK;
+}
+int st_contract_mat_range_workspace_bytes(int rank, int64_t dim, int64_t jlo, int64_t jhi, int elem_size, int64_t* out_bytes) {
+  const HostPlan* hp = get_host_plan(rank, dim);
+  if (!hp) return ST_ERR_INVALID;
+  if (!out_bytes) { set_error("null pointer"); return ST_ERR_INVALID; }
+  if (jlo < 0 || jhi < jlo || jhi > dim) { set_error("mode range [%lld, %lld) outside [0, %lld]", (long long)jlo, (long long)jhi, (long long)dim); return ST_ERR_INVALID; }
+  if (jlo == 0 && jhi == dim) return st_contract_mat_workspace_bytes(rank, dim, elem_size, out_bytes);
+  int64_t tbl = 0;
+  if (elem_size == 8)
+    for (int k = 0; k < rank; ++k) tbl = std::max(tbl, mat_table_bytes(hp, rank, k));
+  *out_bytes = mat_range_elems(hp, rank, jlo, jhi) * 2 * elem_size + tbl;
+  return ST_OK;
+}
+int st_contract_mat_range_f64(int rank, int64_t dim, const double* d_a_flat, const double* d_W, double* d_out_slice, int64_t jlo, int64_t jhi,
+                              void* d_workspace, void* stream) {
+  return contract_mat<double>(rank, dim, d_a_flat, d_W, d_out_slice, d_workspace, (cudaStream_t)stream, jlo, jhi);
+}
+int st_contract_mat_range_f32(int rank, int64_t dim, const float* d_a_flat, const float* d_W, float* d_out_slice, int64_t jlo, int64_t jhi,
+                              void* d_workspace, void* stream) {
+  return contract_mat<float>(rank, dim, d_a_flat, d_W, d_out_slice, d_workspace, (cudaStream_t)stream, jlo, jhi);
 }
 int st_contract_mat_f64(int rank, int64_t dim, const double* d_a_flat, const double* d_W, double* d_out_flat, void* d_workspace, void* stream) {
   return contract_mat<double>(rank, dim, d_a_flat, d_W, d_out_flat, d_workspace, (cudaStream_t)stream);

@@ -352,6 +352,29 @@ def _contract_all_indices_with_matrix(symtensor, W):
     return _wrap_flat_result(cls, symtensor.rank, d, outf)
 
 
+def contract_mat_device(symtensor, W, jlo: int, jhi: int, af=None):
+    """Raw launch of the matrix contraction for the output components whose first (smallest) mode lies in ``[jlo, jhi)`` --
+    the multi-GPU partition by the first output mode (``st_contract_mat_range_*``): returns
+    ``(flat_slice, flat_begin, flat_end)``, the contiguous range of the FLAT-ordered output this call computed.  The
+    intermediates of the mode chain are sharded the same way, so the workspace shrinks with the range."""
+    Wt = W if isinstance(W, torch.Tensor) else torch.as_tensor(np.asarray(W))
+    d = symtensor.dim
+    if tuple(Wt.shape) != (d, d):
+        raise ValueError(f"W must have shape {(d, d)}")
+    tdt = symtensor.torch_dtype
+    af = _flat_buffer(symtensor, tdt) if af is None else af
+    b, e, nbytes = c_i64(0), c_i64(0), c_i64(0)
+    check(lib.st_contract_mat_range_bounds(symtensor.rank, c_i64(d), c_i64(jlo), c_i64(jhi), ctypes.byref(b), ctypes.byref(e)))
+    check(lib.st_contract_mat_range_workspace_bytes(symtensor.rank, c_i64(d), c_i64(jlo), c_i64(jhi), af.element_size(), ctypes.byref(nbytes)))
+    with torch.cuda.device(af.device):
+        Wd = Wt.to(device=af.device, dtype=tdt).contiguous()
+        ws = torch.empty(max(1, nbytes.value // af.element_size() + 1), dtype=tdt, device=af.device)
+        out = torch.empty(max(0, e.value - b.value), dtype=tdt, device=af.device)
+        check(_fn("st_contract_mat_range", tdt)(symtensor.rank, c_i64(d), af.data_ptr(), Wd.data_ptr(), out.data_ptr(), c_i64(jlo), c_i64(jhi),
+                                                ws.data_ptr(), _stream_ptr(af.device)))
+    return out, b.value, e.value
+
+
 def outer_then_contract_vec(a, b, x):
     """Fused ``contract_all_indices_with_vector(multiply.outer(a, b), x)``: the rank-(ra+rb) tensor is never stored
     (BASELINE config 5's pipeline in one pass).  Returns a rank-0 tensor of the operands' class."""

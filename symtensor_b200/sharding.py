@@ -148,3 +148,41 @@ def tensordot22_bounds(dim: int, world: int, align: int = ALIGN) -> List[int]:
         cuts.append(cands[best])
         lo_idx = best
     return cuts + [total]
+
+
+def mat_mode_bounds(rank: int, dim: int, world: int) -> List[int]:
+    """Cut points ``j_0 = 0 < j_1 < ... < j_world = dim`` of the FIRST output mode for the matrix contraction on ``world`` GPUs
+    (``ops.contract_mat_device``): GPU g computes the output components whose smallest index lies in ``[j_g, j_{g+1})``.  Balanced
+    by the flops of the slice's mode chain: step k does 2 d rows_k(range) C(d + r - k - 2, r - k - 1) d flops, where rows_k counts
+    the sorted k-tuples whose first element is in the range (step 0: d times the width of the range).  Pure host arithmetic."""
+    import math
+    if world < 1:
+        raise ValueError("world must be >= 1")
+
+    def below(k, v):  # sorted k-tuples over range(dim) whose first element is < v
+        if k == 0:
+            return 1 if v > 0 else 0
+        return math.comb(dim + k - 1, k) - math.comb(dim - v + k - 1, k)
+
+    def cost(v):  # chain flops for the first mode in [0, v)
+        c = 0
+        for k in range(rank):
+            rows = v if k == 0 else below(k, v) * dim
+            c += rows * math.comb(dim + rank - k - 2, rank - k - 1)
+        return c
+    total = cost(dim)
+    cuts = [0]
+    for g in range(1, world):
+        target = total * g / world
+        lo, hi = cuts[-1], dim
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if cost(mid) >= target:
+                hi = mid
+            else:
+                lo = mid + 1
+        v = lo
+        if v > cuts[-1] + 1 and abs(cost(v - 1) - target) < abs(cost(v) - target):
+            v -= 1
+        cuts.append(min(max(v, cuts[-1]), dim))
+    return cuts + [dim]

@@ -151,6 +151,26 @@ def test_config4_windows_against_the_packed_direct_form(c4_tensor):
     assert abs(lhs - rhs) <= 1e-12 * abs(rhs), (lhs, rhs)
 
 
+def test_config4_first_mode_partition_of_8_gpus(c4_tensor):
+    """BASELINE config 4 cut for 8 GPUs by the first output mode (sharding.mat_mode_bounds): every slice -- computed from its own
+    slice of the mode chain, with its own (smaller) workspace -- equals the corresponding range of the whole result bit for bit."""
+    from symtensor_b200 import sharding
+    A = c4_tensor
+    rank, dim = 6, 64
+    rng = np.random.default_rng(48)
+    W = rng.uniform(0.5, 1.5, (dim, dim)) / dim
+    whole = ops._flat_buffer(st.contract_all_indices_with_matrix(A, W), torch.float64)
+    cuts = sharding.mat_mode_bounds(rank, dim, 8)
+    af = ops._flat_buffer(A, torch.float64)
+    pos = 0
+    for jlo, jhi in zip(cuts[:-1], cuts[1:]):
+        part, b, e = ops.contract_mat_device(A, W, jlo, jhi, af=af)
+        assert b == pos and torch.equal(part, whole[b:e]), (jlo, jhi)
+        pos = e
+        del part
+    assert pos == whole.numel()
+
+
 # ------------------------------------------------------------------------------------------------------------
 # C5: rank 4 (x) rank 4, dim 40, fp32 -> rank 8 (314,457,495 components), then the vector contraction
 # ------------------------------------------------------------------------------------------------------------

@@ -338,3 +338,32 @@ def test_tensordot_tiled_tcgen05_kernel_against_packed_oracle(ra, rb, k, dim, kc
     finally:
         check(lib.st_set_tuning(b"sym22_min_dim", c_i64(96)))
         check(lib.st_set_tuning(b"sym22_kch", c_i64(16)))
+
+
+@pytest.mark.parametrize("rank,dim,dtype", [(4, 12, np.float64), (3, 20, np.float64), (6, 6, np.float64), (5, 9, np.float32), (2, 33, np.float64), (4, 70, np.float64)])
+def test_matrix_first_mode_ranges_concatenate_to_the_whole(rank, dim, dtype):
+    """The multi-GPU partition of contract_all_indices_with_matrix by the FIRST output mode (st_contract_mat_range_*): the slices
+    of 1, 2, 3 and 8 GPUs -- each computed from its own slice of the mode chain -- concatenate bit for bit to the flat-ordered
+    result of the whole contraction, and that agrees with the packed oracle (symtensor/symalg.py:475-496)."""
+    from symtensor_b200 import sharding
+    rng = np.random.default_rng(rank * 37 + dim)
+    A = rand_packed(rank, dim, rng, "normal")
+    W = (rng.standard_normal((dim, dim)) / np.sqrt(dim)).astype(dtype)
+    TA = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=A, device=DEV).astype(dtype)
+    whole = ops._flat_buffer(st.contract_all_indices_with_matrix(TA, W), TA.torch_dtype)
+    if dim <= 20:
+        A_in = {q: v.astype(dtype).astype(np.float64) for q, v in A.items()}
+        ref = po.permcls_to_flat(po.contract_all_indices_with_matrix(A_in, rank, dim, W.astype(np.float64)), rank, dim)
+        scale = po.permcls_to_flat(po.contract_all_indices_with_matrix(absd(A_in), rank, dim, np.abs(W).astype(np.float64)), rank, dim)
+        tol = RTOL64 if dtype == np.float64 else RTOL32
+        assert np.all(np.abs(whole.cpu().numpy().astype(np.float64) - ref) <= tol * np.maximum(scale, 1e-300))
+    for world in (1, 2, 3, 8):
+        cuts = sharding.mat_mode_bounds(rank, dim, world)
+        assert cuts[0] == 0 and cuts[-1] == dim and all(a <= b for a, b in zip(cuts[:-1], cuts[1:]))
+        pos = 0
+        for jlo, jhi in zip(cuts[:-1], cuts[1:]):
+            part, b, e = ops.contract_mat_device(TA, W, jlo, jhi)
+            assert b == pos and e - b == part.numel()
+            assert torch.equal(part, whole[b:e]), (world, jlo, jhi)
+            pos = e
+        assert pos == whole.numel()

@@ -105,3 +105,35 @@ def test_rebalance_equalises_cost():
     times = [dens(cuts[r], cuts[r + 1]) for r in range(4)]
     assert max(times) / (sum(times) / 4) < 1.02
     assert sharding.rebalance([0, 100], [1.0]) == [0, 100]
+
+
+def test_matrix_mode_bounds_balance_the_chain_flops():
+    """sharding.mat_mode_bounds (host arithmetic): monotone cuts covering [0, dim]; at BASELINE config 4 (rank 6 dim 64, 8 GPUs)
+    no slice carries more than 1.35x the mean chain flops (the first mode is an integer: perfect balance is not available)."""
+    import math
+
+    from symtensor_b200 import sharding
+    for rank, dim, world in [(6, 64, 8), (4, 12, 3), (3, 20, 1), (2, 5, 8), (6, 64, 2)]:
+        cuts = sharding.mat_mode_bounds(rank, dim, world)
+        assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == dim
+        assert all(a <= b for a, b in zip(cuts[:-1], cuts[1:]))
+
+    def below(k, v, dim):
+        return (1 if v > 0 else 0) if k == 0 else math.comb(dim + k - 1, k) - math.comb(dim - v + k - 1, k)
+
+    def cost(v, rank, dim):
+        return sum((v if k == 0 else below(k, v, dim) * dim) * math.comb(dim + rank - k - 2, rank - k - 1) for k in range(rank))
+    rank, dim, world = 6, 64, 8
+    cuts = sharding.mat_mode_bounds(rank, dim, world)
+    parts = [cost(b, rank, dim) - cost(a, rank, dim) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert max(parts) <= 1.35 * sum(parts) / world
+
+
+def test_tensordot22_bounds_are_aligned_and_cover():
+    from symtensor_b200 import combinatorics as comb
+    from symtensor_b200 import sharding
+    for dim, world in [(70, 2), (200, 4), (120, 8)]:
+        total = comb.class_table(4, dim).total
+        cuts = sharding.tensordot22_bounds(dim, world)
+        assert len(cuts) == world + 1 and cuts[0] == 0 and cuts[-1] == total
+        assert all(a <= b for a, b in zip(cuts[:-1], cuts[1:])) and all(c % 32 == 0 for c in cuts[:-1])
