@@ -246,6 +246,44 @@ int st_contract_mat_range_f64(int rank, int64_t dim, const double* d_a_flat, con
 int st_contract_mat_range_f32(int rank, int64_t dim, const float* d_a_flat, const float* d_W, float* d_out_slice, int64_t jlo, int64_t jhi,
                               void* d_workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Rows next to the path, so that whole expressions stay on the GPU.  `layout` / `rank` / `dim` describe
+ * the packed buffers (same layout for operands and result; permcls padding is written as zeros).
+ * Elementwise ufuncs on the packed components (SymmetricTensor.default_unary_ufunc / default_binary_ufunc,
+ * symtensor/base.py:1146-1362).  Binary `mode`: 0 = a (op) b, 1 = a (op) scalar, 2 = scalar (op) a.
+ * ------------------------------------------------------------------------------------------------ */
+#define ST_UN_NEGATIVE 0
+#define ST_UN_ABS 1
+#define ST_UN_SQRT 2
+#define ST_UN_SQUARE 3
+#define ST_UN_EXP 4
+#define ST_UN_LOG 5
+#define ST_UN_RECIPROCAL 6
+#define ST_BIN_ADD 0
+#define ST_BIN_SUBTRACT 1
+#define ST_BIN_MULTIPLY 2
+#define ST_BIN_DIVIDE 3
+#define ST_BIN_MAXIMUM 4
+#define ST_BIN_MINIMUM 5
+#define ST_BIN_POWER 6
+int st_elementwise_unary_f64(int op, int layout, int rank, int64_t dim, const double* d_a, double* d_out, void* stream);
+int st_elementwise_unary_f32(int op, int layout, int rank, int64_t dim, const float* d_a, float* d_out, void* stream);
+int st_elementwise_binary_f64(int op, int mode, int layout, int rank, int64_t dim, const double* d_a, const double* d_b, double scalar, double* d_out,
+                              void* stream);
+int st_elementwise_binary_f32(int op, int mode, int layout, int rank, int64_t dim, const float* d_a, const float* d_b, double scalar, float* d_out,
+                              void* stream);
+/* isclose / allclose / array_equal (symtensor/base.py:1521-1684) of two tensors of the same layout, or of a tensor and a scalar
+ * (b_is_scalar).  mode 0: a == b, mode 1: numpy.isclose(a, b, rtol, atol, equal_nan).  *d_all (device int, caller-set to 1) is
+ * cleared when a component fails (allclose / array_equal); d_mask (optional) receives 1 / 0 per component (isclose). */
+int st_compare_f64(int mode, int layout, int rank, int64_t dim, const double* d_a, const double* d_b, int b_is_scalar, double scalar, double rtol,
+                   double atol, int equal_nan, double* d_mask, int* d_all, void* stream);
+int st_compare_f32(int mode, int layout, int rank, int64_t dim, const float* d_a, const float* d_b, int b_is_scalar, double scalar, double rtol, double atol,
+                   int equal_nan, float* d_mask, int* d_all, void* stream);
+/* Partial indexing A[i_1, ..., i_n] (symtensor/permcls_symtensor.py:750-781): the rank-(rank - nfixed) tensor B[K] = A[K + fixed],
+ * one gather per packed coordinate of B.  d_fixed: `nfixed` device int32 indices. */
+int st_slice_f64(int layout, int rank, int64_t dim, int nfixed, const int32_t* d_fixed, const double* d_a, double* d_out, void* stream);
+int st_slice_f32(int layout, int rank, int64_t dim, int nfixed, const int32_t* d_fixed, const float* d_a, float* d_out, void* stream);
+
 /* kernel variant selection for benchmarking / tests: 0 = auto (small classes per component, the rest through the
  * ring kernel), 1 = generic per-element enumerator, 2 = every class through the ring kernel.  Process-wide. */
 int st_set_vec_variant(int variant);

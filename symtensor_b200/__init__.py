@@ -16,7 +16,7 @@ from .flat import CudaFlatSymmetricTensor, FlatSymmetricTensor  # noqa: F401
 from .permcls import (CudaPermClsSymmetricTensor, PermClsSymmetricTensor, PermClsTorchSymmetricTensor,  # noqa: F401
                       TorchPermClsSymmetricTensor)
 from . import ops  # noqa: F401  (registers the CUDA implementations)
-from .symalg import (add, contract_all_indices_with_matrix, contract_all_indices_with_vector, multiply,  # noqa: F401
-                     subtract, tensordot)
+from .symalg import (add, contract_all_indices_with_matrix, contract_all_indices_with_vector, contract_tensor_list,  # noqa: F401
+                     multiply, subtract, tensordot)
 
 __version__ = "0.1.0"

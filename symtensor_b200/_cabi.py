@@ -71,6 +71,14 @@ SIGNATURES = {
     "st_contract_mat_range_workspace_bytes": (c_int, [c_int, c_i64, c_i64, c_i64, c_int, c_i64p]),
     "st_contract_mat_range_f64": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "st_contract_mat_range_f32": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "st_elementwise_unary_f64": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "st_elementwise_unary_f32": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "st_elementwise_binary_f64": (c_int, [c_int, c_int, c_int, c_int, c_i64, c_vp, c_vp, ctypes.c_double, c_vp, c_vp]),
+    "st_elementwise_binary_f32": (c_int, [c_int, c_int, c_int, c_int, c_i64, c_vp, c_vp, ctypes.c_double, c_vp, c_vp]),
+    "st_compare_f64": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int, c_vp, c_vp, c_vp]),
+    "st_compare_f32": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, c_int, c_vp, c_vp, c_vp]),
+    "st_slice_f64": (c_int, [c_int, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "st_slice_f32": (c_int, [c_int, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "st_set_vec_variant": (c_int, [c_int]),
     "st_set_tuning": (c_int, [ctypes.c_char_p, c_i64]),
     "st_debug_vec_timeline": (c_int, [c_vp, c_i64]),

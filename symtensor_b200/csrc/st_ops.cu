@@ -1051,9 +1051,9 @@ static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, 
   const HostPlan* hp = get_host_plan(rank, dim);
   if (jhi < 0) jhi = dim;
   if (jlo < 0 || jhi < jlo || jhi > dim) { set_error("mode range [%lld, %lld) outside [0, %lld]", (long long)jlo, (long long)jhi, (long long)dim); return ST_ERR_INVALID; }
+  if (jhi == jlo && rank > 0 && dim > 0) return ST_OK;  // empty slice
   if (!d_a_flat || !d_out_slice || (rank > 0 && (!d_W || !d_ws))) { set_error("null pointer"); return ST_ERR_INVALID; }
   if (rank == 0 || dim == 0) return check_cuda(cudaMemcpyAsync(d_out_slice, d_a_flat, sizeof(T) * (size_t)P.flat_size, cudaMemcpyDeviceToDevice, stream), "cudaMemcpyAsync");
-  if (jhi == jlo) return ST_OK;
   const bool whole = jlo == 0 && jhi == dim;
   int64_t maxT = 0;
   if (whole) { for (int k = 0; k <= rank; ++k) maxT = std::max(maxT, flat_size_host(hp, k) * flat_size_host(hp, rank - k)); }
@@ -1063,7 +1063,7 @@ static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, 
   for (int k = 0; k < rank; ++k) {
     const int m = rank - k - 1;
     const int64_t nI = flat_size_host(hp, m), nI1 = flat_size_host(hp, m + 1);
-    const int64_t rlo = rows_below(hp, k, jlo), rhi = k == 0 ? 1 : rows_below(hp, k, jhi);  // rows J of this step
+    const int64_t rlo = k == 0 ? 0 : rows_below(hp, k, jlo), rhi = k == 0 ? 1 : rows_below(hp, k, jhi);  // rows J of this step
     const int64_t olo = rows_below(hp, k + 1, jlo);                                          // first output row
     const int64_t nJ = rhi - rlo;
     const int clo = k == 0 ? (int)jlo : 0, chi = k == 0 ? (int)jhi : (int)dim;               // columns j (step 0 only: the partition)

@@ -15,10 +15,11 @@ import torch
 from . import combinatorics as comb
 from ._cabi import LAYOUT_FLAT, c_i64, check, lib
 from .base import SymmetricTensor
+from .elementwise import PackedElementwise
 from .permcls import _TORCH2NP, _is_host, _kernel_dtype, _stream_ptr, pack_dense_device, to_torch_dtype, unpack_dense_device
 
 
-class CudaFlatSymmetricTensor(SymmetricTensor):
+class CudaFlatSymmetricTensor(PackedElementwise, SymmetricTensor):
     data_format = "Flat"
     layout = LAYOUT_FLAT
     array_type = torch.Tensor
@@ -140,8 +141,16 @@ class CudaFlatSymmetricTensor(SymmetricTensor):
     def __getitem__(self, key):
         if isinstance(key, (int, np.integer)):
             key = (int(key),)
-        if not isinstance(key, tuple) or len(key) != self.rank or any(isinstance(k, slice) for k in key):
-            raise NotImplementedError("only full integer indexing is part of the CUDA hot path")
+        if isinstance(key, tuple) and any(isinstance(k, slice) for k in key):
+            if any(isinstance(k, slice) and k != slice(None) for k in key):
+                raise NotImplementedError("only `:` slices are supported ([i_1, ..., i_n, :, ..., :])")
+            key = tuple(int(k) for k in key if not isinstance(k, slice))
+            if len(key) == 0:
+                return self
+        if not isinstance(key, tuple) or len(key) > self.rank:
+            raise KeyError(f"{key}")
+        if len(key) < self.rank:
+            return self.slice_fixed(key)  # rank-lowering gather on the device
         return self._buf[comb.flat_rank(self.dim, key)]
 
     def __setitem__(self, key, value):

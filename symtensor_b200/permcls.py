@@ -26,6 +26,7 @@ import torch
 from . import combinatorics as comb
 from ._cabi import LAYOUT_PERMCLS, c_i64, check, lib
 from .base import SymmetricTensor
+from .elementwise import PackedElementwise
 
 Cls = Tuple[int, ...]
 
@@ -90,7 +91,7 @@ def _kernel_dtype(tdt: torch.dtype) -> bool:
     return tdt in (torch.float32, torch.float64)
 
 
-class CudaPermClsSymmetricTensor(SymmetricTensor):
+class CudaPermClsSymmetricTensor(PackedElementwise, SymmetricTensor):
     """On creation, defaults to a zero tensor (like the reference)."""
 
     data_format = "PermCls"
@@ -335,9 +336,17 @@ class CudaPermClsSymmetricTensor(SymmetricTensor):
         if isinstance(key, (int, np.integer)):
             key = (int(key),)
         if isinstance(key, tuple):
-            if any(isinstance(k, slice) for k in key) or len(key) < self.rank:
-                raise NotImplementedError("Partial / sliced indexing is not part of the CUDA hot path "
-                                          "(symtensor/permcls_symtensor.py:750-781 is host Python).")
+            if any(isinstance(k, slice) for k in key):
+                # only `:` slices, which just drop out of the key (symtensor/permcls_symtensor.py:735-748)
+                if any(isinstance(k, slice) and k != slice(None) for k in key):
+                    raise NotImplementedError("Indexing with subslicing (for example SymmetricTensor[1:3, 0,0]) is not currently implemented. "
+                                              "Only slices of the type [i_1,...,i_n,:,...,:] with i_1,..., i_n all integers are allowed.")
+                key = tuple(int(k) for k in key if not isinstance(k, slice))
+                if len(key) == 0:
+                    return self
+            if len(key) < self.rank:
+                # fewer indices than the rank: the rank-lowering gather (symtensor/permcls_symtensor.py:750-781) on the device
+                return self.slice_fixed(key)
             c, pos = comb.convert_dense_index(self.rank, self.dim, key)
             return self._data[c][pos] if self.rank else self._data[c]
         raise KeyError(f"{key}")

@@ -101,3 +101,54 @@ class UfuncWrapper:
 add = UfuncWrapper(np.add)
 subtract = UfuncWrapper(np.subtract)
 multiply = UfuncWrapper(np.multiply)
+
+
+def contract_tensor_list(symtensor, tensor_list, n_times: int = 1, rule: str = "second_half"):
+    """symtensor/symalg.py:556-642: for A = ``symtensor`` and chi_i = ``tensor_list[i]`` (all symmetric, same shape)
+
+        B = Sym[ sum over the last n indices  A[..., i_1, ..., i_n] (x) chi_{i_1} (x) ... (x) chi_{i_n} ]
+
+    computed as the reference does -- ``C += reduce(multiply.outer, (chi_i for i in idx), A[idx])`` over the index tuples -- but
+    with every piece on the device: ``A[idx]`` is the rank-lowering gather (``st_slice_*``), the products are the symmetrized
+    outer kernels, the accumulation an elementwise add on the packed buffer.  ``rule='second_half'`` (the reference's default)
+    sums only over indices ``>= ceil(dim / 2)``; the reference raises ``NameError`` there because ``math`` is not imported
+    (symalg.py:628) -- this implementation computes what that branch was written to compute.  ``rule='all'`` (any other value in
+    the reference) sums over all indices."""
+    import math
+    from functools import reduce
+    from itertools import product
+
+    tensor_list = list(tensor_list)
+    if not isinstance(symtensor, SymmetricTensor) or not all(isinstance(x, SymmetricTensor) for x in tensor_list):
+        return NotImplemented
+    cls = result_array(symtensor, *tensor_list)
+    A = symtensor
+    if n_times > A.rank:
+        raise ValueError(f"n_times is {n_times}, but cannot do more contractions than {A.rank} with tensor of rank {A.rank}")
+    if len(tensor_list) != A.dim:
+        raise ValueError("`tensor_list` emulates the first dimension of a tensor, and therefore its length must match the dimenion of "
+                         f"`symtensor`.\nSymtensor dim     : {A.dim}\nLength tensor list: {len(tensor_list)}")
+    ranks, dims = {x.rank for x in tensor_list}, {x.dim for x in tensor_list}
+    if len(ranks) > 1 or len(dims) > 1:
+        raise ValueError(f"Tensors in `tensor_list` do not all have the same shape:\n{[x.shape for x in tensor_list]}")
+    chi_rank, chi_dim = next(iter(ranks)), next(iter(dims))
+    if chi_dim != A.dim:
+        raise ValueError("Tensors in `tensor_list` do not have the same dimension as `symtensor`.")
+    if A.rank == 1 and n_times == 1:
+        acc = None
+        for i in range(A.dim):
+            term = tensor_list[i] * A[i]
+            acc = term if acc is None else acc + term
+        return acc if acc is not None else cls(tensor_list[0].rank, tensor_list[0].dim)
+    if rule == "second_half":
+        indices = product(range(math.ceil(A.dim / 2), A.dim), repeat=n_times)
+    else:
+        indices = product(range(A.dim), repeat=n_times)
+    C = None
+    for idx in indices:
+        head = A[idx] if n_times < A.rank else A[idx]  # rank-lowering gather (a scalar tensor entry when n_times == rank)
+        term = reduce(multiply.outer, (tensor_list[i] for i in idx), head)
+        C = term if C is None else C + term
+    if C is None:  # no index to sum over (dim 0 or 1 with 'second_half'): a zero tensor of the result shape
+        C = cls(rank=A.rank + n_times * (chi_rank - 1), dim=A.dim, device=getattr(A, "device", None))
+    return C
