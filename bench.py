@@ -47,6 +47,17 @@ def measured_peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_peak_bf16():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["bf16_tflops"]), True
+        except Exception:
+            pass
+    return 1590.0, False
+
+
 def ncu_traffic(n_comps):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -516,6 +527,27 @@ def run_gpu(args):
         except Exception as e:  # the oracle is optional for the bench line
             cpu_packed = {"error": str(e)[:200]}
 
+    # ---- the other BASELINE configurations (tensordot, matrix contraction, outer -> vector): extra keys of the line
+    other = {}
+    if not args.skip_configs:
+        import bench_configs as bc
+        pk = {"hbm_gbs": measured_peak_hbm()[0], "bf16_tflops": measured_peak_bf16()[0], "measured": measured_peak_bf16()[1]}
+        del shard
+        torch.cuda.empty_cache()
+        for name, fn in (("config5", bc.config5), ("config4", bc.config4), ("config3", bc.config3)):
+            try:
+                other[name] = fn(dev, world, rank, dist if world > 1 else None, pk)
+            except Exception as ex:  # a failed extra must not take the headline line with it
+                other[name] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+            torch.cuda.empty_cache()
+        if world == 1:
+            try:
+                for name, leg in bc.cpu_legs().items():
+                    if name in other and "error" not in other[name]:
+                        other[name]["cpu_baseline"] = leg
+            except Exception as ex:
+                other["cpu_legs_error"] = str(ex)[:200]
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         alg_bytes = n_comps * 8 / world  # per launch (per GPU): every stored fp64 value is read exactly once
@@ -548,6 +580,7 @@ def run_gpu(args):
             line["strong"] = strong
         if serial is not None:
             line["serial"] = serial
+        line.update(other)
         if rebalanced is not None:
             line["config"]["slices"] = "contiguous 32-aligned slices of the packed range, cut points moved until the per-rank kernel times agree"
             line["rebalance"] = rebalanced
@@ -563,6 +596,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--skip-configs", action="store_true", help="only the headline workload (configs[1]); skip configs[2..4]")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -133,6 +133,8 @@ class PackedElementwise:
         return self._binary(3, o, reflected=True)
 
     def __pow__(self, o):
+        if isinstance(o, (int, float)) and o == 2:
+            return self._unary(3)  # like NumPy, x ** 2 is the exact square
         return self._binary(6, o)
 
     def __iadd__(self, o):
