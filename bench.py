@@ -326,56 +326,129 @@ def run_gpu(args):
             desc._buf = shard
             rebalanced = {"kernel_ms_per_rank_before_last_round": [round(v, 4) for v in times],
                           "slice_fractions": [round((cuts[r + 1] - cuts[r]) / total, 4) for r in range(world)]}
-    # N > 1: the scalar all-reduce of step i is enqueued asynchronously and overlaps the kernel of step i + 1 (results
-    # alternate between two buffers; a buffer's collective is waited for before the buffer is written again)
-    outs = [out, torch.zeros_like(out)]
-    wss = [ws, torch.empty_like(ws)] if world > 1 else [ws, ws]
-    pending = [None, None]
-    counter = [0]
+    class Pipeline:
+        """The timed loop over one sharded tensor.  Every step is one ST_VEC_OVERLAP kernel launch over this rank's slice (the
+        operands are resident: the ramp-up of step i + 1 overlaps the tail of step i) and, for N > 1, the all-reduce of one
+        fp64, enqueued asynchronously so that it overlaps the kernel of step i + 1 (results alternate between two buffers; a
+        buffer's collective is waited for before the buffer is written again).  N > 1: the per-step host work (a ctypes call
+        plus a torch.distributed call, ~40 us) would hide kernels of a few tens of us, so a block of steps is captured ONCE
+        in a CUDA graph -- kernel launches with their programmatic edges, the NCCL all-reduces on the collective's stream,
+        the waits that guard the two result buffers -- and the timed region replays it.  Every step is still one kernel
+        launch and one all-reduce; only the host's part is gone."""
 
-    def step():
-        # local streaming kernel over this rank's slice, then (N > 1) the all-reduce of one fp64
-        i = counter[0] & 1
-        counter[0] += 1
-        # the steps contract RESIDENT operands: every launch is flagged ST_VEC_OVERLAP (programmatic dependent launch), so
-        # the ramp-up of step i + 1 overlaps the tail of step i (one kernel launch per step either way)
-        if world == 1:
-            sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, out, ws, overlap=True)
-            return
-        if pending[i] is not None:
-            pending[i].wait()
-        pending[i] = sharding.contract_vec_sharded(RANK, dim, shard, x, begin, end, outs[i], wss[i], async_op=True, overlap=True)
+        def __init__(self, rank_, dim_, shard_, x_, begin_, end_):
+            self.a = (rank_, dim_, shard_, x_, begin_, end_)
+            self.outs = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
+            self.wss = [torch.empty_like(ws) for _ in range(2)] if world > 1 else [ws, ws]
+            self.pending = [None, None]
+            self.count = 0
+            self.graph, self.block, self.error = None, 0, None
 
-    def drain():
-        for i in range(2):
-            if pending[i] is not None:
-                pending[i].wait()
-                pending[i] = None
+        def step(self):
+            i = self.count & 1
+            self.count += 1
+            r_, d_, sh_, x_, b_, e_ = self.a
+            if world == 1:
+                sharding.contract_vec_sharded(r_, d_, sh_, x_, b_, e_, self.outs[0], self.wss[0], overlap=True)
+                return
+            if self.pending[i] is not None:
+                self.pending[i].wait()
+            self.pending[i] = sharding.contract_vec_sharded(r_, d_, sh_, x_, b_, e_, self.outs[i], self.wss[i], async_op=True, overlap=True)
 
-    def timed(nsteps):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.st_launch_count()
-        e0.record()
-        for _ in range(nsteps):
-            step()
-        drain()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
-        return ms, lib.st_launch_count() - l0
+        def drain(self):
+            for i in range(2):
+                if self.pending[i] is not None:
+                    self.pending[i].wait()
+                    self.pending[i] = None
+
+        def result(self):
+            return float(self.outs[(self.count - 1) & 1][0]) if world > 1 else float(self.outs[0][0])
+
+        def build_graph(self, block):
+            if world == 1 or args.no_graph:
+                return
+            try:
+                self.drain()
+                torch.cuda.synchronize()
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(2):  # warm-up on the capture stream (per-stream counters of the library, NCCL)
+                        self.step()
+                    self.drain()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                if block % 2:
+                    block += 1  # whole pairs of steps: the buffer parity at the end of a replay is the one at its start
+                with torch.cuda.graph(g, stream=side):
+                    for _ in range(block):
+                        self.step()
+                    self.drain()
+                torch.cuda.synchronize()
+                g.replay()
+                torch.cuda.synchronize()
+                self.graph, self.block = g, block
+            except Exception as ex:  # fall back to eager launches
+                self.error = f"{type(ex).__name__}: {str(ex)[:200]}"
+                self.graph = None
+                self.pending = [None, None]
+                try:
+                    torch.cuda.synchronize()
+                except Exception:
+                    pass
+            ok = torch.tensor([1 if self.graph is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok[0]) == 0:  # all ranks or none
+                self.graph = None
+
+        def timed(self, nsteps):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = lib.st_launch_count()
+            e0.record()
+            if self.graph is not None and nsteps % self.block == 0:
+                for _ in range(nsteps // self.block):
+                    self.graph.replay()
+                launched = nsteps
+            else:
+                for _ in range(nsteps):
+                    self.step()
+                self.drain()
+                launched = lib.st_launch_count() - l0
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t[0])
+            return ms, launched
+
+        def how(self):
+            if world == 1:
+                return "one host launch per step"
+            if self.graph is not None:
+                return "a CUDA graph of %d steps (kernel launches with programmatic edges + NCCL all-reduces), replayed" % self.block
+            return "one host launch per step" + (f" (graph capture failed: {self.error})" if self.error else "")
+
+    def graph_block(nsteps):
+        for b in (20, 10, 8, 6, 4, 2):
+            if nsteps % b == 0:
+                return b
+        return nsteps + (nsteps & 1)
+
+    pipe = Pipeline(RANK, dim, shard, x, begin, end)
+    step, drain = pipe.step, pipe.drain
 
     for _ in range(max(args.warmup, 3)):
         step()
     drain()
+    pipe.build_graph(graph_block(args.steps))
     with ClockSampler(local) as clocks:
-        ms, launches = timed(args.steps)
+        ms, launches = pipe.timed(args.steps)
     ms_per_step = ms / args.steps
     value = n_comps / (ms_per_step * 1e-3)
     # the same launches WITHOUT the overlap (each launch starts after the previous one has completely finished): the
@@ -395,7 +468,7 @@ def run_gpu(args):
         isolated = {"ms_per_step": iso_ms, "value": n_comps / (iso_ms * 1e-3), "unit": "packed components/s",
                     "hbm_gbs": n_comps * 8 / (iso_ms * 1e-3) / 1e9,
                     "note": "back-to-back launches without ST_VEC_OVERLAP: launch i + 1 starts when launch i has completely finished"}
-    result = float(outs[(counter[0] - 1) & 1][0]) if world > 1 else float(out[0])
+    result = pipe.result()
     serial = None
     if world > 1:
         # the same step without the overlap (kernel, then a blocking all-reduce): reported next to the headline
@@ -427,22 +500,31 @@ def run_gpu(args):
         d2.dim = DIM
         d2._buf = sh2
 
-        def step2():
-            sharding.contract_vec_sharded(RANK, DIM, sh2, x2, b2, e2_, out, ws)
+        pipe2 = Pipeline(RANK, DIM, sh2, x2, b2, e2_)
         for _ in range(5):
-            step2()
+            pipe2.step()
+        pipe2.drain()
+        pipe2.build_graph(graph_block(args.steps))
+        ms2, _ = pipe2.timed(args.steps)
+        t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+        strong = {"value": sum(t200.sizes) / (float(t[0]) / args.steps * 1e-3), "unit": "packed components/s",
+                  "ms_per_step": float(t[0]) / args.steps, "workload": "rank 4 dim 200 cut %d ways" % world, "launch": pipe2.how(),
+                  "note": "same pipeline as the headline (overlapped launches, asynchronous all-reduce); 'serial' below is the un-pipelined step"}
+        # un-pipelined latency of ONE contraction of the dim-200 tensor on N GPUs: kernel, then a blocking all-reduce, from the host
+        for _ in range(3):
+            sharding.contract_vec_sharded(RANK, DIM, sh2, x2, b2, e2_, out, ws)
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            step2()
+            sharding.contract_vec_sharded(RANK, DIM, sh2, x2, b2, e2_, out, ws)
         e1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        strong = {"value": sum(t200.sizes) / (float(t[0]) / args.steps * 1e-3), "unit": "packed components/s",
-                  "ms_per_step": float(t[0]) / args.steps, "workload": "rank 4 dim 200 cut %d ways" % world}
+        strong["latency_ms_unpipelined"] = float(t[0])
+        del pipe2
 
     # ---- end to end through the reference-facing API with HOST buffers (rank 0 of N = 1 only)
     e2e = None
@@ -581,6 +663,8 @@ def run_gpu(args):
         if serial is not None:
             line["serial"] = serial
         line.update(other)
+        if world > 1:
+            line["config"]["launch"] = pipe.how()
         if rebalanced is not None:
             line["config"]["slices"] = "contiguous 32-aligned slices of the packed range, cut points moved until the per-rank kernel times agree"
             line["rebalance"] = rebalanced
@@ -596,6 +680,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="N > 1: launch every step from the host instead of replaying a CUDA graph")
     ap.add_argument("--skip-configs", action="store_true", help="only the headline workload (configs[1]); skip configs[2..4]")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -137,7 +137,8 @@ __device__ __forceinline__ double outer_terms(const int32_t* __restrict__ F, int
       if ((mask >> p) & 1u) { sa += G[RA - 1 - ia][p]; ++ia; }
       else { sb += G[RB - 1 - ib][p]; ++ib; }
     }
-    acc += (double)af[base_a - sa] * (double)bf[base_b - sb];
+    if (sizeof(T) == 4) acc += (double)((float)af[base_a - sa] * (float)bf[base_b - sb]);  // fp32: one rounding of the product (6e-8), fp64 sum
+    else acc += (double)af[base_a - sa] * (double)bf[base_b - sb];
   }
   return acc;
 }
@@ -157,7 +158,13 @@ __global__ void __launch_bounds__(256) outer_fast_kernel(PlanView P, const T* __
   __syncthreads();
   const int base_a = (int)(binom_at(P.binom, P.rank, d + RA - 1, RA) - 1), base_b = (int)(binom_at(P.binom, P.rank, d + RB - 1, RB) - 1);
   double total = 0.0;
-  for (int64_t c = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < end; c += (int64_t)gridDim.x * blockDim.x) {
+  // A CTA takes CHUNKS of consecutive coordinates (not a grid-stride): consecutive components share their leading indices,
+  // so the operand entries a chunk gathers (~4 distinct floats per component) stay in L1 -- the operands (494 KB each at
+  // BASELINE config 5) do not fit L1 as a whole, and with a grid-stride every 256 components started cold (L2 latency).
+  constexpr int64_t kChunk = 8192;
+  const int64_t nchunks = (end - begin + kChunk - 1) / kChunk;
+  for (int64_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
+  for (int64_t c = begin + ch * kChunk + threadIdx.x; c < end && c < begin + (ch + 1) * kChunk; c += blockDim.x) {
     int32_t K[ST_MAX_RANK];
     if (!permcls_coord_sorted(P, c, K)) {
       if (!VEC) out[c - begin] = T(0);

@@ -24,12 +24,13 @@
 // truncation, so a CHAIN is at most 256 products long (st_ops.cu: measured 1.4e-5 of sum|terms| at 1024, 3.5e-6 at 256):
 // after every chain the issuer commits the accumulator to the epilogue (tmem-full barrier) and continues in the other
 // accumulator; the epilogue warps drain it with tcgen05.ld and add the chains in REGISTERS with round-to-nearest (each
-// thread keeps 128 columns of its row).  At the end of a pairing the thread scales by 1/6 and adds its values straight
-// into the packed permcls output with red.global.add.f32 (the position of (i, j, k, l) is a sum of four per-index terms,
-// kept in shared-memory tables per tile); the output range is zeroed first and every component receives exactly three
-// adds, all from the same CTA in a fixed order, so the result is deterministic.  Elements with repeated indices
-// (diagonal tiles) go through the generic class rank.  [begin, end) ranges of the output are served by the tiles that
-// intersect them -- the multi-GPU partition, no collective.
+// thread keeps 128 columns of its row).  At the end of a pairing the thread scales by 1/6 and writes (first pairing) or adds
+// (red.global.add.f32, the other two) its values into the tile's own contiguous 128 KB SLOT of a scratch buffer -- one
+// page, L2-resident across the three pairings; the three contributions of a component come from the same CTA in a fixed
+// order, so the result is deterministic.  A second, plain HBM-bound kernel (sym22_scatter_kernel) moves the slots into the
+// packed permcls layout: the position of (i < j < k < l) is a sum of four per-index terms, components with repeated indices
+// (diagonal tiles) go through the generic class rank.  Tiles are processed in batches of 32768 (4 GB of slots).
+// [begin, end) ranges of the output are served by the tiles that intersect them -- the multi-GPU partition, no collective.
 #include <cuda.h>
 
 #include <algorithm>
@@ -49,6 +50,7 @@ constexpr int TN = BJ * BJ;   // 256 columns: the other two
 constexpr int NTHREADS = 384;
 constexpr int CHAIN_K = 256;  // products per TMEM accumulation chain
 constexpr int SMEM_STAGE_BUDGET = 192 * 1024;
+constexpr int64_t kBatchTiles = 32768;  // tiles per launch: their slots (4 GB) are the scratch part of the workspace
 
 template <int KCH>
 struct Geo {
@@ -64,7 +66,8 @@ struct Geo {
 struct Params {
   PlanView P;          // plan of the rank-4 output
   int64_t begin, end;  // packed output coordinates served by this launch
-  float* out;          // points at coordinate `begin`
+  float* out;          // points at coordinate `begin` (sym22_scatter_kernel)
+  float* scratch;      // one 128 KB slot per tile of the launch (tile t of the launch -> slot t)
   const unsigned long long* tiles;  // block numbers p | q << 16 | r << 32 | s << 48 of i, j, k (16 wide) and l (8 wide)
   int64_t ntiles;
   int32_t nst;         // stages per K segment (Kp / KCH)
@@ -161,11 +164,36 @@ __device__ __forceinline__ int64_t element_coord(const PlanView& P, int64_t base
   return P.cls[ci].offset + permcls_rank_vals(P, P.cls[ci], vals);
 }
 
-// one output of a tile that is not "fast" (repeated indices, the ragged edge, or a launch range that cuts the tile)
-__device__ __noinline__ void slow_add(const PlanView& P, int64_t base1111, int64_t begin, int64_t end, float* out, int gi, int gj, int gk, int gl,
-                                      float v) {
-  const int64_t coord = element_coord(P, base1111, gi, gj, gk, gl);
-  if (coord >= begin && coord < end) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(out + (coord - begin)), "f"(v) : "memory");
+// Second pass: the tiles' slots (tile-major, L(i, j, k, l) = ((i 16 + j) 16 + k) 8 + l) -> the packed permcls output.  One CTA
+// per tile; a thread handles consecutive L, so 8 lanes write the 8 consecutive l of one (i, j, k) = one 32-byte sector, and
+// the many warps in flight hide the page walks of the scattered rows.  Components outside [begin, end), unsorted index
+// combinations of diagonal tiles and indices beyond the tensor are skipped; every component of the range is written exactly
+// once (by the one tile that holds it).  Strictly increasing indices take the four-term formula from shared-memory tables,
+// repeated indices the generic class rank.
+__global__ void __launch_bounds__(256) sym22_scatter_kernel(PlanView P, const unsigned long long* __restrict__ tiles, const float* __restrict__ scratch,
+                                                            float* __restrict__ out, int64_t begin, int64_t end) {
+  __shared__ long long Ti[BJ], Tj[BJ], Tk[BJ], Tl[BL];
+  const unsigned long long tw = tiles[blockIdx.x];
+  const int i0 = (int)(tw & 0xffff) * BJ, j0 = (int)((tw >> 16) & 0xffff) * BJ, k0 = (int)((tw >> 32) & 0xffff) * BJ,
+            l0 = (int)((tw >> 48) & 0xffff) * BL;
+  if (threadIdx.x < BJ) {
+    Ti[threadIdx.x] = binom_at(P.binom, 4, P.dim - 1 - (i0 + threadIdx.x), 4);
+    Tj[threadIdx.x] = binom_at(P.binom, 4, P.dim - 1 - (j0 + threadIdx.x), 3);
+    Tk[threadIdx.x] = binom_at(P.binom, 4, P.dim - 1 - (k0 + threadIdx.x), 2);
+    if (threadIdx.x < BL) Tl[threadIdx.x] = binom_at(P.binom, 4, P.dim - 1 - (l0 + threadIdx.x), 1);
+  }
+  __syncthreads();
+  const int64_t base1111 = P.cls[P.ncls - 1].offset + binom_at(P.binom, 4, P.dim, 4) - 1;
+  const float* __restrict__ slot = scratch + (size_t)blockIdx.x * (TM * TN);
+  for (int L = threadIdx.x; L < TM * TN; L += 256) {
+    const int l = L & 7, k = (L >> 3) & 15, j = (L >> 7) & 15, i = L >> 11;
+    const int gi = i0 + i, gj = j0 + j, gk = k0 + k, gl = l0 + l;
+    if (!(gi <= gj && gj <= gk && gk <= gl) || gl >= P.dim) continue;
+    int64_t coord;
+    if (gi < gj && gj < gk && gk < gl) coord = base1111 - Ti[i] - Tj[j] - Tk[k] - Tl[l];
+    else coord = element_coord(P, base1111, gi, gj, gk, gl);
+    if (coord >= begin && coord < end) out[coord - begin] = slot[L];
+  }
 }
 
 template <int KCH>
@@ -274,12 +302,9 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
     }
   } else if (warp >= 4) {
     // ===================== epilogue (8 warps) =====================
-    const PlanView& P = prm.P;
-    const int et = threadIdx.x - 128;          // 0..255
     const int lq = warp & 3;                   // TMEM lane quarter this warp may read
     const int half = (warp - 4) >> 2;          // which 128 of the 256 columns
     const int m = lq * 32 + lane;              // row of the tile
-    const int64_t base1111 = P.cls[P.ncls - 1].offset + binom_at(P.binom, 4, P.dim, 4) - 1;
     int buf = 0;
     uint32_t fph[2] = {0, 0};
     bool ok = true;
@@ -287,11 +312,6 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
     long long t_wait = 0, t_drain = 0, t_write = 0, t_fence = 0, t_bar = 0;  // debug 64: where an epilogue warp spends its time
     float acc[TN / 2];
     for (int64_t t = blockIdx.x; t < prm.ntiles && ok; t += gridDim.x) {
-      const unsigned long long tw = prm.tiles[t];
-      const int i0 = (int)(tw & 0xffff) * BJ, j0 = (int)((tw >> 16) & 0xffff) * BJ, k0 = (int)((tw >> 32) & 0xffff) * BJ,
-                l0 = (int)((tw >> 48) & 0xffff) * BL;
-      // all indices distinct and inside the tensor: positions are sums of four per-index terms (`fast`)
-      const bool fast = i0 + BJ - 1 < j0 && j0 + BJ - 1 < k0 && k0 + BJ - 1 < l0 && l0 + BL - 1 < P.dim;
       for (int pr = 0; pr < 3 && ok; ++pr) {
 #pragma unroll
         for (int c = 0; c < TN / 2; ++c) acc[c] = 0.f;
@@ -325,46 +345,27 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
         // ---- this pairing's share of the outputs: 1/6 of (G[rows|cols] + G[cols|rows])
         const float sixth = 1.0f / 6.0f;
         const long long c_w = clock64();
-        if (prm.debug & 1) {
-        } else if (fast) {
-          // positions without tables or shared memory (the tensor core and the TMA unit saturate the shared-memory pipe:
-          // an LDS of the epilogue waited ~1000 clocks there): coord = base - T4(i) - T3(j) - T2(k) - T1(l), T_r(g) = C(d-1-g, r);
-          // the row term and the term of the column's first index are computed directly, the second index steps through
-          // 16 consecutive values by finite differences.  Adds outside the launch range [begin, end) are predicated off.
+        if (!(prm.debug & 1)) {
+          // The tile's 16 x 16 x 16 x 8 outputs go to ITS OWN contiguous 128 KB slot of a scratch buffer, at
+          // L(i, j, k, l) = ((i 16 + j) 16 + k) 8 + l  -- not straight into the packed output: there the 256 (i, j) pairs of a
+          // tile sit in ~100 different 2 MB pages and every scattered add of the epilogue cost a page walk (~500 clocks per
+          // instruction: the adds took longer than the GEMMs).  In the slot the first pairing's rows (k, l) are whole
+          // 128-byte lines per warp store, the other pairings add 4 sectors per warp instruction, everything within one page
+          // and (evict-last) in L2; sym22_scatter_kernel then moves the slots to the packed layout with plain stores.
+          float* slot = prm.scratch + (size_t)t * (TM * TN);
           const int x = m >> 3, z = m & 7;
-          const int64_t dm1 = P.dim - 1;
-          const int64_t rterm = (dm1 - (l0 + z)) + (pr == 0 ? c2(dm1 - (k0 + x)) : pr == 1 ? c3(dm1 - (j0 + x)) : c4(dm1 - (i0 + x)));
-          const int64_t row_off = base1111 - prm.begin - rterm;
-          const uint64_t span = (uint64_t)(prm.end - prm.begin);
-          const int64_t ns0 = dm1 - (pr == 0 ? j0 : k0);  // n = d - 1 - g of the column's second index at w = 0
+          if (pr == 0) {  // rows (k, l), columns (i, j): L = n 128 + m
 #pragma unroll
-          for (int yy = 0; yy < TN / 32; ++yy) {
-            const int y = half * (TN / 32) + yy;
-            const int64_t tf = pr == 2 ? c3(dm1 - (j0 + y)) : c4(dm1 - (i0 + y));
-            int64_t off, d1, d2 = ns0 - 2;
-            if (pr == 0) { off = row_off - tf - c3(ns0); d1 = c2(ns0 - 1); }
-            else { off = row_off - tf - c2(ns0); d1 = ns0 - 1; }
+            for (int c = 0; c < TN / 2; ++c)
+              asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(slot + (half * (TN / 2) + c) * TM + m), "f"(acc[c] * sixth), "l"(opol) : "memory");
+          } else {
+            // pairing 1: rows (j, l), columns (i, k): L = ((y 16 + x) 16 + w) 8 + z;  pairing 2: rows (i, l), columns (j, k): L = ((x 16 + y) 16 + w) 8 + z
 #pragma unroll
-            for (int w = 0; w < 16; ++w) {
-              if ((uint64_t)off < span)
-                asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(prm.out + off), "f"(acc[yy * 16 + w] * sixth), "l"(opol) : "memory");
-              off += d1;  // T(w + 1) = T(w) - C(n_w - 1, r - 1)
-              if (pr == 0) { d1 -= d2; d2 -= 1; }
-              else d1 -= 1;
+            for (int c = 0; c < TN / 2; ++c) {
+              const int n = half * (TN / 2) + c, y = n >> 4, w = n & 15;
+              const int L = ((pr == 1 ? y * 16 + x : x * 16 + y) * 16 + w) * 8 + z;
+              asm volatile("red.global.add.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(slot + L), "f"(acc[c] * sixth), "l"(opol) : "memory");
             }
-          }
-        } else {
-          const int x = m >> 3, z = m & 7;
-#pragma unroll
-          for (int c = 0; c < TN / 2; ++c) {
-            const int n = half * (TN / 2) + c;
-            const int y = n >> 4, w = n & 15;
-            const int gl = l0 + z;
-            int gi, gj, gk;
-            if (pr == 0) { gk = k0 + x; gi = i0 + y; gj = j0 + w; }
-            else if (pr == 1) { gj = j0 + x; gi = i0 + y; gk = k0 + w; }
-            else { gi = i0 + x; gj = j0 + y; gk = k0 + w; }
-            slow_add(P, base1111, prm.begin, prm.end, prm.out, gi, gj, gk, gl, acc[c] * sixth);
           }
         }
         // a component gets its three adds from three different threads of this CTA: keep them in pairing order (fp32 adds do
@@ -491,7 +492,11 @@ int workspace_bytes(int k, int64_t dim, int64_t* out) {
   const int64_t K = contracted_count(k, dim);
   if (K < 0) return ST_ERR_INVALID;
   const int64_t Kp = round_up(std::max<int64_t>(K, 1), 32);
-  const __int128 bytes = (__int128)4 * dim * dim * Kp * 4 + 4096;
+  // control block, the four expanded operand arrays, the tile slots of one batch (at most kBatchTiles tiles of 128 KB)
+  const int64_t nbj = (dim + BJ - 1) / BJ, nbl = (dim + BL - 1) / BL;
+  const __int128 all_tiles = (__int128)nbj * nbj * nbj * nbl;
+  const __int128 slots = all_tiles < (__int128)kBatchTiles ? all_tiles : (__int128)kBatchTiles;
+  const __int128 bytes = (__int128)4 * dim * dim * Kp * 4 + 4096 + slots * (TM * TN * 4);
   if (bytes > (__int128)INT64_MAX) { set_error("workspace does not fit int64"); return ST_ERR_OVERFLOW; }
   *out = (int64_t)bytes;
   return ST_OK;
@@ -625,21 +630,34 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   for (int a = 0; a < 4 && !rc; ++a) rc = make_map(&maps[a], src[a], dim, Kp, kch, BL, BJ);      // row boxes (first: 16, l: 8)
   for (int a = 0; a < 4 && !rc; ++a) rc = make_map(&maps[4 + a], src[a], dim, Kp, kch, BJ, BJ);  // column boxes (16 x 16)
   if (rc) return rc;
-  Params prm;
-  prm.P = Pn;
-  prm.begin = begin;
-  prm.end = end;
-  prm.out = d_out;
-  prm.tiles = tl.d;
-  prm.ntiles = tl.n;
-  prm.nst = (int32_t)(Kp / kch);
-  prm.debug = g_debug;
-  prm.err = d_err;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = (int)std::min<int64_t>(tl.n, sms);
-  return kch == 32 ? launch<32>(maps, prm, grid, stream) : launch<16>(maps, prm, grid, stream);
+  float* scratch = x + 4 * n1;
+  const int64_t nbj = (dim + BJ - 1) / BJ, nbl = (dim + BL - 1) / BL;
+  const int64_t cap = std::min<int64_t>(kBatchTiles, nbj * nbj * nbj * nbl);
+  // batches of tiles: GEMM kernel into the slots, then the scatter of the slots into the packed output (same stream)
+  for (int64_t t0 = 0; t0 < tl.n; t0 += cap) {
+    Params prm;
+    prm.P = Pn;
+    prm.begin = begin;
+    prm.end = end;
+    prm.out = d_out;
+    prm.scratch = scratch;
+    prm.tiles = tl.d + t0;
+    prm.ntiles = std::min<int64_t>(cap, tl.n - t0);
+    prm.nst = (int32_t)(Kp / kch);
+    prm.debug = g_debug;
+    prm.err = d_err;
+    const int grid = (int)std::min<int64_t>(prm.ntiles, sms);
+    rc = kch == 32 ? launch<32>(maps, prm, grid, stream) : launch<16>(maps, prm, grid, stream);
+    if (rc) return rc;
+    sym22_scatter_kernel<<<(unsigned)prm.ntiles, 256, 0, stream>>>(Pn, prm.tiles, scratch, d_out, begin, end);
+    count_launch();
+    rc = check_cuda(cudaGetLastError(), "sym22_scatter_kernel");
+    if (rc) return rc;
+  }
+  return ST_OK;
 }
 
 }  // namespace s22
