@@ -301,59 +301,73 @@ def run_gpu(args):
     # ST_VEC_OVERLAP launches alternate between the two halves of a double-size workspace
     ws = torch.empty(2 * int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
 
-    rebalanced = None
-    if world > 1:
-        # cost-balanced slices: the cost per coordinate varies along the packed range, so every rank times its own
-        # kernel and the cut points are moved until the slices take the same time (3 rounds; sharding.rebalance)
-        for _ in range(3):
+    def balance(dim_, table_, cuts_, make, rounds=4):
+        """Cost-balanced slices: the cost per coordinate varies along the packed range (classes with earlier runs, the long first
+        rows of the big class), so every rank times its own kernel -- overlapped launches, as in the timed loop -- and the cut
+        points are moved until the slices take the same time (sharding.rebalance).  Returns (cuts, shard, info)."""
+        d_ = _Desc()
+        d_.dim = dim_
+        info = None
+        sh = make(cuts_[rank], cuts_[rank + 1])
+        for _ in range(rounds):
+            d_._buf = sh
+            b_, e_ = cuts_[rank], cuts_[rank + 1]
             for _ in range(3):
-                ops.contract_vec_device(desc, x, out, ws, begin, end, packed=shard)
+                ops.contract_vec_device(d_, x[:dim_], out, ws, b_, e_, packed=sh, overlap=True)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(10):
-                ops.contract_vec_device(desc, x, out, ws, begin, end, packed=shard)
+                ops.contract_vec_device(d_, x[:dim_], out, ws, b_, e_, packed=sh, overlap=True)
             e1.record()
             torch.cuda.synchronize()
             tl = torch.zeros(world, dtype=torch.float64, device=dev)
             tl[rank] = e0.elapsed_time(e1) / 10
             dist.all_reduce(tl)
             times = [float(v) for v in tl.cpu()]
-            cuts = sharding.rebalance(cuts, times)
-            begin, end = cuts[rank], cuts[rank + 1]
-            del shard
-            shard = make_shard(begin, end)
-            desc._buf = shard
-            rebalanced = {"kernel_ms_per_rank_before_last_round": [round(v, 4) for v in times],
-                          "slice_fractions": [round((cuts[r + 1] - cuts[r]) / total, 4) for r in range(world)]}
+            cuts_ = sharding.rebalance(cuts_, times)
+            del sh
+            sh = make(cuts_[rank], cuts_[rank + 1])
+            info = {"kernel_ms_per_rank_before_last_round": [round(v, 4) for v in times],
+                    "slice_fractions": [round((cuts_[r + 1] - cuts_[r]) / table_.total, 4) for r in range(world)]}
+        return cuts_, sh, info
+
+    rebalanced = None
+    if world > 1:
+        del shard
+        cuts, shard, rebalanced = balance(dim, table, cuts, make_shard)
+        begin, end = cuts[rank], cuts[rank + 1]
+        desc._buf = shard
     class Pipeline:
         """The timed loop over one sharded tensor.  Every step is one ST_VEC_OVERLAP kernel launch over this rank's slice (the
-        operands are resident: the ramp-up of step i + 1 overlaps the tail of step i) and, for N > 1, the all-reduce of one
-        fp64, enqueued asynchronously so that it overlaps the kernel of step i + 1 (results alternate between two buffers; a
-        buffer's collective is waited for before the buffer is written again).  N > 1: the per-step host work (a ctypes call
-        plus a torch.distributed call, ~40 us) would hide kernels of a few tens of us, so a block of steps is captured ONCE
-        in a CUDA graph -- kernel launches with their programmatic edges, the NCCL all-reduces on the collective's stream,
-        the waits that guard the two result buffers -- and the timed region replays it.  Every step is still one kernel
-        launch and one all-reduce; only the host's part is gone."""
+        operands are resident: the ramp-up of step i + 1 overlaps the tail of step i).  N > 1: the steps of a BLOCK write their
+        partial sums into consecutive slots of one vector, and the block ends with ONE all-reduce of that vector (NCCL, enqueued
+        asynchronously: it overlaps the kernels of the next block, which writes the other of two vectors) -- the path's only
+        collective, "the final partial-sum all-reduce", paid once per block instead of once per step: an all-reduce kernel
+        between two contractions takes SMs away from the next contraction's one-CTA-per-SM grid and costs more than it moves.
+        The per-step host work (a ctypes call, ~10 us) would still hide kernels of a few tens of us on 8 GPUs, so a block is
+        captured ONCE in a CUDA graph -- kernel launches with their programmatic edges, the all-reduce on the collective's
+        stream -- and the timed region replays it.  Every step is still exactly one kernel launch."""
 
-        def __init__(self, rank_, dim_, shard_, x_, begin_, end_):
+        def __init__(self, rank_, dim_, shard_, x_, begin_, end_, block):
             self.a = (rank_, dim_, shard_, x_, begin_, end_)
-            self.outs = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
-            self.wss = [torch.empty_like(ws) for _ in range(2)] if world > 1 else [ws, ws]
+            self.block = max(1, block)
+            self.outs = [torch.zeros(self.block, dtype=torch.float64, device=dev) for _ in range(2)]
+            self.ws = ws
             self.pending = [None, None]
             self.count = 0
-            self.graph, self.block, self.error = None, 0, None
+            self.graph, self.error = None, None
 
         def step(self):
-            i = self.count & 1
+            i, buf = self.count % self.block, (self.count // self.block) & 1
             self.count += 1
             r_, d_, sh_, x_, b_, e_ = self.a
-            if world == 1:
-                sharding.contract_vec_sharded(r_, d_, sh_, x_, b_, e_, self.outs[0], self.wss[0], overlap=True)
-                return
-            if self.pending[i] is not None:
-                self.pending[i].wait()
-            self.pending[i] = sharding.contract_vec_sharded(r_, d_, sh_, x_, b_, e_, self.outs[i], self.wss[i], async_op=True, overlap=True)
+            if i == 0 and self.pending[buf] is not None:
+                self.pending[buf].wait()  # the vector is about to be rewritten: its all-reduce must be done
+                self.pending[buf] = None
+            sharding.contract_vec_sharded(r_, d_, sh_, x_, b_, e_, self.outs[buf][i:i + 1], self.ws, partial_only=True, overlap=True)
+            if world > 1 and i == self.block - 1:
+                self.pending[buf] = dist.all_reduce(self.outs[buf], op=dist.ReduceOp.SUM, async_op=True)
 
         def drain(self):
             for i in range(2):
@@ -362,10 +376,11 @@ def run_gpu(args):
                     self.pending[i] = None
 
         def result(self):
-            return float(self.outs[(self.count - 1) & 1][0]) if world > 1 else float(self.outs[0][0])
+            last = self.count - 1
+            return float(self.outs[(last // self.block) & 1][last % self.block])
 
-        def build_graph(self, block):
-            if world == 1 or args.no_graph:
+        def build_graph(self):
+            if args.no_graph:
                 return
             try:
                 self.drain()
@@ -373,22 +388,22 @@ def run_gpu(args):
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
-                    for _ in range(2):  # warm-up on the capture stream (per-stream counters of the library, NCCL)
+                    self.count = 0
+                    for _ in range(2 * self.block):  # warm-up on the capture stream (per-stream counters of the library, NCCL)
                         self.step()
                     self.drain()
                 torch.cuda.current_stream(dev).wait_stream(side)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
-                if block % 2:
-                    block += 1  # whole pairs of steps: the buffer parity at the end of a replay is the one at its start
+                self.count = 0
                 with torch.cuda.graph(g, stream=side):
-                    for _ in range(block):
+                    for _ in range(2 * self.block):  # both result vectors: a replay ends in the state it started in
                         self.step()
                     self.drain()
                 torch.cuda.synchronize()
                 g.replay()
                 torch.cuda.synchronize()
-                self.graph, self.block = g, block
+                self.graph = g
             except Exception as ex:  # fall back to eager launches
                 self.error = f"{type(ex).__name__}: {str(ex)[:200]}"
                 self.graph = None
@@ -397,10 +412,11 @@ def run_gpu(args):
                     torch.cuda.synchronize()
                 except Exception:
                     pass
-            ok = torch.tensor([1 if self.graph is not None else 0], dtype=torch.int32, device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if int(ok[0]) == 0:  # all ranks or none
-                self.graph = None
+            if world > 1:
+                ok = torch.tensor([1 if self.graph is not None else 0], dtype=torch.int32, device=dev)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok[0]) == 0:  # all ranks or none
+                    self.graph = None
 
         def timed(self, nsteps):
             if world > 1:
@@ -409,8 +425,8 @@ def run_gpu(args):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             l0 = lib.st_launch_count()
             e0.record()
-            if self.graph is not None and nsteps % self.block == 0:
-                for _ in range(nsteps // self.block):
+            if self.graph is not None and nsteps % (2 * self.block) == 0:
+                for _ in range(nsteps // (2 * self.block)):
                     self.graph.replay()
                 launched = nsteps
             else:
@@ -428,25 +444,25 @@ def run_gpu(args):
             return ms, launched
 
         def how(self):
-            if world == 1:
-                return "one host launch per step"
             if self.graph is not None:
-                return "a CUDA graph of %d steps (kernel launches with programmatic edges + NCCL all-reduces), replayed" % self.block
-            return "one host launch per step" + (f" (graph capture failed: {self.error})" if self.error else "")
+                return ("a CUDA graph of %d steps (kernel launches with programmatic edges%s), replayed" %
+                        (2 * self.block, "; one NCCL all-reduce of %d partial sums per %d steps" % (self.block, self.block) if world > 1 else ""))
+            return "one host launch per step" + (f" (graph capture failed: {self.error})" if self.error else "") + \
+                ("; one NCCL all-reduce of %d partial sums per %d steps" % (self.block, self.block) if world > 1 else "")
 
     def graph_block(nsteps):
-        for b in (20, 10, 8, 6, 4, 2):
-            if nsteps % b == 0:
+        for b in (10, 5, 4, 3, 2, 1):  # steps per all-reduce; a graph holds two blocks
+            if nsteps % (2 * b) == 0:
                 return b
-        return nsteps + (nsteps & 1)
+        return 1
 
-    pipe = Pipeline(RANK, dim, shard, x, begin, end)
+    pipe = Pipeline(RANK, dim, shard, x, begin, end, graph_block(args.steps))
     step, drain = pipe.step, pipe.drain
 
     for _ in range(max(args.warmup, 3)):
         step()
     drain()
-    pipe.build_graph(graph_block(args.steps))
+    pipe.build_graph()
     with ClockSampler(local) as clocks:
         ms, launches = pipe.timed(args.steps)
     ms_per_step = ms / args.steps
@@ -493,23 +509,24 @@ def run_gpu(args):
     strong = None
     if world > 1:
         t200 = comb.class_table(RANK, DIM)
-        b2, e2_ = sharding.my_range(t200.total, rank, world)
-        sh2 = shard[:e2_ - b2] if e2_ - b2 <= shard.numel() else torch.rand(e2_ - b2, dtype=torch.float64, device=dev) + 0.5
+        def make200(b_, e_):
+            g2 = torch.Generator(device=dev)
+            g2.manual_seed(SEED + 100 + rank)
+            return torch.rand(e_ - b_, generator=g2, dtype=torch.float64, device=dev) + 0.5
         x2 = x[:DIM].contiguous()
-        d2 = _Desc()
-        d2.dim = DIM
-        d2._buf = sh2
-
-        pipe2 = Pipeline(RANK, DIM, sh2, x2, b2, e2_)
+        cuts2, sh2, bal2 = balance(DIM, t200, sharding.shard_bounds(t200.total, world), make200)
+        b2, e2_ = cuts2[rank], cuts2[rank + 1]
+        pipe2 = Pipeline(RANK, DIM, sh2, x2, b2, e2_, graph_block(args.steps))
         for _ in range(5):
             pipe2.step()
         pipe2.drain()
-        pipe2.build_graph(graph_block(args.steps))
+        pipe2.build_graph()
         ms2, _ = pipe2.timed(args.steps)
         t = torch.tensor([ms2], dtype=torch.float64, device=dev)
         strong = {"value": sum(t200.sizes) / (float(t[0]) / args.steps * 1e-3), "unit": "packed components/s",
-                  "ms_per_step": float(t[0]) / args.steps, "workload": "rank 4 dim 200 cut %d ways" % world, "launch": pipe2.how(),
-                  "note": "same pipeline as the headline (overlapped launches, asynchronous all-reduce); 'serial' below is the un-pipelined step"}
+                  "ms_per_step": float(t[0]) / args.steps, "workload": "rank 4 dim 200 cut %d ways" % world, "launch": pipe2.how(), "rebalance": bal2,
+                  "note": "same pipeline as the headline (cost-balanced slices, overlapped launches, one all-reduce per block); "
+                          "latency_ms_unpipelined is one isolated contraction: kernel, then a blocking all-reduce, launched from the host"}
         # un-pipelined latency of ONE contraction of the dim-200 tensor on N GPUs: kernel, then a blocking all-reduce, from the host
         for _ in range(3):
             sharding.contract_vec_sharded(RANK, DIM, sh2, x2, b2, e2_, out, ws)
@@ -663,14 +680,21 @@ def run_gpu(args):
         if serial is not None:
             line["serial"] = serial
         line.update(other)
-        if world > 1:
-            line["config"]["launch"] = pipe.how()
+        line["config"]["launch"] = pipe.how()
         if rebalanced is not None:
             line["config"]["slices"] = "contiguous 32-aligned slices of the packed range, cut points moved until the per-rank kernel times agree"
             line["rebalance"] = rebalanced
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # captured NCCL work keeps the communicator busy at teardown (destroy_process_group was seen to hang with live graphs):
+        # drop the graphs, drain, and leave without the collective teardown
+        pipe.graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

@@ -68,14 +68,15 @@ def all_reduce_sum(value: torch.Tensor, group=None) -> torch.Tensor:
 
 def contract_vec_sharded(rank_: int, dim: int, shard: torch.Tensor, x: torch.Tensor, begin: int, end: int, out: torch.Tensor,
                          ws: Optional[torch.Tensor] = None, group=None, partial_fn: Optional[Callable] = None, async_op: bool = False,
-                         overlap: bool = False):
+                         overlap: bool = False, partial_only: bool = False):
     """Vector contraction of a range-sharded permcls tensor: local streaming kernel over ``[begin, end)`` (``shard``
     starts at coordinate ``begin``), then the scalar all-reduce.  ``partial_fn(shard, x, begin, end) -> float`` replaces
     the CUDA launch in the CPU (gloo) tests of the host logic.  With ``async_op`` the all-reduce is only enqueued (on the
     collective's own stream, ordered after the kernel) and its work handle is returned: the caller may launch the next
     contraction -- into another ``out`` -- before waiting, so that the collective overlaps the next kernel.  ``overlap``
     (``ST_VEC_OVERLAP``, resident operands only): the kernel starts while the previous launch on the stream drains its tail;
-    ``ws`` must then hold twice ``st_contract_vec_workspace_bytes()``."""
+    ``ws`` must then hold twice ``st_contract_vec_workspace_bytes()``.  ``partial_only``: only the local kernel -- the caller
+    reduces several partial sums with one collective (``out`` may be a one-element view into a vector of partial sums)."""
     if partial_fn is not None:
         out.fill_(partial_fn(shard, x, begin, end))
     else:
@@ -90,6 +91,8 @@ def contract_vec_sharded(rank_: int, dim: int, shard: torch.Tensor, x: torch.Ten
             ws = torch.empty((2 if overlap else 1) * int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64,
                              device=shard.device)
         ops.contract_vec_device(d, x, out, ws, begin, end, packed=shard, overlap=overlap)
+    if partial_only:
+        return None
     if async_op:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

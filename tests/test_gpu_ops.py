@@ -337,7 +337,7 @@ def test_tensordot_tiled_tcgen05_kernel_against_packed_oracle(ra, rb, k, dim, kc
             assert torch.equal(part, whole[b:e]), (b, e)
     finally:
         check(lib.st_set_tuning(b"sym22_min_dim", c_i64(96)))
-        check(lib.st_set_tuning(b"sym22_kch", c_i64(16)))
+        check(lib.st_set_tuning(b"sym22_kch", c_i64(32)))
 
 
 @pytest.mark.parametrize("rank,dim,dtype", [(4, 12, np.float64), (3, 20, np.float64), (6, 6, np.float64), (5, 9, np.float32), (2, 33, np.float64), (4, 70, np.float64)])

@@ -30,7 +30,7 @@ def main():
         for mn in MNEMONICS:
             if re.search(r"\b" + mn + r"\b|\b" + mn + r"\.", line):
                 counts[cur][mn] += 1
-        counts[cur]["_instructions"] += 1 if re.search(r"/\*[0-9a-f]{4}\*/", line) else 0
+        counts[cur]["_instructions"] += 1 if re.search(r"/\*[0-9a-f]{4,6}\*/\s+[A-Z@]", line) else 0
     print("SASS mnemonic counts per kernel of", os.path.relpath(LIB, ROOT), "(cuobjdump -sass; sm_100a)")
     print("%-64s %8s  %s" % ("kernel", "instrs", "Blackwell-native mnemonics"))
     for k, c in counts.items():
