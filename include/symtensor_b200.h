@@ -296,6 +296,13 @@ int st_set_tuning(const char* key, int64_t value);
  * boundaries ([cta][16] stamps, then one finish stamp per warp of the grid); this copies the first n stamps of
  * the last launch to the host.  Profiling aid (tools/vec_timeline.py), not part of the reference-facing surface. */
 int st_debug_vec_timeline(unsigned long long* h_out, int64_t n);
+/* debug (host only): `count` consecutive representative multi-indices of class `cls` from position `pos` -- the first by a full
+ * unrank, the rest by the odometer step the outer kernel uses; returns the number written (rank ints each). */
+int64_t st_debug_permcls_successors(int rank, int64_t dim, int32_t cls, int64_t pos, int64_t count, int32_t* h_idx);
+/* debug (host only): the sorted multi-index of every coordinate of [begin, end) of the permcls layout (rank ints each, -1 for
+ * alignment padding) as the multiply.outer kernel's row walk hands them to its lanes (spans of `span` coordinates, batches of
+ * 32); dim <= 255; returns end - begin. */
+int64_t st_debug_rowwalk(int rank, int64_t dim, int64_t begin, int64_t end, int64_t span, int32_t* h_idx);
 /* debug (host only): the tile words p | q << 16 | r << 32 | s << 48 (index blocks 16 / 16 / 16 / 8) the tiled tensordot kernel
  * runs for the output range [begin, end) of a rank-4 result; returns their number (writes at most `cap`). */
 int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end, unsigned long long* h_out, int64_t cap);

@@ -82,6 +82,8 @@ SIGNATURES = {
     "st_set_vec_variant": (c_int, [c_int]),
     "st_set_tuning": (c_int, [ctypes.c_char_p, c_i64]),
     "st_debug_vec_timeline": (c_int, [c_vp, c_i64]),
+    "st_debug_permcls_successors": (c_i64, [c_int, c_i64, ctypes.c_int32, c_i64, c_i64, c_vp]),
+    "st_debug_rowwalk": (c_i64, [c_int, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "st_debug_sym22_tiles": (c_i64, [c_i64, c_i64, c_i64, c_vp, c_i64]),
     "st_launch_count": (c_i64, []),
 }

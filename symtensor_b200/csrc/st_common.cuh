@@ -189,6 +189,53 @@ ST_HD void flat_unrank_r(const PlanView& P, int64_t pos, int r, int32_t* s) {
   for (int k = 0; k < r; ++k) s[k] -= k;
 }
 
+// Successor of a component in its class's storage order (the sigma-index order, lexicographic in the runs' combinations, the
+// last run varying fastest): `vals` (class order) is advanced in place; false at the end of the class.  An odometer step --
+// a few dozen instructions instead of the divisions and binary searches of a full unrank -- for kernels that walk runs of
+// consecutive coordinates.  Run j is an increasing combination of the values not used by runs 0 .. j-1.
+// skip: the last `skip` values of the last run are treated as exhausted, i.e. the result is the first component of the next
+// ROW (the stretch of consecutive components that differ only in those values).
+ST_HD bool permcls_advance(const PlanView& P, const ClassDesc& C, int32_t* vals, int skip) {
+  const int32_t d = (int32_t)P.dim;
+  for (int j = C.nruns - 1; j >= 0; --j) {
+    const int s = C.run_start[j], g = C.run_len[j];
+    for (int i = g - 1 - (j == C.nruns - 1 ? skip : 0); i >= 0; --i) {
+      const int32_t a = vals[s + i];
+      int32_t avail = d - 1 - a;  // values above a that earlier runs have not taken
+      for (int u = 0; u < s; ++u) avail -= (vals[u] > a);
+      if (avail < g - i) continue;  // position i cannot move: no room for it and the positions after it
+      // advance position i, then the positions after it take the next free values
+      int32_t v = a;
+      for (int q = i; q < g; ++q) {
+        bool taken;
+        do {
+          ++v;
+          taken = false;
+          for (int u = 0; u < s; ++u) taken = taken || (vals[u] == v);
+        } while (taken);
+        vals[s + q] = v;
+      }
+      // later runs restart at their first combination: the smallest values not used before them
+      for (int jj = j + 1; jj < C.nruns; ++jj) {
+        const int s2 = C.run_start[jj], g2 = C.run_len[jj];
+        int32_t w = -1;
+        for (int q = 0; q < g2; ++q) {
+          bool taken;
+          do {
+            ++w;
+            taken = false;
+            for (int u = 0; u < s2; ++u) taken = taken || (vals[u] == w);
+          } while (taken);
+          vals[s2 + q] = w;
+        }
+      }
+      return true;
+    }
+  }
+  return false;
+}
+ST_HD bool permcls_next_vals(const PlanView& P, const ClassDesc& C, int32_t* vals) { return permcls_advance(P, C, vals, 0); }
+
 // class containing the packed coordinate c (offsets ascending); padding belongs to the class before it
 ST_HD int class_of_coord(const PlanView& P, int64_t c) {
   int lo = 0, hi = P.ncls - 1;
@@ -197,6 +244,187 @@ ST_HD int class_of_coord(const PlanView& P, int64_t c) {
     if (P.offsets[mid] <= c) lo = mid; else hi = mid - 1;
   }
   return lo;
+}
+
+// ---- row walk: a warp-uniform cursor over consecutive packed coordinates ----------------------------------------------
+// A ROW is the stretch of consecutive components of a class that differ only in the last tau = min(g, 3) values of the last
+// run (g values): those run through the increasing tau-combinations of the m values above the run's previous value that the
+// earlier runs have not taken, in lexicographic order -- C(m, tau) components, ~300 on average at rank 8 dim 40.  A warp that
+// serves 32 consecutive coordinates walks the (few) rows that cover them with uniform odometer steps (permcls_advance) and
+// every lane decodes its own component from its offset in its row: no per-component unrank of the whole multi-index.  What
+// a lane latches: the row's values in class order packed in bytes (hence dim <= 255), the previous value b, m and its offset.
+constexpr int kRowTauMax = 3;
+constexpr int kRowBinomStride = 256;  // C(n, 2) and C(n, 3) for n < 256: the lane-side table [2][256]
+
+struct RowCursor {
+  int32_t ci;        // class of `cur` (ncls: past the end)
+  int32_t off;       // position of `cur` inside its row
+  int64_t cur;       // first coordinate not handed out yet
+  int64_t cls_end;   // end of class ci's components; [cls_end, next_off) is alignment padding
+  int64_t next_off;  // first coordinate of class ci + 1
+  int32_t vals[ST_MAX_RANK];  // the row's component values in class order (the last tau: any component of the row)
+};
+
+struct RowLatch {
+  unsigned long long valsp;  // values in class order, one per byte (the tail bytes are the lane's to fill)
+  int32_t b, m, o, ci;
+  int32_t state;  // 0: not served (coordinates behind a class's padding), 1: component, 2: alignment padding
+};
+
+// per-class constants of the lane-side decode, packed: bits 0..31 the value position of every index entry (4 bits each,
+// entries beyond the rank -> 7, whose byte is 0xff whenever the rank is below 8), 32..35 tau, 36..39 the number of values,
+// 40..43 the number of values of earlier runs
+ST_HD unsigned long long row_class_info(const ClassDesc& C, int rank) {
+  unsigned long long e2v = 0;
+  int e = 0;
+  for (int v = 0; v < C.nvals; ++v)
+    for (int m = 0; m < C.mult[v]; ++m) e2v |= (unsigned long long)v << (4 * e++);
+  for (; e < 8; ++e) e2v |= 7ull << (4 * e);
+  const int g = C.nruns ? C.run_len[C.nruns - 1] : 0;
+  const int tau = g < kRowTauMax ? g : kRowTauMax;
+  (void)rank;
+  return e2v | ((unsigned long long)tau << 32) | ((unsigned long long)C.nvals << 36) | ((unsigned long long)(C.nruns ? C.run_start[C.nruns - 1] : 0) << 40);
+}
+
+ST_HD void rowcursor_enter_class(const PlanView& P, RowCursor& rc, int ci) {
+  rc.ci = ci;
+  rc.off = 0;
+  if (ci >= P.ncls) { rc.cur = rc.cls_end = rc.next_off = INT64_MAX; return; }
+  const ClassDesc& C = P.cls[ci];
+  rc.cur = C.offset;
+  rc.cls_end = C.offset + C.size;
+  rc.next_off = P.offsets[ci + 1];
+  for (int i = 0; i < C.nvals; ++i) rc.vals[i] = i;  // first component: every run takes the smallest values left
+}
+
+// the row at the cursor: previous value b of the last run (-1 if the tail is the whole run), the number m of free values
+// above it; returns the row's length C(m, tau)
+ST_HD int32_t rowcursor_row(const PlanView& P, const RowCursor& rc, int32_t* b_out, int32_t* m_out) {
+  const ClassDesc& C = P.cls[rc.ci];
+  const int s = C.run_start[C.nruns - 1], g = C.run_len[C.nruns - 1];
+  const int tau = g < kRowTauMax ? g : kRowTauMax;
+  const int32_t b = g > tau ? rc.vals[C.nvals - tau - 1] : -1;
+  int32_t m = (int32_t)P.dim - 1 - b;
+  for (int u = 0; u < s; ++u) m -= (rc.vals[u] > b);
+  *b_out = b;
+  *m_out = m;
+  return (int32_t)binom_at(P.binom, P.rank, m, tau);
+}
+
+ST_HD void rowcursor_seek(const PlanView& P, RowCursor& rc, int64_t c) {
+  const int ci = class_of_coord(P, c);
+  rowcursor_enter_class(P, rc, ci);
+  rc.cur = c;
+  if (c >= rc.cls_end) return;
+  const ClassDesc& C = P.cls[ci];
+  permcls_unrank_vals(P, C, c - C.offset, rc.vals);
+  // position inside the row: the lexicographic rank of the tail among the combinations of the free values above b
+  const int s = C.run_start[C.nruns - 1], g = C.run_len[C.nruns - 1];
+  const int tau = g < kRowTauMax ? g : kRowTauMax;
+  int32_t b, m;
+  int32_t r = rowcursor_row(P, rc, &b, &m) - 1;
+  for (int k = 0; k < tau; ++k) {
+    const int32_t v = rc.vals[C.nvals - 1 - k];
+    int32_t y = v - b - 1;  // its index among the free values above b
+    for (int u = 0; u < s; ++u) y -= (rc.vals[u] > b && rc.vals[u] < v);
+    r -= (int32_t)binom_at(P.binom, P.rank, m - 1 - y, k + 1);
+  }
+  rc.off = r;
+}
+
+ST_HD unsigned long long rowcursor_pack(const PlanView& P, const RowCursor& rc) {
+  const ClassDesc& C = P.cls[rc.ci];
+  unsigned long long p = ~0ull;
+  for (int i = 0; i < C.nvals; ++i) p = (p & ~(0xffull << (8 * i))) | ((unsigned long long)rc.vals[i] << (8 * i));
+  return p;
+}
+
+// Serve the coordinates below `batch_end`: every lane of a warp calls this with the same cursor (so the walk is uniform) and
+// its own coordinate c, and leaves with the latch of the row that holds c.  The cursor ends at batch_end (inside a row if one
+// straddles it) or at the start of a later class.
+ST_HD void rowcursor_serve(const PlanView& P, RowCursor& rc, int64_t c, int64_t batch_end, RowLatch& L) {
+  L.state = 0;
+  while (rc.cur < batch_end) {
+    if (rc.cur >= rc.cls_end) {  // alignment padding, then the next class
+      if (c >= rc.cur && c < rc.next_off) L.state = 2;
+      rowcursor_enter_class(P, rc, rc.ci + 1);
+      continue;
+    }
+    int32_t b, m;
+    const int32_t len = rowcursor_row(P, rc, &b, &m) - rc.off;  // what is left of the row
+    const int64_t left = batch_end - rc.cur;
+    const int32_t take = left < (int64_t)len ? (int32_t)left : len;
+    if (c >= rc.cur && c < rc.cur + take) {
+      L.valsp = rowcursor_pack(P, rc); L.b = b; L.m = m; L.o = rc.off + (int32_t)(c - rc.cur); L.ci = rc.ci; L.state = 1;
+    }
+    rc.cur += take;
+    if (take < len) {
+      rc.off += take;  // the row straddles the batch
+    } else {
+      rc.off = 0;
+      const ClassDesc& C = P.cls[rc.ci];
+      const int g = C.run_len[C.nruns - 1];
+      if (rc.cur < rc.cls_end) permcls_advance(P, C, rc.vals, g < kRowTauMax ? g : kRowTauMax);
+    }
+  }
+}
+
+// lane side: the sorted multi-index (8 slots, entries beyond the rank are 0xff) of the o-th component of a row.
+// info = row_class_info of the row's class; B23[(k - 2) * kRowBinomStride + n] = C(n, k) for k = 2, 3.
+ST_HD void row_component(unsigned long long valsp, int32_t b, int32_t m, int32_t o, unsigned long long info, const int32_t* B23, int32_t* K) {
+  const int tau = (int)((info >> 32) & 15), nvals = (int)((info >> 36) & 15), s = (int)((info >> 40) & 15);
+  // the earlier runs' values above b, the only ones the tail has to step over (others: out of the way)
+  int32_t used[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int32_t w = (int32_t)((valsp >> (8 * u)) & 0xffull);
+    used[u] = (u < s && w > b) ? w : 0x7fffffff;
+  }
+  int32_t prev = -1, r = o;
+#pragma unroll
+  for (int i = 0; i < kRowTauMax; ++i) {
+    if (i >= tau) break;
+    const int k = tau - i;
+    int32_t y;
+    if (k == 1) {
+      y = prev + 1 + r;
+    } else {
+      const int32_t* Bk = B23 + (k - 2) * kRowBinomStride;
+      const int32_t all = Bk[m - 1 - prev];
+      int32_t lo = prev + 1, hi = m - k;
+      while (lo < hi) {
+        const int32_t mid = (lo + hi + 1) >> 1;
+        if (all - Bk[m - mid] <= r) lo = mid; else hi = mid - 1;
+      }
+      r -= all - Bk[m - lo];
+      y = lo;
+    }
+    prev = y;
+    // the y-th free value above b
+    int32_t v = b + 1 + y;
+    if (s > 0) {
+      for (;;) {
+        int32_t cnt = 0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cnt += (used[u] <= v);
+        if (b + 1 + y + cnt == v) break;
+        v = b + 1 + y + cnt;
+      }
+    }
+    const int pos = nvals - tau + i;
+    valsp = (valsp & ~(0xffull << (8 * pos))) | ((unsigned long long)v << (8 * pos));
+  }
+  // class order -> one value per index entry -> sorted (odd-even merge sort network for 8 keys)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) K[e] = (int32_t)((valsp >> (8 * ((info >> (4 * e)) & 7))) & 0xffull);
+#define ST_CE(i, j) { const int32_t lo_ = K[i] < K[j] ? K[i] : K[j], hi_ = K[i] < K[j] ? K[j] : K[i]; K[i] = lo_; K[j] = hi_; }
+  ST_CE(0, 1) ST_CE(2, 3) ST_CE(4, 5) ST_CE(6, 7)
+  ST_CE(0, 2) ST_CE(1, 3) ST_CE(4, 6) ST_CE(5, 7)
+  ST_CE(1, 2) ST_CE(5, 6)
+  ST_CE(0, 4) ST_CE(1, 5) ST_CE(2, 6) ST_CE(3, 7)
+  ST_CE(2, 4) ST_CE(3, 5)
+  ST_CE(1, 2) ST_CE(3, 4) ST_CE(5, 6)
+#undef ST_CE
 }
 
 // packed coordinate of the permcls layout -> sorted multi-index (false for alignment padding)
@@ -247,5 +475,6 @@ void count_launch(int n = 1);
 int check_cuda(cudaError_t e, const char* what);
 // cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (device, kernel) -- the attribute is per device (st_vec.cu)
 int set_max_dynamic_smem(const void* func, int bytes);
+int sm_count();  // of the current device (st_vec.cu)
 
 }  // namespace st

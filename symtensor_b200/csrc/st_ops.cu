@@ -196,6 +196,150 @@ __global__ void __launch_bounds__(256) outer_fast_kernel(PlanView P, const T* __
   }
 }
 
+// ---- symmetrized outer product, row walk (round 2) ----------------------------------------------------------------
+// outer_fast_kernel spends ~70 % of its instructions on the per-component unrank (divisions, binary searches) and most of
+// the rest on the n - 2 integer adds per subset.  Here
+//  * a warp serves 32 CONSECUTIVE coordinates at a time (lane = coordinate: coalesced stores, neighbouring operand entries)
+//    and finds their multi-indices by walking the few rows that cover them with a warp-uniform odometer (RowCursor in
+//    st_common.cuh): one full unrank per span of kSpan coordinates instead of one per component;
+//  * the rank sums of a subset are split into the low and the high half of the sorted positions: the partial sums of the
+//    2^(n/2) half-subsets are formed once per component (registers), a subset then costs one add per operand.
+// dim <= 255 (the latched multi-index is packed in bytes, the rank-term table has a fixed row stride).
+// (A first version walked rows of ONE varying value -- ~4 components each at rank 8 dim 40, seven rows per batch -- and was
+// slower than the per-component unrank: the uniform walk costs whole warp instructions, 3,700 per batch against ~600 for
+// the 32 components' products.  With the last three values in the lanes' hands a row has ~300 components.)
+constexpr int kRowsStride = 256;  // entries per rank-term row in shared memory
+constexpr int kRowsSpan = 2048;   // coordinates per warp task (one seek each)
+
+template <typename T, int RA, int RB>
+__device__ __forceinline__ double outer_terms_split(const int32_t* __restrict__ Fs, const int32_t* K, const T* __restrict__ af,
+                                                    const T* __restrict__ bf, int base_a, int base_b) {
+  constexpr int N = RA + RB, TM = RA > RB ? RA : RB, L = N / 2, H = N - L;
+  int32_t saLo[1 << L], sbLo[1 << L], saHi[1 << H], sbHi[1 << H];
+  {
+    int32_t G[TM][L > 0 ? L : 1];
+#pragma unroll
+    for (int p = 0; p < L; ++p)
+#pragma unroll
+      for (int t = 0; t < TM; ++t) G[t][p] = Fs[t * kRowsStride + K[p]];
+#pragma unroll
+    for (unsigned lo = 0; lo < (1u << L); ++lo) {
+      const int ja = __popc(lo);
+      if (ja > RA || L - ja > RB) continue;
+      int sa = base_a, sb = base_b, ia = 0, ib = 0;
+#pragma unroll
+      for (int p = 0; p < L; ++p) {
+        if ((lo >> p) & 1u) { sa -= G[RA - 1 - ia][p]; ++ia; }
+        else { sb -= G[RB - 1 - ib][p]; ++ib; }
+      }
+      saLo[lo] = sa; sbLo[lo] = sb;
+    }
+  }
+  {
+    int32_t G[TM][H];
+#pragma unroll
+    for (int p = 0; p < H; ++p)
+#pragma unroll
+      for (int t = 0; t < TM; ++t) G[t][p] = Fs[t * kRowsStride + K[L + p]];
+#pragma unroll
+    for (unsigned hi = 0; hi < (1u << H); ++hi) {
+      const int jh = __popc(hi);
+      if (jh > RA || RA - jh > L || H - jh > RB) continue;
+      int sa = 0, sb = 0, ia = RA - jh, ib = L - (RA - jh);  // entries the low half has taken
+#pragma unroll
+      for (int p = 0; p < H; ++p) {
+        if ((hi >> p) & 1u) { sa += G[RA - 1 - ia][p]; ++ia; }
+        else { sb += G[RB - 1 - ib][p]; ++ib; }
+      }
+      saHi[hi] = sa; sbHi[hi] = sb;
+    }
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (unsigned lo = 0; lo < (1u << L); ++lo) {
+    const int ja = __popc(lo);
+    if (ja > RA || L - ja > RB) continue;
+    if (sizeof(T) == 4) {
+      float part = 0.f;  // fp32: the products of one low half-subset (at most C(H, H/2) of them) in fp32, the halves in fp64
+#pragma unroll
+      for (unsigned hi = 0; hi < (1u << H); ++hi) {
+        if (__popc(hi) != RA - ja) continue;
+        part = fmaf((float)af[saLo[lo] - saHi[hi]], (float)bf[sbLo[lo] - sbHi[hi]], part);
+      }
+      acc += (double)part;
+    } else {
+#pragma unroll
+      for (unsigned hi = 0; hi < (1u << H); ++hi) {
+        if (__popc(hi) != RA - ja) continue;
+        acc += (double)af[saLo[lo] - saHi[hi]] * (double)bf[sbLo[lo] - sbHi[hi]];
+      }
+    }
+  }
+  return acc;
+}
+
+template <typename T, int RA, int RB, bool VEC>
+__global__ void __launch_bounds__(256, 2) outer_rows_kernel(PlanView P, const T* __restrict__ af, const T* __restrict__ bf, T* __restrict__ out,
+                                                         const T* __restrict__ x, double* __restrict__ partials, int64_t begin, int64_t end,
+                                                         double inv_count) {
+  constexpr int N = RA + RB, TM = RA > RB ? RA : RB;
+  __shared__ int32_t Fs[TM * kRowsStride];
+  __shared__ int32_t B23[2 * kRowBinomStride];  // C(n, 2), C(n, 3): the lanes' decode of their offset in a row
+  __shared__ unsigned long long cinfo[32];      // row_class_info per class (a rank <= 8 has at most 22 classes)
+  __shared__ double red[32];
+  const int d = (int)P.dim;
+  for (int e = threadIdx.x; e < TM * kRowsStride; e += blockDim.x) {
+    const int tt = e / kRowsStride, v = e % kRowsStride;
+    Fs[e] = v < d ? (int32_t)binom_at(P.binom, P.rank, d - 1 + tt - v, tt + 1) : 0;
+  }
+  for (int e = threadIdx.x; e < 2 * kRowBinomStride; e += blockDim.x) {
+    const int n = e % kRowBinomStride;
+    B23[e] = e < kRowBinomStride ? n * (n - 1) / 2 : n * (n - 1) * (n - 2) / 6;
+  }
+  for (int e = threadIdx.x; e < P.ncls && e < 32; e += blockDim.x) cinfo[e] = row_class_info(P.cls[e], N);
+  __syncthreads();
+  const int base_a = (int)(binom_at(P.binom, P.rank, d + RA - 1, RA) - 1), base_b = (int)(binom_at(P.binom, P.rank, d + RB - 1, RB) - 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double total = 0.0;
+  const int64_t ntasks = (end - begin + kRowsSpan - 1) / kRowsSpan;
+  for (int64_t task = (int64_t)blockIdx.x * wpb + warp; task < ntasks; task += (int64_t)gridDim.x * wpb) {
+    const int64_t s0 = begin + task * kRowsSpan, s1 = s0 + kRowsSpan < end ? s0 + kRowsSpan : end;
+    RowCursor rc;
+    rowcursor_seek(P, rc, s0);
+    for (int64_t b = s0; b < s1; b += 32) {
+      const int64_t c = b + lane, be = b + 32 < s1 ? b + 32 : s1;
+      RowLatch R;
+      rowcursor_serve(P, rc, c, be, R);
+      if (c >= be) continue;
+      if (R.state != 1) {
+        if (!VEC) out[c - begin] = T(0);
+        continue;
+      }
+      int32_t K[8];
+      row_component(R.valsp, R.b, R.m, R.o, cinfo[R.ci], B23, K);
+      const double acc = outer_terms_split<T, RA, RB>(Fs, K, af, bf, base_a, base_b);
+      if (VEC) {
+        double w = (double)P.cls[R.ci].gamma;
+#pragma unroll
+        for (int p = 0; p < N; ++p) w *= (double)x[K[p]];
+        total += acc * inv_count * w;
+      } else {
+        out[c - begin] = (T)(acc * inv_count);
+      }
+    }
+  }
+  if (VEC) {
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) red[warp] = total;
+    __syncthreads();
+    if (warp == 0) {
+      double s = lane < wpb ? red[lane] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) partials[blockIdx.x] = s;
+    }
+  }
+}
+
 // tensordot epilogue with compile-time free ranks: C_K = inv_count * sum_S G[rank(K_S)][rank(K_S^c)] (same scheme as
 // outer_fast_kernel: rank terms from shared memory, subsets unrolled)
 template <typename T, int NA, int NB>
@@ -874,14 +1018,32 @@ static int flat_to_permcls(int rank, int64_t dim, const T* d_in, T* d_out, int64
 
 int g_gram_umma = 1;   // fp32 tensordot Gram matrix on tcgen05 (0: the CUDA-core kernel; test hook)
 int g_outer_fast = 1;  // compile-time-rank outer kernels (0: the run-time-rank kernel; test hook)
+int g_outer_rows = 1;  // ... with the warp-uniform row walk (0: one unrank per component, outer_fast_kernel; test hook)
 
 // launch the compile-time-rank kernel for (ra, rb) if there is one (ra >= rb; the symmetrized product commutes, so the
 // caller swaps the operands otherwise); false: not instantiated / operands too large for 32-bit ranks
 template <typename T, bool VEC>
 static bool launch_outer_fast(const HostPlan* hp, const PlanView& P, int ra, int rb, const T* a, const T* b, T* out, const T* x, double* partials,
-                              int64_t begin, int64_t end, int grid, cudaStream_t stream) {
+                              int64_t begin, int64_t end, int grid, cudaStream_t stream, int* used_grid = nullptr) {
+  if (used_grid) *used_grid = grid;
   if (!g_outer_fast || ra < rb || rb < 1 || ra > 4) return false;
   if (flat_size_host(hp, ra) >= 2147483647LL || hp->dim >= 2147483647LL / 8) return false;
+  if (g_outer_rows && hp->dim <= 255) {  // row walk: one warp task per kRowsSpan coordinates, as many CTAs as are resident
+    const double inv = 1.0 / binom_double(ra + rb, ra);
+    const int64_t ntasks = (end - begin + kRowsSpan - 1) / kRowsSpan;
+#define ST_OUTER_ROWS_CASE(RA, RB)                                                                                                  \
+  if (ra == RA && rb == RB) {                                                                                                       \
+    int occ = 0;                                                                                                                    \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, outer_rows_kernel<T, RA, RB, VEC>, 256, 0) != cudaSuccess || occ < 1) occ = 1; \
+    const int g = (int)std::min<int64_t>(std::min<int64_t>((ntasks + 7) / 8, (int64_t)sm_count() * occ), VEC ? grid : (1 << 30));     \
+    outer_rows_kernel<T, RA, RB, VEC><<<std::max(g, 1), 256, 0, stream>>>(P, a, b, out, x, partials, begin, end, inv);                \
+    if (used_grid) *used_grid = std::max(g, 1);                                                                                     \
+    return true;                                                                                                                    \
+  }
+    ST_OUTER_ROWS_CASE(1, 1) ST_OUTER_ROWS_CASE(2, 1) ST_OUTER_ROWS_CASE(2, 2) ST_OUTER_ROWS_CASE(3, 1) ST_OUTER_ROWS_CASE(3, 2)
+    ST_OUTER_ROWS_CASE(3, 3) ST_OUTER_ROWS_CASE(4, 1) ST_OUTER_ROWS_CASE(4, 2) ST_OUTER_ROWS_CASE(4, 3) ST_OUTER_ROWS_CASE(4, 4)
+#undef ST_OUTER_ROWS_CASE
+  }
   const size_t smem = (size_t)ra * hp->dim * sizeof(int32_t);
   if (smem > 40 * 1024) return false;
   const double inv = 1.0 / binom_double(ra + rb, ra);
@@ -927,12 +1089,12 @@ static int outer_vec(int ra, int rb, int64_t dim, const T* d_a_flat, const T* d_
   if (rc) return rc;
   if (begin < 0 || end < begin || end > P.total) { set_error("range outside the packed tensor"); return ST_ERR_INVALID; }
   if (!d_a_flat || !d_b_flat || !d_out || !d_ws || (dim > 0 && !d_x)) { set_error("null pointer"); return ST_ERR_INVALID; }
-  const int grid = std::min(grid_1d(std::max<int64_t>(end - begin, 1), 256), kOuterVecCtas);
+  int grid = std::min(grid_1d(std::max<int64_t>(end - begin, 1), 256), kOuterVecCtas);
   {
     const HostPlan* hp = get_host_plan(ra + rb, dim);
     const bool sw = ra < rb;
     if (!hp || !launch_outer_fast<T, true>(hp, P, sw ? rb : ra, sw ? ra : rb, sw ? d_b_flat : d_a_flat, sw ? d_a_flat : d_b_flat, nullptr, d_x, d_ws,
-                                           begin, end, grid, stream))
+                                           begin, end, grid, stream, &grid))
       outer_vec_kernel<T><<<grid, 256, 0, stream>>>(P, ra, rb, d_a_flat, d_b_flat, d_x, d_ws, begin, end, 1.0 / binom_double(ra + rb, ra));
   }
   if (sizeof(T) == 8) sum_partials_kernel<<<1, 256, 0, stream>>>(d_ws, grid, reinterpret_cast<double*>(d_out), nullptr);

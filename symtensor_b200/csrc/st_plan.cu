@@ -7,6 +7,7 @@
 //   SymmetricTensor.indep_size                        symtensor/base.py:833-844
 //   PosRegistry / _convert_dense_index (single index) symtensor/permcls_symtensor.py:422-479
 //   flat index_of_multicombination                    symtensor/flat_symtensor.py:39-50
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -256,6 +257,64 @@ int st_host_permcls_rank(int rank, int64_t dim, const int32_t* idx, int32_t* cls
   *cls = c;
   *pos = permcls_rank_vals(P, P.cls[c], vals);
   return ST_OK;
+}
+
+// debug / test hook (host only): `count` consecutive components of class `cls` from position `pos`, the first by a full
+// unrank, the others by odometer steps (permcls_next_vals: what the outer kernel walks its runs with); returns how many were
+// written (fewer at the end of the class)
+int64_t st_debug_permcls_successors(int rank, int64_t dim, int32_t cls, int64_t pos, int64_t count, int32_t* idx) {
+  const HostPlan* hp = get_host_plan(rank, dim);
+  if (!hp || !idx || cls < 0 || cls >= hp->ncls) return -1;
+  const PlanView P = hp->host_view();
+  const ClassDesc& C = P.cls[cls];
+  if (pos < 0 || pos >= C.size) return 0;
+  int32_t vals[ST_MAX_RANK];
+  permcls_unrank_vals(P, C, pos, vals);
+  int64_t n = 0;
+  for (;;) {
+    int o = 0;
+    for (int i = 0; i < C.nvals; ++i) for (int m = 0; m < C.mult[i]; ++m) idx[n * rank + o++] = vals[i];
+    ++n;
+    if (n >= count || !permcls_next_vals(P, C, vals)) break;
+  }
+  return n;
+}
+
+// debug / test hook (host only): the row walk the multiply.outer kernel serves its coordinates with, replayed on the CPU --
+// spans of `span` coordinates (a seek each), batches of 32 lanes, every lane with its own copy of the batch's cursor.  Writes
+// the sorted multi-index of every coordinate of [begin, end) (rank ints each; -1 for padding) and returns end - begin.
+int64_t st_debug_rowwalk(int rank, int64_t dim, int64_t begin, int64_t end, int64_t span, int32_t* idx) {
+  const HostPlan* hp = get_host_plan(rank, dim);
+  if (!hp || !idx || dim > 255 || rank > 8 || span < 1 || begin < 0 || end < begin) return -1;
+  const PlanView P = hp->host_view();
+  if (end > P.total) return -1;
+  std::vector<int32_t> B23(2 * kRowBinomStride);
+  for (int k = 2; k <= 3; ++k)
+    for (int n = 0; n < kRowBinomStride; ++n) B23[(k - 2) * kRowBinomStride + n] = k == 2 ? n * (n - 1) / 2 : n * (n - 1) * (n - 2) / 6;
+  for (int64_t s0 = begin; s0 < end; s0 += span) {
+    const int64_t s1 = std::min(end, s0 + span);
+    RowCursor rc;
+    rowcursor_seek(P, rc, s0);
+    for (int64_t b = s0; b < s1; b += 32) {
+      const int64_t be = std::min(s1, b + 32);
+      RowCursor after = rc;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int64_t c = b + lane;
+        RowCursor mine = rc;
+        RowLatch L;
+        rowcursor_serve(P, mine, c, be, L);
+        if (lane == 0) after = mine;
+        if (c >= be) continue;
+        int32_t* o = idx + (c - begin) * rank;
+        if (L.state != 1) { for (int i = 0; i < rank; ++i) o[i] = -1; continue; }
+        int32_t K[8];
+        row_component(L.valsp, L.b, L.m, L.o, row_class_info(P.cls[L.ci], rank), B23.data(), K);
+        for (int i = 0; i < rank; ++i) o[i] = K[i];
+      }
+      rc = after;
+    }
+  }
+  return end - begin;
 }
 
 int st_host_permcls_unrank(int rank, int64_t dim, int32_t cls, int64_t pos, int32_t* idx) {

@@ -727,7 +727,7 @@ unsigned long long* g_timeline = nullptr;  // debug: device buffer of kTimelineS
 static const size_t kTimelineSlots = 148 * 16 + 4096 + 4096 * 8;
 int g_ring_direct = 1;                 // ring kernel: allow the table-free pair walk (2: with vec_force_tau 2, force it)
 int64_t g_ring_table_max = 72 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
-extern int g_mat_dmma, g_outer_fast, g_gram_umma, g_sym22;  // st_ops.cu
+extern int g_mat_dmma, g_outer_fast, g_outer_rows, g_gram_umma, g_sym22;  // st_ops.cu
 extern int64_t g_sym22_min_dim;
 namespace s22 { extern int g_kch, g_debug; }  // st_sym22.cu
 int64_t g_short_segment = 1024;  // classes whose segments are shorter than this take the per-component phase (tuning knob)
@@ -897,7 +897,7 @@ static const int64_t kMaxDirTiles = (int64_t)1 << 23;  // 256 MB of directory at
 // ring kernel: strategy + ring geometry + tile size.  The slot size is the preferred one unless a class would lose
 // its best tail length to the rings' shared memory: then smaller slots are tried (small copies cost bandwidth,
 // a shorter tail costs much more).
-static int sm_count();
+int sm_count();
 static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<TailStrategy>& st, StratEntry& e) {
   const int NW = g_ring_warps, R = g_ring_slots;
   // shared memory kept away from the tables: the rings at their preferred slot size, their control structures and --
@@ -1067,7 +1067,7 @@ static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
   return ST_OK;
 }
 
-static int sm_count() {
+int sm_count() {
   static std::mutex mu;
   static std::map<int, int> counts;  // per device
   int dev = 0;
@@ -1410,6 +1410,7 @@ int st_set_tuning(const char* key, int64_t value) {
   const std::string k(key);
   if (k == "mat_dmma" && (value == 0 || value == 1)) { g_mat_dmma = (int)value; return ST_OK; }
   if (k == "outer_fast" && (value == 0 || value == 1)) { g_outer_fast = (int)value; return ST_OK; }
+  if (k == "outer_rows" && (value == 0 || value == 1)) { g_outer_rows = (int)value; return ST_OK; }
   if (k == "gram_umma" && (value == 0 || value == 1)) { g_gram_umma = (int)value; return ST_OK; }
   if (k == "sym22" && (value == 0 || value == 1)) { g_sym22 = (int)value; return ST_OK; }
   if (k == "sym22_min_dim" && value >= 1) { g_sym22_min_dim = value; return ST_OK; }

@@ -278,6 +278,45 @@ def test_outer_compile_time_rank_and_run_time_rank_kernels_agree():
         assert abs(v0 - v1) <= 1e-12 * abs(v0)
 
 
+def test_outer_row_walk_kernel_agrees_with_the_per_component_unrank_kernels():
+    """multiply.outer through the row-walk kernel (outer_rows_kernel: warp-uniform odometer over the rows that cover 32
+    consecutive coordinates, half-split subset sums) against the kernel that unranks every component (outer_fast_kernel) and
+    the run-time-rank kernel: whole tensors, ranges that begin and end mid-row / mid-class, fp64 and fp32, fused vector path."""
+    from symtensor_b200 import combinatorics as comb, ops
+    from symtensor_b200._cabi import c_i64, check, lib
+    for ra, rb, dim in [(4, 4, 7), (4, 4, 3), (2, 4, 9), (3, 3, 11), (3, 1, 40), (1, 1, 50), (4, 3, 6), (2, 2, 70), (1, 4, 12),
+                        (2, 1, 255), (4, 4, 10)]:
+        rng = np.random.default_rng(ra * 100 + rb * 10 + dim)
+        A, B = rand_packed(ra, dim, rng, "pos"), rand_packed(rb, dim, rng, "pos")
+        x = rng.uniform(0.5, 1.5, dim)
+        TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=A, device=DEV)
+        TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=B, device=DEV)
+        total = comb.class_table(ra + rb, dim).total
+        ranges = [(0, total), (total // 3 + 5, total - 7), (max(0, total // 2 - 1), min(total, total // 2 + 4099))]
+        for tdt in (torch.float64, torch.float32):
+            TAt, TBt = (TA, TB) if tdt == torch.float64 else (TA.astype(np.float32), TB.astype(np.float32))
+            outs = {}
+            for rows in (0, 1):
+                try:
+                    check(lib.st_set_tuning(b"outer_rows", c_i64(rows)))
+                    got = []
+                    for b, e in ranges:
+                        part = torch.full((e - b,), -777.0, dtype=tdt, device=DEV)
+                        ops.outer_device(TAt, TBt, part, b, e, tdt)
+                        got.append(part)
+                    outs[rows] = (got, float(ops.outer_then_contract_vec(TAt, TBt, x.astype(np.float32 if tdt == torch.float32 else np.float64))))
+                finally:
+                    check(lib.st_set_tuning(b"outer_rows", c_i64(1)))
+            for g0, g1 in zip(outs[0][0], outs[1][0]):
+                if tdt == torch.float64:
+                    assert torch.allclose(g0, g1, rtol=1e-13, atol=1e-300), (ra, rb, dim)
+                else:  # fp32 (positive data): the two kernels round the sum of the products differently
+                    assert torch.allclose(g0, g1, rtol=2e-6, atol=0), (ra, rb, dim)
+                assert torch.equal(g0 == 0, g1 == 0)  # the alignment padding
+            v0, v1 = outs[0][1], outs[1][1]
+            assert abs(v0 - v1) <= (1e-11 if tdt == torch.float64 else 2e-4) * max(abs(v0), 1e-3), (ra, rb, dim, v0, v1)
+
+
 def test_tensordot_fp32_tensor_core_gram_matches_cuda_core_gram_and_oracle():
     """fp32 tensordot: the tcgen05 (3xTF32, two-level accumulation) Gram kernel against the CUDA-core kernel and the
     fp64 oracle, including contraction lengths beyond one accumulation chain (K > 256) and K not a multiple of 4."""

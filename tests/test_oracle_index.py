@@ -128,3 +128,48 @@ def test_closed_form_equals_generator_exhaustive():
                 for p, v in enumerate(gen):
                     assert io.permcls_rank(cls, d, v) == p
                     assert io.permcls_unrank(cls, d, p) == v
+
+
+def test_odometer_successor_reproduces_the_storage_order():
+    """permcls_next_vals (the odometer step the multiply.outer kernel walks its runs of consecutive coordinates with) against
+    the oracle's enumeration of sigma-index order: every class of ranks 1..8 at small dims, from several start positions."""
+    import ctypes
+
+    from symtensor_b200._cabi import c_i64, lib
+    for rank, dim in [(1, 5), (2, 6), (3, 5), (4, 7), (5, 6), (6, 7), (8, 9), (4, 3), (6, 5)]:
+        for ci, cls in enumerate(io.perm_classes(rank)):
+            ref = io.class_repindex(cls, dim)
+            n = len(ref)
+            if n == 0:
+                continue
+            for start in sorted({0, n // 3, max(0, n - 5)}):
+                want = ref[start:start + 400]
+                buf = np.full((len(want) + 3, rank), -1, dtype=np.int32)
+                got = lib.st_debug_permcls_successors(rank, c_i64(dim), ci, c_i64(start), c_i64(len(buf)), buf.ctypes.data)
+                assert got == min(len(buf), n - start), (rank, dim, cls, start, got)
+                assert np.array_equal(buf[:min(got, len(want))], want[:got]), (rank, dim, cls, start)
+
+
+def test_row_walk_hands_every_coordinate_its_sorted_multi_index():
+    """The warp-uniform row walk of the multiply.outer kernel (RowCursor, rowcursor_serve, row_component in st_common.cuh),
+    replayed on the CPU by st_debug_rowwalk: every coordinate of the permcls layout gets the sorted multi-index the oracle's
+    enumeration of the storage order gives it, padding included, for whole tensors and for spans that start mid-row."""
+    from symtensor_b200._cabi import c_i64, lib
+    from symtensor_b200 import combinatorics as comb
+    for rank, dim in [(1, 5), (2, 6), (3, 5), (4, 7), (5, 6), (6, 7), (8, 9), (4, 3), (6, 5), (7, 4), (8, 3), (2, 40), (3, 37)]:
+        tab = comb.class_table(rank, dim)
+        want = np.full((tab.total, rank), -1, dtype=np.int32)
+        for cls, off in zip(io.perm_classes(rank), tab.offsets):
+            rep = io.class_repindex(cls, dim)
+            if len(rep):
+                want[off:off + len(rep)] = np.sort(rep, axis=1)
+        for span in (tab.total, 1024, 96, 37):
+            got = np.full((tab.total, rank), -7, dtype=np.int32)
+            n = lib.st_debug_rowwalk(rank, c_i64(dim), c_i64(0), c_i64(tab.total), c_i64(span), got.ctypes.data)
+            assert n == tab.total
+            bad = np.nonzero((got != want).any(axis=1))[0]
+            assert len(bad) == 0, (rank, dim, span, bad[:5], got[bad[:5]], want[bad[:5]])
+        b, e = tab.total // 3, tab.total - 5
+        got = np.full((e - b, rank), -7, dtype=np.int32)
+        assert lib.st_debug_rowwalk(rank, c_i64(dim), c_i64(b), c_i64(e), c_i64(200), got.ctypes.data) == e - b
+        assert np.array_equal(got, want[b:e]), (rank, dim, "range")

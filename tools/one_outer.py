@@ -10,11 +10,15 @@ import bench_configs as bc  # noqa: E402
 from symtensor_b200 import combinatorics as comb, ops  # noqa: E402
 
 frac = float(sys.argv[1]) if len(sys.argv) > 1 else 0.125
+start = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+if len(sys.argv) > 3:  # python tools/one_outer.py FRACTION START ROWS(0|1)
+    from symtensor_b200._cabi import c_i64, check, lib
+    check(lib.st_set_tuning(b"outer_rows", c_i64(int(sys.argv[3]))))
 dev = torch.device("cuda:0")
 A, B = bc.device_tensor(4, 40, 1, torch.float32, dev), bc.device_tensor(4, 40, 2, torch.float32, dev)
 af, bf = ops._flat_buffer(A, torch.float32), ops._flat_buffer(B, torch.float32)
 total = comb.class_table(8, 40).total
-b = int(total * 0.5) // 32 * 32
+b = int(total * start) // 32 * 32
 e = min(total, b + int(total * frac) // 32 * 32)
 out = torch.empty(e - b, dtype=torch.float32, device=dev)
 for _ in range(2):
