@@ -263,6 +263,7 @@ struct RowCursor {
   int64_t cls_end;   // end of class ci's components; [cls_end, next_off) is alignment padding
   int64_t next_off;  // first coordinate of class ci + 1
   int32_t vals[ST_MAX_RANK];  // the row's component values in class order (the last tau: any component of the row)
+  unsigned long long valsp;   // ... packed one per byte (0xff fill), refreshed whenever the row changes
 };
 
 struct RowLatch {
@@ -295,6 +296,7 @@ ST_HD void rowcursor_enter_class(const PlanView& P, RowCursor& rc, int ci) {
   rc.cls_end = C.offset + C.size;
   rc.next_off = P.offsets[ci + 1];
   for (int i = 0; i < C.nvals; ++i) rc.vals[i] = i;  // first component: every run takes the smallest values left
+  rc.valsp = 0x0706050403020100ull | (C.nvals < 8 ? ~0ull << (8 * C.nvals) : 0ull);
 }
 
 // the row at the cursor: previous value b of the last run (-1 if the tail is the whole run), the number m of free values
@@ -309,6 +311,13 @@ ST_HD int32_t rowcursor_row(const PlanView& P, const RowCursor& rc, int32_t* b_o
   *b_out = b;
   *m_out = m;
   return (int32_t)binom_at(P.binom, P.rank, m, tau);
+}
+
+ST_HD void rowcursor_pack(const PlanView& P, RowCursor& rc) {
+  const ClassDesc& C = P.cls[rc.ci];
+  unsigned long long p = ~0ull;
+  for (int i = 0; i < C.nvals; ++i) p = (p & ~(0xffull << (8 * i))) | ((unsigned long long)rc.vals[i] << (8 * i));
+  rc.valsp = p;
 }
 
 ST_HD void rowcursor_seek(const PlanView& P, RowCursor& rc, int64_t c) {
@@ -330,13 +339,7 @@ ST_HD void rowcursor_seek(const PlanView& P, RowCursor& rc, int64_t c) {
     r -= (int32_t)binom_at(P.binom, P.rank, m - 1 - y, k + 1);
   }
   rc.off = r;
-}
-
-ST_HD unsigned long long rowcursor_pack(const PlanView& P, const RowCursor& rc) {
-  const ClassDesc& C = P.cls[rc.ci];
-  unsigned long long p = ~0ull;
-  for (int i = 0; i < C.nvals; ++i) p = (p & ~(0xffull << (8 * i))) | ((unsigned long long)rc.vals[i] << (8 * i));
-  return p;
+  rowcursor_pack(P, rc);
 }
 
 // Serve the coordinates below `batch_end`: every lane of a warp calls this with the same cursor (so the walk is uniform) and
@@ -355,7 +358,7 @@ ST_HD void rowcursor_serve(const PlanView& P, RowCursor& rc, int64_t c, int64_t 
     const int64_t left = batch_end - rc.cur;
     const int32_t take = left < (int64_t)len ? (int32_t)left : len;
     if (c >= rc.cur && c < rc.cur + take) {
-      L.valsp = rowcursor_pack(P, rc); L.b = b; L.m = m; L.o = rc.off + (int32_t)(c - rc.cur); L.ci = rc.ci; L.state = 1;
+      L.valsp = rc.valsp; L.b = b; L.m = m; L.o = rc.off + (int32_t)(c - rc.cur); L.ci = rc.ci; L.state = 1;
     }
     rc.cur += take;
     if (take < len) {
@@ -364,7 +367,10 @@ ST_HD void rowcursor_serve(const PlanView& P, RowCursor& rc, int64_t c, int64_t 
       rc.off = 0;
       const ClassDesc& C = P.cls[rc.ci];
       const int g = C.run_len[C.nruns - 1];
-      if (rc.cur < rc.cls_end) permcls_advance(P, C, rc.vals, g < kRowTauMax ? g : kRowTauMax);
+      if (rc.cur < rc.cls_end) {
+        permcls_advance(P, C, rc.vals, g < kRowTauMax ? g : kRowTauMax);
+        rowcursor_pack(P, rc);
+      }
     }
   }
 }

@@ -1,0 +1,265 @@
+// contract_all_indices_with_matrix, fp64, dims up to 64: one step of the mode chain as a PERSISTENT producer / consumer
+// pipeline (round 2).  Reference semantics: symtensor/symalg.py:476-496 (the chain itself: st_ops.cu, contract_mat).
+//
+//   T_{k+1}[(J, j); I] = sum_a W[a, j] T_k[J; sort(a, I)],   j >= max(J)
+//
+// A work item is (J, tile of 64 consecutive I): the 64 x 64 operand S[a][i] = T_k[J][map[a][i]] is gathered from the packed
+// row of J through the step's gather map, multiplied by the columns j >= max(J) of W on the FP64 tensor pipe
+// (mma.sync.m8n8k4.f64, SASS DMMA; tcgen05 has no f64 kind) and written to the rows (J, j) of T_{k+1}, which are consecutive.
+// What the first kernel (mat_step_dmma_kernel) lost, measured per step with ncu at BASELINE config 4 (rank 6 dim 64):
+//  * the late steps are millions of small items and every CTA began with a serial unrank of J by one thread, a W tile from
+//    L2 and a cold pipeline: 28.6 ms for step 4, whose traffic is 18 GB (3 ms of HBM time);
+//  * gathers were staged through registers with two block-wide barriers per 32-deep chunk;
+//  * whole 32-column blocks were multiplied although only the columns j >= max(J) are stored (1.5 - 2.5x the DMMAs).
+// Here: CTAs are persistent (two per SM) and claim chunks of consecutive items from a global counter; W sits in shared
+// memory for the whole kernel; four PRODUCER warps walk the item sequence, read the gather map and issue 8-byte cp.async
+// gathers straight into a two-stage ring of operand tiles (completion through cp.async.mbarrier.arrive on the stage's
+// `full` barrier; invalid entries are zero-filled by the same instruction with src-size 0), one producer lane keeps J by
+// odometer steps and publishes the item descriptor; eight CONSUMER warps wait on `full`, multiply only the 8-column blocks
+// that hold a column j >= max(J) (dealt alternately to the two column groups), store, and release the stage on `empty`.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+
+#include "st_common.cuh"
+
+namespace st {
+namespace matpipe {
+
+constexpr int TI = 64;   // rows I per tile
+constexpr int TA = 64;   // contraction length held per tile (dim <= 64)
+constexpr int LD = 68;   // row stride in doubles: 4 mod 16, conflict-free fragment loads
+constexpr int NCONS = 256, NPROD = 128, NTHREADS = NCONS + NPROD;
+constexpr int CH = 8;    // items per claim
+constexpr int kSmemBytes = (3 * TA * LD) * 8 + 256;
+
+struct Desc {
+  long long i0;        // first row I of the tile
+  long long out_base;  // element offset of the output row (J, jlast) in T_{k+1}
+  int jlast;           // first stored column
+  int valid;
+};
+
+__device__ __forceinline__ uint32_t saddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// the arrival fires when every cp.async this thread has issued so far has landed (counts as one of the expected arrivals)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// bounded wait: a barrier that never completes must end the kernel with an error, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (int it = 0; it < (1 << 26); ++it) {
+    uint32_t ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2) mat_pipe_kernel(PlanView P, int k, const double* __restrict__ Tk, const double* __restrict__ W,
+                                                               double* __restrict__ Tn, long long nJ, long long nI, long long nI1,
+                                                               const int32_t* __restrict__ tbl, long long rlo, int clo, int chi,
+                                                               unsigned long long* __restrict__ counter) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* Ws = reinterpret_cast<double*>(smem_raw);            // [TA][LD]   W[a][j]
+  double* Ss = Ws + TA * LD;                                     // [2][TA][LD] S[a][i]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ss + 2 * TA * LD);  // full[2], empty[2]
+  Desc* desc = reinterpret_cast<Desc*>(bars + 4);                // [2]
+  long long* s_claim = reinterpret_cast<long long*>(desc + 2);   // [2]
+  const int d = (int)P.dim;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < TA * LD; e += NTHREADS) {
+    const int a = e / LD, j = e % LD;
+    Ws[e] = (a < d && j < d) ? W[a * d + j] : 0.0;
+  }
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(saddr(bars + b), NPROD + 1);   // full: every producer's cp.async arrival + the descriptor writer
+      mbar_init(saddr(bars + 2 + b), NCONS / 32);  // empty: one arrival per consumer warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const long long tilesI = (nI + TI - 1) / TI;
+  const long long total = nJ * tilesI;
+
+  if (tid >= NCONS) {
+    // ---------------- producers ----------------
+    const int pt = tid - NCONS;
+    int32_t J[ST_MAX_RANK];
+    long long jr_cur = -2;
+    long long w = 0, cend = 0;  // the first claim happens at n = 0
+    unsigned long long next_claim = 0;
+    int slot = 0;
+    if (pt == 0) next_claim = atomicAdd(counter, (unsigned long long)CH);
+    for (long long n = 0;; ++n) {
+      if (w == cend) {  // next chunk of items (the claim was issued a chunk ago)
+        if (pt == 0) s_claim[slot] = (long long)next_claim;
+        asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+        w = s_claim[slot];
+        cend = w + CH;
+        slot ^= 1;
+        if (pt == 0) next_claim = atomicAdd(counter, (unsigned long long)CH);
+      }
+      const int buf = (int)(n & 1);
+      mbar_wait(saddr(bars + 2 + buf), (uint32_t)(((n >> 1) & 1) ^ 1));
+      const uint32_t full = saddr(bars + buf);
+      if (w >= total) {  // no more work: tell the consumers and leave
+        if (pt == 0) {
+          desc[buf].valid = 0;
+          mbar_arrive(full);
+        }
+        cp_async_arrive(full);
+        break;
+      }
+      const long long jrel = w / tilesI, t = w - jrel * tilesI;
+      const long long jr = rlo + jrel, i0 = t * TI;
+      if (pt == 0) {
+        if (jr != jr_cur) {
+          if (jr == jr_cur + 1 && k > 0) {  // successor of a sorted k-tuple over range(d)
+            int q = k - 1;
+            while (q > 0 && J[q] == d - 1) --q;
+            const int32_t v = J[q] + 1;
+            for (int s = q; s < k; ++s) J[s] = v;
+          } else if (k > 0) {
+            flat_unrank_r(P, jr, k, J);
+          }
+          jr_cur = jr;
+        }
+        const int jl = max(k ? J[k - 1] : 0, clo);
+        J[k] = jl;
+        desc[buf].i0 = i0;
+        desc[buf].out_base = flat_rank_r(P, J, k + 1) * nI;
+        desc[buf].jlast = jl;
+        desc[buf].valid = 1;
+        mbar_arrive(full);  // (release: the descriptor is visible to whoever sees the phase complete)
+      }
+      const double* __restrict__ row = Tk + jr * nI1;
+      double* Sb = Ss + buf * TA * LD;
+      const int r = pt & 63;
+      const bool rvalid = i0 + r < nI;
+      const int32_t* __restrict__ tcol = tbl + i0 + r;
+#pragma unroll 1
+      for (int u0 = 0; u0 < TA / 2; u0 += 8) {
+        int32_t idx[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int a = 2 * (u0 + u) + (pt >> 6);
+          idx[u] = (rvalid && a < d) ? __ldg(tcol + (long long)a * nI) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int a = 2 * (u0 + u) + (pt >> 6);
+          cp_async_8(saddr(Sb + a * LD + r), idx[u] >= 0 ? (const void*)(row + idx[u]) : (const void*)Tk, idx[u] >= 0 ? 8u : 0u);
+        }
+      }
+      cp_async_arrive(full);
+      ++w;
+    }
+    return;
+  }
+
+  // ---------------- consumers ----------------
+  const int lane = tid & 31, warp = tid >> 5;
+  const int wr = warp & 3, wc = warp >> 2;  // 16-row block of the tile; column group
+  const int kend = (d + 3) & ~3;
+  const int jb1 = (chi + 7) >> 3;
+  for (long long n = 0;; ++n) {
+    const int buf = (int)(n & 1);
+    mbar_wait(saddr(bars + buf), (uint32_t)((n >> 1) & 1));
+    const Desc D = desc[buf];
+    if (!D.valid) break;
+    const double* Sb = Ss + buf * TA * LD;
+    const int jb0 = D.jlast >> 3;
+    if (D.i0 + wr * 16 < nI && jb0 + wc < jb1) {
+      double acc[2][4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      const int nblk = (jb1 - jb0 - wc + 1) >> 1;  // this warp's 8-column blocks: jb0 + wc + 2 jj, jj < nblk <= 4
+      const double* ap = Sb + (lane & 3) * LD + wr * 16 + (lane >> 2);
+      const double* bp = Ws + (lane & 3) * LD + (jb0 + wc) * 8 + (lane >> 2);
+#pragma unroll 4
+      for (int kk = 0; kk < kend; kk += 4) {
+        const double a0 = ap[kk * LD], a1 = ap[kk * LD + 8];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          if (jj < nblk) {
+            const double b = bp[kk * LD + jj * 16];
+            dmma(acc[0][jj], a0, b);
+            dmma(acc[1][jj], a1, b);
+          }
+        }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        if (jj >= nblk) break;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int col = (jb0 + wc + 2 * jj) * 8 + 2 * (lane & 3) + h;
+          if (col < D.jlast || col >= chi) continue;
+          double* orow = Tn + D.out_base + (long long)(col - D.jlast) * nI;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const long long ii = D.i0 + wr * 16 + i * 8 + (lane >> 2);
+            if (ii < nI) orow[ii] = acc[i][jj][h];
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(saddr(bars + 2 + buf));
+  }
+}
+
+// one 8-byte work counter per (device, stream), allocated once (never freed)
+static unsigned long long* counter_for(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, unsigned long long*> ctrs;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  auto key = std::make_pair(dev, stream);
+  auto it = ctrs.find(key);
+  if (it != ctrs.end()) return it->second;
+  unsigned long long* p = nullptr;
+  if (cudaMalloc(&p, 256) != cudaSuccess) return nullptr;
+  ctrs[key] = p;
+  return p;
+}
+
+// launches one step through the pipeline kernel; false (nothing enqueued): shape not covered (dim > 64, no gather map)
+bool launch_step(const PlanView& P, int k, const double* Tk, const double* W, double* Tn, int64_t nJ, int64_t nI, int64_t nI1, const int32_t* tbl,
+                 int64_t rlo, int clo, int chi, cudaStream_t stream) {
+  if (P.dim > TA || !tbl || nI < 1 || nJ < 1) return false;
+  unsigned long long* ctr = counter_for(stream);
+  if (!ctr) return false;
+  if (set_max_dynamic_smem(reinterpret_cast<const void*>(mat_pipe_kernel), kSmemBytes) != ST_OK) return false;
+  cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream);
+  const int64_t tilesI = (nI + TI - 1) / TI;
+  const int64_t chunks = (nJ * tilesI + CH - 1) / CH;
+  const int grid = (int)std::min<int64_t>(chunks, (int64_t)sm_count() * 2);
+  mat_pipe_kernel<<<grid, NTHREADS, kSmemBytes, stream>>>(P, k, Tk, W, Tn, (long long)nJ, (long long)nI, (long long)nI1, tbl, (long long)rlo, clo, chi, ctr);
+  return true;
+}
+
+}  // namespace matpipe
+}  // namespace st

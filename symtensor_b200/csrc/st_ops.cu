@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256) outer_fast_kernel(PlanView P, const T* __
 //    st_common.cuh): one full unrank per span of kSpan coordinates instead of one per component;
 //  * the rank sums of a subset are split into the low and the high half of the sorted positions: the partial sums of the
 //    2^(n/2) half-subsets are formed once per component (registers), a subset then costs one add per operand.
+// 256 threads, at most 128 registers (two CTAs per SM): (128 threads, 96 registers) and (256, 80) spill and measured 15 % slower.
 // dim <= 255 (the latched multi-index is packed in bytes, the rank-term table has a fixed row stride).
 // (A first version walked rows of ONE varying value -- ~4 components each at rank 8 dim 40, seven rows per batch -- and was
 // slower than the per-component unrank: the uniform walk costs whole warp instructions, 3,700 per batch against ~600 for
@@ -215,26 +216,8 @@ template <typename T, int RA, int RB>
 __device__ __forceinline__ double outer_terms_split(const int32_t* __restrict__ Fs, const int32_t* K, const T* __restrict__ af,
                                                     const T* __restrict__ bf, int base_a, int base_b) {
   constexpr int N = RA + RB, TM = RA > RB ? RA : RB, L = N / 2, H = N - L;
-  int32_t saLo[1 << L], sbLo[1 << L], saHi[1 << H], sbHi[1 << H];
-  {
-    int32_t G[TM][L > 0 ? L : 1];
-#pragma unroll
-    for (int p = 0; p < L; ++p)
-#pragma unroll
-      for (int t = 0; t < TM; ++t) G[t][p] = Fs[t * kRowsStride + K[p]];
-#pragma unroll
-    for (unsigned lo = 0; lo < (1u << L); ++lo) {
-      const int ja = __popc(lo);
-      if (ja > RA || L - ja > RB) continue;
-      int sa = base_a, sb = base_b, ia = 0, ib = 0;
-#pragma unroll
-      for (int p = 0; p < L; ++p) {
-        if ((lo >> p) & 1u) { sa -= G[RA - 1 - ia][p]; ++ia; }
-        else { sb -= G[RB - 1 - ib][p]; ++ib; }
-      }
-      saLo[lo] = sa; sbLo[lo] = sb;
-    }
-  }
+  // high half: the partial rank sums of all its half-subsets (registers); low half: formed per half-subset in the loop below
+  int32_t saHi[1 << H], sbHi[1 << H];
   {
     int32_t G[TM][H];
 #pragma unroll
@@ -254,32 +237,46 @@ __device__ __forceinline__ double outer_terms_split(const int32_t* __restrict__ 
       saHi[hi] = sa; sbHi[hi] = sb;
     }
   }
+  int32_t G[TM][L > 0 ? L : 1];
+#pragma unroll
+  for (int p = 0; p < L; ++p)
+#pragma unroll
+    for (int t = 0; t < TM; ++t) G[t][p] = Fs[t * kRowsStride + K[p]];
   double acc = 0.0;
 #pragma unroll
   for (unsigned lo = 0; lo < (1u << L); ++lo) {
     const int ja = __popc(lo);
     if (ja > RA || L - ja > RB) continue;
+    int saLo = base_a, sbLo = base_b;
+    {
+      int ia = 0, ib = 0;
+#pragma unroll
+      for (int p = 0; p < L; ++p) {
+        if ((lo >> p) & 1u) { saLo -= G[RA - 1 - ia][p]; ++ia; }
+        else { sbLo -= G[RB - 1 - ib][p]; ++ib; }
+      }
+    }
     if (sizeof(T) == 4) {
       float part = 0.f;  // fp32: the products of one low half-subset (at most C(H, H/2) of them) in fp32, the halves in fp64
 #pragma unroll
       for (unsigned hi = 0; hi < (1u << H); ++hi) {
         if (__popc(hi) != RA - ja) continue;
-        part = fmaf((float)af[saLo[lo] - saHi[hi]], (float)bf[sbLo[lo] - sbHi[hi]], part);
+        part = fmaf((float)af[saLo - saHi[hi]], (float)bf[sbLo - sbHi[hi]], part);
       }
       acc += (double)part;
     } else {
 #pragma unroll
       for (unsigned hi = 0; hi < (1u << H); ++hi) {
         if (__popc(hi) != RA - ja) continue;
-        acc += (double)af[saLo[lo] - saHi[hi]] * (double)bf[sbLo[lo] - sbHi[hi]];
+        acc += (double)af[saLo - saHi[hi]] * (double)bf[sbLo - sbHi[hi]];
       }
     }
   }
   return acc;
 }
 
-template <typename T, int RA, int RB, bool VEC>
-__global__ void __launch_bounds__(256, 2) outer_rows_kernel(PlanView P, const T* __restrict__ af, const T* __restrict__ bf, T* __restrict__ out,
+template <typename T, int RA, int RB, bool VEC, int THREADS = 256, int MINB = 2>
+__global__ void __launch_bounds__(THREADS, MINB) outer_rows_kernel(PlanView P, const T* __restrict__ af, const T* __restrict__ bf, T* __restrict__ out,
                                                          const T* __restrict__ x, double* __restrict__ partials, int64_t begin, int64_t end,
                                                          double inv_count) {
   constexpr int N = RA + RB, TM = RA > RB ? RA : RB;
@@ -889,27 +886,19 @@ __global__ void __launch_bounds__(256, 2) mat_step_dmma_kernel(PlanView P, int k
 __global__ void __launch_bounds__(256, 2) mat_last_dmma_kernel(PlanView P, int k, const double* __restrict__ Tk, const double* __restrict__ W,
                                                                double* __restrict__ Tn, int64_t nJ, int64_t rbase) {
   // rows [rbase, nJ) of the sorted k-tuples (global row numbers; Tk / Tn indexed globally)
-  constexpr int TI = 64, TJ = 64, TK = 32, LD = 68;
-  __shared__ double Ss[TK][LD];
+  constexpr int TI = 64, TJ = 64, TK = 32, LD = 68, LDS = 36;  // LDS = 4 mod 16: conflict-free stores (a fastest) and fragment loads
+  __shared__ double Ss[TI][LDS];  // [row][a]: the rows of Tk are contiguous in a
   __shared__ double Ws[TK][LD];
   __shared__ int64_t cJ[TI];
   __shared__ int32_t jl[TI];
-  __shared__ int32_t Jt[TI][ST_MAX_RANK];
   const int64_t d = P.dim;
   const int64_t r0 = rbase + (int64_t)blockIdx.x * TI;
   const int64_t j0 = (int64_t)blockIdx.y * TJ;
-  if (threadIdx.x == 0) {
-    flat_unrank_r(P, r0, k, Jt[0]);
-    for (int r = 1; r < TI && r0 + r < nJ; ++r) {  // successor of a sorted k-tuple over range(d)
-      int q = k - 1;
-      while (q >= 0 && Jt[r - 1][q] == d - 1) --q;
-      for (int s = 0; s < k; ++s) Jt[r][s] = s < q ? Jt[r - 1][s] : Jt[r - 1][q] + 1;
-    }
-  }
-  __syncthreads();
+  // every row's own J, in parallel (round 1 let one thread walk the 64 successors: ~5,000 clocks before the first load, the
+  // whole cost of the step at BASELINE config 4)
   if (threadIdx.x < TI && r0 + threadIdx.x < nJ) {
     int32_t Jn[ST_MAX_RANK];
-    for (int q = 0; q < k; ++q) Jn[q] = Jt[threadIdx.x][q];
+    flat_unrank_r(P, r0 + threadIdx.x, k, Jn);
     Jn[k] = (int32_t)(d - 1);
     cJ[threadIdx.x] = flat_rank_r(P, Jn, k + 1);
     jl[threadIdx.x] = k ? Jn[k - 1] : 0;
@@ -924,8 +913,8 @@ __global__ void __launch_bounds__(256, 2) mat_last_dmma_kernel(PlanView P, int k
   for (int64_t a0 = 0; a0 < d; a0 += TK) {
     __syncthreads();
     for (int e = threadIdx.x; e < TI * TK; e += 256) {
-      const int aa = e % TK, r = e / TK;  // a fastest: the rows of Tk are contiguous in a
-      Ss[aa][r] = (r0 + r < nJ && a0 + aa < d) ? Tk[(r0 + r) * d + a0 + aa] : 0.0;
+      const int aa = e % TK, r = e / TK;
+      Ss[r][aa] = (r0 + r < nJ && a0 + aa < d) ? Tk[(r0 + r) * d + a0 + aa] : 0.0;
     }
     for (int e = threadIdx.x; e < TJ * TK; e += 256) {
       const int c = e % TJ, aa = e / TJ;
@@ -936,7 +925,7 @@ __global__ void __launch_bounds__(256, 2) mat_last_dmma_kernel(PlanView P, int k
     for (int kk = 0; kk < TK; kk += 4) {
       double af[2], bf[4];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) af[i] = Ss[kk + (lane & 3)][wr * 16 + i * 8 + (lane >> 2)];
+      for (int i = 0; i < 2; ++i) af[i] = Ss[wr * 16 + i * 8 + (lane >> 2)][kk + (lane & 3)];
 #pragma unroll
       for (int j = 0; j < 4; ++j) bf[j] = Ws[kk + (lane & 3)][wc * 32 + j * 8 + (lane >> 2)];
 #pragma unroll
@@ -1031,18 +1020,22 @@ static bool launch_outer_fast(const HostPlan* hp, const PlanView& P, int ra, int
   if (g_outer_rows && hp->dim <= 255) {  // row walk: one warp task per kRowsSpan coordinates, as many CTAs as are resident
     const double inv = 1.0 / binom_double(ra + rb, ra);
     const int64_t ntasks = (end - begin + kRowsSpan - 1) / kRowsSpan;
-#define ST_OUTER_ROWS_CASE(RA, RB)                                                                                                  \
-  if (ra == RA && rb == RB) {                                                                                                       \
+#define ST_OUTER_ROWS_LAUNCH(KERNEL, THREADS)                                                                                        \
+  {                                                                                                                                 \
     int occ = 0;                                                                                                                    \
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, outer_rows_kernel<T, RA, RB, VEC>, 256, 0) != cudaSuccess || occ < 1) occ = 1; \
-    const int g = (int)std::min<int64_t>(std::min<int64_t>((ntasks + 7) / 8, (int64_t)sm_count() * occ), VEC ? grid : (1 << 30));     \
-    outer_rows_kernel<T, RA, RB, VEC><<<std::max(g, 1), 256, 0, stream>>>(P, a, b, out, x, partials, begin, end, inv);                \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL, THREADS, 0) != cudaSuccess || occ < 1) occ = 1;                   \
+    const int wpb = THREADS / 32;                                                                                                   \
+    const int g = (int)std::min<int64_t>(std::min<int64_t>((ntasks + wpb - 1) / wpb, (int64_t)sm_count() * occ), VEC ? grid : (1 << 30)); \
+    KERNEL<<<std::max(g, 1), THREADS, 0, stream>>>(P, a, b, out, x, partials, begin, end, inv);                                       \
     if (used_grid) *used_grid = std::max(g, 1);                                                                                     \
     return true;                                                                                                                    \
   }
+#define ST_OUTER_ROWS_CASE(RA, RB) \
+  if (ra == RA && rb == RB) ST_OUTER_ROWS_LAUNCH((outer_rows_kernel<T, RA, RB, VEC>), 256)
     ST_OUTER_ROWS_CASE(1, 1) ST_OUTER_ROWS_CASE(2, 1) ST_OUTER_ROWS_CASE(2, 2) ST_OUTER_ROWS_CASE(3, 1) ST_OUTER_ROWS_CASE(3, 2)
     ST_OUTER_ROWS_CASE(3, 3) ST_OUTER_ROWS_CASE(4, 1) ST_OUTER_ROWS_CASE(4, 2) ST_OUTER_ROWS_CASE(4, 3) ST_OUTER_ROWS_CASE(4, 4)
 #undef ST_OUTER_ROWS_CASE
+#undef ST_OUTER_ROWS_LAUNCH
   }
   const size_t smem = (size_t)ra * hp->dim * sizeof(int32_t);
   if (smem > 40 * 1024) return false;
@@ -1206,6 +1199,13 @@ static int64_t mat_range_elems(const HostPlan* hp, int rank, int64_t jlo, int64_
   return maxT;
 }
 
+// st_mat.cu: persistent producer / consumer pipeline for one step (fp64, dim <= 64, gather map present)
+namespace matpipe {
+bool launch_step(const PlanView& P, int k, const double* Tk, const double* W, double* Tn, int64_t nJ, int64_t nI, int64_t nI1, const int32_t* tbl,
+                 int64_t rlo, int clo, int chi, cudaStream_t stream);
+}
+int g_mat_pipe = 1;  // (0: the first DMMA kernel for every step; test hook "mat_pipe")
+
 // C = (W^T)^{(x) r} . A restricted to the output components whose FIRST (smallest) mode j1 lies in [jlo, jhi): the flat
 // range [rows_below(r, jlo), rows_below(r, jhi)) of the output, written to d_out_slice (which starts at that position).
 // Every intermediate T_k of the chain shards with it (rows J whose first element is in the range), so a GPU of a
@@ -1256,8 +1256,10 @@ static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, 
       } else if (tb > 0) {
         mat_index_kernel<<<(unsigned)((nI + 255) / 256), 256, 0, stream>>>(P, m, nI, tbl);
         count_launch();
-        mat_step_dmma_kernel<true><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
-                                                              reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, NT, rlo, clo, chi);
+        if (!g_mat_pipe || !matpipe::launch_step(P, k, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
+                                                 reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, rlo, clo, chi, stream))
+          mat_step_dmma_kernel<true><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
+                                                                reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, NT, rlo, clo, chi);
       } else {
         mat_step_dmma_kernel<false><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
                                                                reinterpret_cast<double*>(dst), nJ, nI, nI1, nullptr, NT, rlo, clo, chi);

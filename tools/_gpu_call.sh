@@ -1,5 +1,4 @@
-python -m pytest tests/test_gpu_ops.py tests/test_gpu_configs.py -x -q -m gpu -k "outer or config5" > gpurun_out/r2b_pytest_outer.log 2>&1; tail -5 gpurun_out/r2b_pytest_outer.log
-for rows in 1; do python tools/one_outer.py 0.125 0.5 $rows; python tools/one_outer.py 0.5 0.0 $rows; python tools/one_outer.py 0.5 0.5 $rows; done > gpurun_out/r2b_outer_plain.log 2>&1
-cat gpurun_out/r2b_outer_plain.log
-ncu --set full --import-source on --clock-control none -k regex:outer_rows -c 1 -s 2 -o gpurun_out/r2b_outer_rows2 python tools/one_outer.py 0.125 0.5 1 > gpurun_out/r2b_outer_ncu.log 2>&1
-tail -3 gpurun_out/r2b_outer_ncu.log
+timeout 600 python -m pytest tests/test_gpu_ops.py tests/test_gpu_configs.py -x -q -m gpu -k "matrix or config4" > gpurun_out/r2b_pytest_mat.log 2>&1; tail -5 gpurun_out/r2b_pytest_mat.log
+timeout 300 python tools/bench_ops.py mat > gpurun_out/r2b_mat_plain.log 2>&1; tail -2 gpurun_out/r2b_mat_plain.log
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none -k regex:mat_ -c 12 --csv --log-file gpurun_out/r2b_mat_launches2.csv python tools/bench_ops.py mat > gpurun_out/r2b_mat_ncu.log 2>&1
+tail -2 gpurun_out/r2b_mat_ncu.log
