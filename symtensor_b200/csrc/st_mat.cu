@@ -12,11 +12,14 @@
 //  * gathers were staged through registers with two block-wide barriers per 32-deep chunk;
 //  * whole 32-column blocks were multiplied although only the columns j >= max(J) are stored (1.5 - 2.5x the DMMAs).
 // Here: CTAs are persistent (two per SM) and claim chunks of consecutive items from a global counter; W sits in shared
-// memory for the whole kernel; four PRODUCER warps walk the item sequence, read the gather map and issue 8-byte cp.async
-// gathers straight into a two-stage ring of operand tiles (completion through cp.async.mbarrier.arrive on the stage's
-// `full` barrier; invalid entries are zero-filled by the same instruction with src-size 0), one producer lane keeps J by
-// odometer steps and publishes the item descriptor; eight CONSUMER warps wait on `full`, multiply only the 8-column blocks
-// that hold a column j >= max(J) (dealt alternately to the two column groups), store, and release the stage on `empty`.
+// memory for the whole kernel; four PRODUCER warps walk the item sequence, read the gather map (a tile ahead, into registers)
+// and issue 8-byte cp.async gathers straight into a two-stage ring of operand tiles (completion through
+// cp.async.mbarrier.arrive on the stage's `full` barrier; invalid entries are zero-filled by the same instruction with
+// src-size 0), one producer lane keeps J by odometer steps and publishes the item descriptor; eight CONSUMER warps wait on
+// `full`, multiply only the 8-column blocks that hold a column j >= max(J) (dealt alternately to the two column groups of
+// warps; a branch per block count -- a predicated-off DMMA still takes its 16 cycles of the pipe), store, and release the
+// stage on `empty`.  The shape is a template of the constants below: one CTA per SM with a five-stage ring, sixteen consumer
+// and eight producer warps (NGROUP 2, NPROD 256, STAGES 5) measured SLOWER (105 ms against 83 ms for the whole chain).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,9 +35,12 @@ namespace matpipe {
 constexpr int TI = 64;   // rows I per tile
 constexpr int TA = 64;   // contraction length held per tile (dim <= 64)
 constexpr int LD = 68;   // row stride in doubles: 4 mod 16, conflict-free fragment loads
-constexpr int NCONS = 256, NPROD = 128, NTHREADS = NCONS + NPROD;
-constexpr int CH = 8;    // items per claim
-constexpr int kSmemBytes = (3 * TA * LD) * 8 + 256;
+constexpr int NGROUP = 1;                      // consumer groups of 8 warps: group g multiplies the items n = g (mod NGROUP) of the CTA
+constexpr int NCONS = 256 * NGROUP, NPROD = 128, NTHREADS = NCONS + NPROD;
+constexpr int STAGES = 2;                      // operand tiles in the ring (two CTAs per SM: W + 2 tiles = 104 KB each)
+constexpr int CTAS_PER_SM = 2;
+constexpr int CH = 8;                          // items per claim
+constexpr int kSmemBytes = ((1 + STAGES) * TA * LD) * 8 + 512;
 
 struct Desc {
   long long i0;        // first row I of the tile
@@ -73,16 +79,48 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(NTHREADS, 2) mat_pipe_kernel(PlanView P, int k, const double* __restrict__ Tk, const double* __restrict__ W,
+// one warp's 16 rows x NB 8-column blocks of a tile: NB x 2 accumulators over the whole contraction, then the store.
+// Accumulator (i, jj) holds rows i * 8 + lane / 4, columns col0 + 16 jj + {0, 1} of the warp's blocks.
+template <int NB>
+__device__ __forceinline__ void tile_mma(const double* __restrict__ ap, const double* __restrict__ bp, int kend, double* __restrict__ obase, long long nI,
+                                         int col0, int jlast, int chi, int rows_left) {
+  double acc[2][NB][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < NB; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll 4
+  for (int kk = 0; kk < kend; kk += 4) {
+    const double a0 = ap[kk * LD], a1 = ap[kk * LD + 8];
+#pragma unroll
+    for (int jj = 0; jj < NB; ++jj) {
+      const double b = bp[kk * LD + jj * 16];
+      dmma(acc[0][jj], a0, b);
+      dmma(acc[1][jj], a1, b);
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < NB; ++jj)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int col = col0 + 16 * jj + h;
+      if (col < jlast || col >= chi) continue;
+      double* orow = obase + (long long)(16 * jj + h) * nI;
+      if (rows_left > 0) orow[0] = acc[0][jj][h];
+      if (rows_left > 8) orow[8] = acc[1][jj][h];
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mat_pipe_kernel(PlanView P, int k, const double* __restrict__ Tk, const double* __restrict__ W,
                                                                double* __restrict__ Tn, long long nJ, long long nI, long long nI1,
                                                                const int32_t* __restrict__ tbl, long long rlo, int clo, int chi,
                                                                unsigned long long* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* Ws = reinterpret_cast<double*>(smem_raw);            // [TA][LD]   W[a][j]
-  double* Ss = Ws + TA * LD;                                     // [2][TA][LD] S[a][i]
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ss + 2 * TA * LD);  // full[2], empty[2]
-  Desc* desc = reinterpret_cast<Desc*>(bars + 4);                // [2]
-  long long* s_claim = reinterpret_cast<long long*>(desc + 2);   // [2]
+  double* Ss = Ws + TA * LD;                                     // [STAGES][TA][LD] S[a][i]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ss + STAGES * TA * LD);  // full[STAGES], empty[STAGES]
+  Desc* desc = reinterpret_cast<Desc*>(bars + 2 * STAGES);       // [STAGES]
+  long long* s_claim = reinterpret_cast<long long*>(desc + STAGES);  // [2]
   const int d = (int)P.dim;
   const int tid = threadIdx.x;
   for (int e = tid; e < TA * LD; e += NTHREADS) {
@@ -90,9 +128,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) mat_pipe_kernel(PlanView P, int k
     Ws[e] = (a < d && j < d) ? W[a * d + j] : 0.0;
   }
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < STAGES; ++b) {
       mbar_init(saddr(bars + b), NPROD + 1);   // full: every producer's cp.async arrival + the descriptor writer
-      mbar_init(saddr(bars + 2 + b), NCONS / 32);  // empty: one arrival per consumer warp
+      mbar_init(saddr(bars + STAGES + b), 8);  // empty: one arrival per warp of the group that multiplied the tile
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -105,12 +143,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) mat_pipe_kernel(PlanView P, int k
     const int pt = tid - NCONS;
     int32_t J[ST_MAX_RANK];
     long long jr_cur = -2;
-    long long w = 0, cend = 0;  // the first claim happens at n = 0
+    long long w = 0, cend = 0;  // the first claim happens at the first item
     unsigned long long next_claim = 0;
     int slot = 0;
     if (pt == 0) next_claim = atomicAdd(counter, (unsigned long long)CH);
-    for (long long n = 0;; ++n) {
-      if (w == cend) {  // next chunk of items (the claim was issued a chunk ago)
+    constexpr int AQ = NPROD / 64, PER = TA / AQ;  // a thread gathers the rows a = AQ u + aq of its column
+    const int r = pt & 63, aq = pt >> 6;
+    // the next item of this CTA's sequence (all producers compute the same sequence)
+    auto next_item = [&]() {
+      if (w == cend) {  // next chunk of items (its claim was issued a chunk ago)
         if (pt == 0) s_claim[slot] = (long long)next_claim;
         asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
         w = s_claim[slot];
@@ -118,19 +159,46 @@ __global__ void __launch_bounds__(NTHREADS, 2) mat_pipe_kernel(PlanView P, int k
         slot ^= 1;
         if (pt == 0) next_claim = atomicAdd(counter, (unsigned long long)CH);
       }
-      const int buf = (int)(n & 1);
-      mbar_wait(saddr(bars + 2 + buf), (uint32_t)(((n >> 1) & 1) ^ 1));
+    };
+    // gather-map entries of an item's column: issued a whole tile ahead, so that their latency overlaps the wait for the stage
+    int32_t idx[PER];
+    auto load_idx = [&](long long wi) {
+      if (wi >= total) return;
+      const long long jrel = wi / tilesI, i0 = (wi - jrel * tilesI) * TI;
+      const bool rvalid = i0 + r < nI;
+      const int32_t* __restrict__ tcol = tbl + i0 + r;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int a = AQ * u + aq;
+        idx[u] = (rvalid && a < d) ? __ldg(tcol + (long long)a * nI) : -1;
+      }
+    };
+    next_item();
+    load_idx(w);
+    int n_end = 0;
+    for (long long n = 0;; ++n) {
+      const int buf = (int)(n % STAGES);
+      mbar_wait(saddr(bars + STAGES + buf), (uint32_t)(((n / STAGES) & 1) ^ 1));
       const uint32_t full = saddr(bars + buf);
-      if (w >= total) {  // no more work: tell the consumers and leave
+      if (w >= total) {  // no more work: tell every consumer group (one empty item each) and leave
         if (pt == 0) {
           desc[buf].valid = 0;
           mbar_arrive(full);
         }
         cp_async_arrive(full);
-        break;
+        if (++n_end == NGROUP) break;
+        continue;
       }
       const long long jrel = w / tilesI, t = w - jrel * tilesI;
       const long long jr = rlo + jrel, i0 = t * TI;
+      const double* __restrict__ row = Tk + jr * nI1;
+      double* Sb = Ss + buf * TA * LD;
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int a = AQ * u + aq;
+        cp_async_8(saddr(Sb + a * LD + r), idx[u] >= 0 ? (const void*)(row + idx[u]) : (const void*)Tk, idx[u] >= 0 ? 8u : 0u);
+      }
+      cp_async_arrive(full);
       if (pt == 0) {
         if (jr != jr_cur) {
           if (jr == jr_cur + 1 && k > 0) {  // successor of a sorted k-tuple over range(d)
@@ -151,82 +219,42 @@ __global__ void __launch_bounds__(NTHREADS, 2) mat_pipe_kernel(PlanView P, int k
         desc[buf].valid = 1;
         mbar_arrive(full);  // (release: the descriptor is visible to whoever sees the phase complete)
       }
-      const double* __restrict__ row = Tk + jr * nI1;
-      double* Sb = Ss + buf * TA * LD;
-      const int r = pt & 63;
-      const bool rvalid = i0 + r < nI;
-      const int32_t* __restrict__ tcol = tbl + i0 + r;
-#pragma unroll 1
-      for (int u0 = 0; u0 < TA / 2; u0 += 8) {
-        int32_t idx[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int a = 2 * (u0 + u) + (pt >> 6);
-          idx[u] = (rvalid && a < d) ? __ldg(tcol + (long long)a * nI) : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int a = 2 * (u0 + u) + (pt >> 6);
-          cp_async_8(saddr(Sb + a * LD + r), idx[u] >= 0 ? (const void*)(row + idx[u]) : (const void*)Tk, idx[u] >= 0 ? 8u : 0u);
-        }
-      }
-      cp_async_arrive(full);
       ++w;
+      next_item();
+      load_idx(w);
     }
     return;
   }
 
   // ---------------- consumers ----------------
-  const int lane = tid & 31, warp = tid >> 5;
+  const int lane = tid & 31, warp = (tid >> 5) & 7, group = tid >> 8;
   const int wr = warp & 3, wc = warp >> 2;  // 16-row block of the tile; column group
   const int kend = (d + 3) & ~3;
   const int jb1 = (chi + 7) >> 3;
-  for (long long n = 0;; ++n) {
-    const int buf = (int)(n & 1);
-    mbar_wait(saddr(bars + buf), (uint32_t)((n >> 1) & 1));
+  for (long long n = group;; n += NGROUP) {
+    const int buf = (int)(n % STAGES);
+    mbar_wait(saddr(bars + buf), (uint32_t)((n / STAGES) & 1));
     const Desc D = desc[buf];
     if (!D.valid) break;
     const double* Sb = Ss + buf * TA * LD;
     const int jb0 = D.jlast >> 3;
     if (D.i0 + wr * 16 < nI && jb0 + wc < jb1) {
-      double acc[2][4][2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
       const int nblk = (jb1 - jb0 - wc + 1) >> 1;  // this warp's 8-column blocks: jb0 + wc + 2 jj, jj < nblk <= 4
       const double* ap = Sb + (lane & 3) * LD + wr * 16 + (lane >> 2);
       const double* bp = Ws + (lane & 3) * LD + (jb0 + wc) * 8 + (lane >> 2);
-#pragma unroll 4
-      for (int kk = 0; kk < kend; kk += 4) {
-        const double a0 = ap[kk * LD], a1 = ap[kk * LD + 8];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          if (jj < nblk) {
-            const double b = bp[kk * LD + jj * 16];
-            dmma(acc[0][jj], a0, b);
-            dmma(acc[1][jj], a1, b);
-          }
-        }
-      }
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        if (jj >= nblk) break;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int col = (jb0 + wc + 2 * jj) * 8 + 2 * (lane & 3) + h;
-          if (col < D.jlast || col >= chi) continue;
-          double* orow = Tn + D.out_base + (long long)(col - D.jlast) * nI;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const long long ii = D.i0 + wr * 16 + i * 8 + (lane >> 2);
-            if (ii < nI) orow[ii] = acc[i][jj][h];
-          }
-        }
+      double* obase = Tn + D.out_base + (long long)((jb0 + wc) * 8 + 2 * (lane & 3) - D.jlast) * nI + D.i0 + wr * 16 + (lane >> 2);
+      const int col0 = (jb0 + wc) * 8 + 2 * (lane & 3);
+      const int rows_left = (int)min((long long)16, nI - D.i0 - wr * 16) - (lane >> 2);  // rows i * 8 + lane / 4 below it are stored
+      // (a branch per block count, not a predicate per DMMA: a predicated-off DMMA still takes its 16 cycles of the pipe)
+      switch (nblk) {
+        case 1: tile_mma<1>(ap, bp, kend, obase, nI, col0, D.jlast, chi, rows_left); break;
+        case 2: tile_mma<2>(ap, bp, kend, obase, nI, col0, D.jlast, chi, rows_left); break;
+        case 3: tile_mma<3>(ap, bp, kend, obase, nI, col0, D.jlast, chi, rows_left); break;
+        default: tile_mma<4>(ap, bp, kend, obase, nI, col0, D.jlast, chi, rows_left); break;
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(saddr(bars + 2 + buf));
+    if (lane == 0) mbar_arrive(saddr(bars + STAGES + buf));
   }
 }
 
@@ -256,7 +284,7 @@ bool launch_step(const PlanView& P, int k, const double* Tk, const double* W, do
   cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream);
   const int64_t tilesI = (nI + TI - 1) / TI;
   const int64_t chunks = (nJ * tilesI + CH - 1) / CH;
-  const int grid = (int)std::min<int64_t>(chunks, (int64_t)sm_count() * 2);
+  const int grid = (int)std::min<int64_t>(chunks, (int64_t)sm_count() * CTAS_PER_SM);
   mat_pipe_kernel<<<grid, NTHREADS, kSmemBytes, stream>>>(P, k, Tk, W, Tn, (long long)nJ, (long long)nI, (long long)nI1, tbl, (long long)rlo, clo, chi, ctr);
   return true;
 }

@@ -44,6 +44,56 @@ __global__ void flat_to_permcls_kernel(PlanView P, const T* __restrict__ in, T* 
   }
 }
 
+// Row-walk converters (round 2; ranks <= 8, dims <= 255): a warp serves 32 consecutive permcls coordinates, finds their
+// sorted multi-indices with the warp-uniform odometer of st_common.cuh (RowCursor) and ranks them in the flat layout with
+// per-entry terms from shared memory -- ~150 instructions per component instead of the ~2,500 of an unrank / classify /
+// rank round trip (12 ms and 8 ms either side of contract_all_indices_with_matrix at BASELINE config 4).
+constexpr int kConvSpan = 2048;
+
+template <typename T, bool TO_FLAT>
+__global__ void __launch_bounds__(256) rowwalk_convert_kernel(PlanView P, const T* __restrict__ in, T* __restrict__ out, int64_t begin, int64_t end) {
+  __shared__ int64_t Fl[8 * 256];   // Fl[t][v] = C(d - 1 + t - v, t + 1): the flat rank is C(d+r-1, r) - 1 - sum_p Fl[r-1-p][K[p]]
+  __shared__ int32_t B23[2 * kRowBinomStride];
+  __shared__ unsigned long long cinfo[32];
+  const int d = (int)P.dim, rk = P.rank;
+  for (int e = threadIdx.x; e < 8 * 256; e += blockDim.x) {
+    const int tt = e >> 8, v = e & 255;
+    Fl[e] = (v < d && tt < rk) ? binom_at(P.binom, P.rank, d - 1 + tt - v, tt + 1) : 0;
+  }
+  for (int e = threadIdx.x; e < 2 * kRowBinomStride; e += blockDim.x) {
+    const int n = e % kRowBinomStride;
+    B23[e] = e < kRowBinomStride ? n * (n - 1) / 2 : n * (n - 1) * (n - 2) / 6;
+  }
+  for (int e = threadIdx.x; e < P.ncls && e < 32; e += blockDim.x) cinfo[e] = row_class_info(P.cls[e], rk);
+  __syncthreads();
+  const int64_t base = P.flat_size - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int64_t ntasks = (end - begin + kConvSpan - 1) / kConvSpan;
+  for (int64_t task = (int64_t)blockIdx.x * wpb + warp; task < ntasks; task += (int64_t)gridDim.x * wpb) {
+    const int64_t s0 = begin + task * kConvSpan, s1 = s0 + kConvSpan < end ? s0 + kConvSpan : end;
+    RowCursor rc;
+    rowcursor_seek(P, rc, s0);
+    for (int64_t b = s0; b < s1; b += 32) {
+      const int64_t c = b + lane, be = b + 32 < s1 ? b + 32 : s1;
+      RowLatch R;
+      rowcursor_serve(P, rc, c, be, R);
+      if (c >= be) continue;
+      if (R.state != 1) {
+        if (!TO_FLAT) out[c - begin] = T(0);
+        continue;
+      }
+      int32_t K[8];
+      row_component(R.valsp, R.b, R.m, R.o, cinfo[R.ci], B23, K);
+      int64_t pos = base;
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if (p < rk) pos -= Fl[((rk - 1 - p) << 8) + K[p]];
+      if (TO_FLAT) out[pos] = in[c];
+      else out[c - begin] = in[pos];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // symmetrized outer product: one thread per packed output component, C(n, ra) gathered products
 // ------------------------------------------------------------------------------------------------------
@@ -749,13 +799,26 @@ ST_HD int64_t merged_rank(const PlanView& P, const int32_t* I, int m, int64_t a)
   return pos;
 }
 
-// gather map of one step, built once and shared by all J: tbl[a * nI + i] = flat rank of sort(a, I_i)
+// gather map of one step, built once and shared by all J: tbl[a * nI + i] = flat rank of sort(a, I_i).
+// With F[t][v] = C(d-1+t-v, t+1) the rank of the merged tuple is  base - PS[p] - F[m-p][a],  p = #{q: I[q] <= a},
+// PS[p] = sum_{q<p} F[m-q][I[q]] + sum_{q>=p} F[m-1-q][I[q]]:  one unrank of I, then a few instructions per a (p only grows).
 __global__ void __launch_bounds__(256) mat_index_kernel(PlanView P, int m, int64_t nI, int32_t* __restrict__ tbl) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nI) return;
   int32_t I[ST_MAX_RANK];
   flat_unrank_r(P, i, m, I);
-  for (int64_t a = 0; a < P.dim; ++a) tbl[a * nI + i] = (int32_t)merged_rank(P, I, m, a);
+  const int64_t d = P.dim;
+  const int64_t base = binom_at(P.binom, P.rank, d + m, m + 1) - 1;
+  int64_t ps = 0;
+  for (int q = 0; q < m; ++q) ps += binom_at(P.binom, P.rank, d - 1 + (m - 1 - q) - I[q], m - q);
+  int p = 0;
+  for (int64_t a = 0; a < d; ++a) {
+    while (p < m && I[p] <= a) {
+      ps += binom_at(P.binom, P.rank, d - 1 + (m - p) - I[p], m - p + 1) - binom_at(P.binom, P.rank, d - 1 + (m - 1 - p) - I[p], m - p);
+      ++p;
+    }
+    tbl[a * nI + i] = (int32_t)(base - ps - binom_at(P.binom, P.rank, d - 1 + (m - p) - a, m - p + 1));
+  }
 }
 
 __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
@@ -980,6 +1043,8 @@ static double binom_double(int n, int k) {
   return v;
 }
 
+int g_conv_rows = 1;  // row-walk layout converters (0: one unrank / rank round trip per component; test hook "conv_rows")
+
 template <typename T>
 static int permcls_to_flat(int rank, int64_t dim, const T* d_in, T* d_out, cudaStream_t stream) {
   PlanView P;
@@ -987,7 +1052,12 @@ static int permcls_to_flat(int rank, int64_t dim, const T* d_in, T* d_out, cudaS
   if (rc) return rc;
   if (get_host_plan(rank, dim)->flat_overflow) { set_error("flat size does not fit int64"); return ST_ERR_OVERFLOW; }
   if (!d_in || !d_out) { set_error("null pointer"); return ST_ERR_INVALID; }
-  permcls_to_flat_kernel<T><<<grid_1d(P.flat_size, 256), 256, 0, stream>>>(P, d_in, d_out);
+  if (g_conv_rows && rank >= 1 && rank <= 8 && dim <= 255) {
+    const int64_t ntasks = (P.total + kConvSpan - 1) / kConvSpan;
+    rowwalk_convert_kernel<T, true><<<(unsigned)std::min<int64_t>((ntasks + 7) / 8, (int64_t)sm_count() * 8), 256, 0, stream>>>(P, d_in, d_out, 0, P.total);
+  } else {
+    permcls_to_flat_kernel<T><<<grid_1d(P.flat_size, 256), 256, 0, stream>>>(P, d_in, d_out);
+  }
   count_launch();
   return check_cuda(cudaGetLastError(), "permcls_to_flat_kernel");
 }
@@ -1000,7 +1070,12 @@ static int flat_to_permcls(int rank, int64_t dim, const T* d_in, T* d_out, int64
   if (begin < 0 || end < begin || end > P.total) { set_error("range [%lld, %lld) outside [0, %lld]", (long long)begin, (long long)end, (long long)P.total); return ST_ERR_INVALID; }
   if (end == begin) return ST_OK;
   if (!d_in || !d_out) { set_error("null pointer"); return ST_ERR_INVALID; }
-  flat_to_permcls_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(P, d_in, d_out, begin, end);
+  if (g_conv_rows && rank >= 1 && rank <= 8 && dim <= 255) {
+    const int64_t ntasks = (end - begin + kConvSpan - 1) / kConvSpan;
+    rowwalk_convert_kernel<T, false><<<(unsigned)std::min<int64_t>((ntasks + 7) / 8, (int64_t)sm_count() * 8), 256, 0, stream>>>(P, d_in, d_out, begin, end);
+  } else {
+    flat_to_permcls_kernel<T><<<grid_1d(end - begin, 256), 256, 0, stream>>>(P, d_in, d_out, begin, end);
+  }
   count_launch();
   return check_cuda(cudaGetLastError(), "flat_to_permcls_kernel");
 }

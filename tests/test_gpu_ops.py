@@ -278,6 +278,53 @@ def test_outer_compile_time_rank_and_run_time_rank_kernels_agree():
         assert abs(v0 - v1) <= 1e-12 * abs(v0)
 
 
+def test_row_walk_layout_converters_agree_with_the_unrank_kernels():
+    """permcls <-> flat re-ordering through the row-walk kernels (rowwalk_convert_kernel) against the kernels that unrank /
+    classify / rank every component: bit-identical buffers, including output ranges that start and end mid-row."""
+    from symtensor_b200 import combinatorics as comb
+    from symtensor_b200._cabi import c_i64, check, lib
+    for rank, dim in [(1, 9), (2, 40), (3, 37), (4, 12), (5, 9), (6, 8), (8, 5), (8, 3), (4, 255), (7, 6)]:
+        tab = comb.class_table(rank, dim)
+        n_flat = comb.indep_size(rank, dim)
+        for tdt, fn in ((torch.float64, "f64"), (torch.float32, "f32")):
+            src = torch.rand(tab.total, dtype=tdt, device=DEV)
+            got = {}
+            for rows in (0, 1):
+                try:
+                    check(lib.st_set_tuning(b"conv_rows", c_i64(rows)))
+                    flat = torch.full((n_flat,), -5.0, dtype=tdt, device=DEV)
+                    check(getattr(lib, "st_permcls_to_flat_" + fn)(rank, c_i64(dim), src.data_ptr(), flat.data_ptr(), None))
+                    b, e = tab.total // 3 + 3, tab.total - 2
+                    back = torch.full((tab.total,), -5.0, dtype=tdt, device=DEV)
+                    part = torch.full((e - b,), -5.0, dtype=tdt, device=DEV)
+                    check(getattr(lib, "st_flat_to_permcls_" + fn)(rank, c_i64(dim), flat.data_ptr(), back.data_ptr(), c_i64(0), c_i64(tab.total), None))
+                    check(getattr(lib, "st_flat_to_permcls_" + fn)(rank, c_i64(dim), flat.data_ptr(), part.data_ptr(), c_i64(b), c_i64(e), None))
+                    torch.cuda.synchronize()
+                    got[rows] = (flat, back, part)
+                finally:
+                    check(lib.st_set_tuning(b"conv_rows", c_i64(1)))
+            for x0, x1 in zip(got[0], got[1]):
+                assert torch.equal(x0, x1), (rank, dim, fn)
+            assert float(got[1][0].min()) >= 0.0  # every flat position was written
+
+
+def test_matrix_pipeline_kernel_agrees_with_the_first_dmma_kernel():
+    """contract_all_indices_with_matrix (fp64, dim <= 64): the persistent producer / consumer step kernel (st_mat.cu) against
+    the per-CTA kernel of round 1, whole tensors and first-mode partitions."""
+    from symtensor_b200._cabi import c_i64, check, lib
+    for rank, dim in [(2, 64), (3, 33), (4, 20), (5, 11), (6, 9), (3, 64), (4, 7)]:
+        rng = np.random.default_rng(rank * 100 + dim)
+        TA = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=rand_packed(rank, dim, rng, "normal"), device=DEV)
+        W = rng.standard_normal((dim, dim))
+        try:
+            check(lib.st_set_tuning(b"mat_pipe", c_i64(0)))
+            C0 = st.contract_all_indices_with_matrix(TA, W).packed.clone()
+        finally:
+            check(lib.st_set_tuning(b"mat_pipe", c_i64(1)))
+        C1 = st.contract_all_indices_with_matrix(TA, W).packed
+        assert torch.allclose(C0, C1, rtol=1e-13, atol=1e-13), (rank, dim)
+
+
 def test_outer_row_walk_kernel_agrees_with_the_per_component_unrank_kernels():
     """multiply.outer through the row-walk kernel (outer_rows_kernel: warp-uniform odometer over the rows that cover 32
     consecutive coordinates, half-split subset sums) against the kernel that unranks every component (outer_fast_kernel) and
