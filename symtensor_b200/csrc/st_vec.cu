@@ -765,6 +765,8 @@ static int g_ring_slots = 2;           // ring slots per warp
 static int g_ring_bytes = 4096;        // preferred bytes per slot (shrunk to 1536 / 1024 when the table needs the room)
 static int g_ring_bytes_max = 4096;    // slots grow up to this when shared memory is left over
 static int g_ring_tile_bytes = 49152;    // bytes per tile (directory granularity; rounded to whole slots)
+static int64_t g_short_launch_bytes = 160ll << 20;  // launches over a SLICE of at most this many bytes use tiles of ...
+static int64_t g_short_launch_slots = 4;            // ... this many ring slots (tuning keys "vec_short_launch_bytes" / "_slots")
 static int g_ring_small_tiles = 1;       // shrink the tiles of tensors too small to give every warp a full-size tile
 static int g_ring_group = 4;             // dynamic deal: tiles per group at the start of a class (1: every tile on its own)
 static int g_ring_ondemand = 2;          // dynamic deal: rounds at the end of an ungrouped class claimed on demand
@@ -898,7 +900,7 @@ static const int64_t kMaxDirTiles = (int64_t)1 << 23;  // 256 MB of directory at
 // its best tail length to the rings' shared memory: then smaller slots are tried (small copies cost bandwidth,
 // a shorter tail costs much more).
 int sm_count();
-static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<TailStrategy>& st, StratEntry& e) {
+static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<TailStrategy>& st, StratEntry& e, int64_t nsub_cap = 0) {
   const int NW = g_ring_warps, R = g_ring_slots;
   // shared memory kept away from the tables: the rings at their preferred slot size, their control structures and --
   // only when some class needs them -- the per-warp relabelled copies of x
@@ -950,6 +952,9 @@ static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<Tai
     const int64_t per_warp = (total * esize + W * bytes - 1) / (W * bytes);  // slots per warp, rounded up
     nsub = std::min<int64_t>(nsub, std::max<int64_t>(1, per_warp));
   }
+  // short launches over a slice of the tensor (strong scaling: 1/8 of BASELINE config 2 is 69 MB, ~10 us of HBM time): the
+  // launch lasts as long as its costliest tile, and one 48 KB tile of a class walked with gaps takes a warp 55 us -- small tiles
+  if (nsub_cap > 0) nsub = std::min<int64_t>(nsub, nsub_cap);
   {
     // one workspace slot per tile of the whole tensor: grow the tiles until they fit
     auto total_tiles = [&](int64_t te) { int64_t n = 0; for (int c = 0; c < hp->ncls; ++c) n += (hp->h_cls[c].size + te - 1) / te; return n; };
@@ -961,7 +966,7 @@ static bool compute_ring_strategy(const HostPlan* hp, int esize, std::vector<Tai
 }
 
 // strategy of vec_ring_kernel for (device, rank, dim, element size): tail lengths, ring geometry, tile size, directories
-static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
+static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out, int64_t nsub_cap = 0) {
   const bool ring = true;
   int64_t tile = 0;
   const HostPlan* hp = get_host_plan(rank, dim);
@@ -970,7 +975,7 @@ static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_smu);
-  StratKey key{dev, rank, esize, 1, dim, 0};
+  StratKey key{dev, rank, esize, 1, dim, nsub_cap};
   auto it = g_strats.find(key);
   if (it != g_strats.end()) { *out = it->second; return ST_OK; }
   StratEntry e;
@@ -990,7 +995,7 @@ static int get_strategy(int rank, int64_t dim, int esize, StratEntry* out) {
   e.tile_elems = tile;
   std::vector<TailStrategy> st;
   if (ring) {
-    e.supported = compute_ring_strategy(hp, esize, st, e);
+    e.supported = compute_ring_strategy(hp, esize, st, e, nsub_cap);
     tile = e.tile_elems;
     if (getenv("ST_VEC_DEBUG")) {
       fprintf(stderr, "[st] ring strategy rank %d dim %lld esize %d: supported %d warps %d slots %d slot_bytes %d tile_elems %lld tbl_cap %d binom_smem %d cdesc_smem %d smem %zu tau:",
@@ -1236,7 +1241,8 @@ static int vec_partials(int layout, int rank, int64_t dim, const T* d_packed, in
   StratEntry se;
   se.supported = false;
   if (layout == ST_LAYOUT_PERMCLS && rank > 0 && g_variant != 1) {
-    rc = get_strategy(rank, dim, (int)sizeof(T), &se);
+    const bool short_launch = (end - begin) * (int64_t)sizeof(T) <= g_short_launch_bytes && (begin > 0 || end < total);
+    rc = get_strategy(rank, dim, (int)sizeof(T), &se, short_launch ? g_short_launch_slots : 0);
     if (rc) return rc;
     if (!se.supported && g_variant == 2) { set_error("tail-table kernel unavailable for dim %lld", (long long)dim); return ST_ERR_UNSUPPORTED; }
   }
@@ -1461,6 +1467,8 @@ int st_set_tuning(const char* key, int64_t value) {
     }
     if (k == "vec_ring_group" && value >= 1 && value <= 64) { g_ring_group = (int)value; return ST_OK; }
     if (k == "vec_ring_fine" && value >= 0 && value <= 64) { g_ring_fine = (int)value; return ST_OK; }
+    if (k == "vec_short_launch_bytes" && value >= 0) { g_short_launch_bytes = value; return ST_OK; }
+    if (k == "vec_short_launch_slots" && value >= 1 && value <= 64) { g_short_launch_slots = value; return ST_OK; }
     if (k == "vec_ring_small_tiles" && (value == 0 || value == 1)) {
       g_ring_small_tiles = (int)value;
       std::lock_guard<std::mutex> lk(g_smu);
