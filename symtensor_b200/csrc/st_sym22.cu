@@ -399,6 +399,40 @@ sym22_umma_kernel(const __grid_constant__ CUtensorMap mAhr, const __grid_constan
   }
 }
 
+// The same for ONE contracted index (k = 1: BASELINE config 3), where J is its own flat rank and has multiplicity 1: a CTA
+// per (chunk, first), 32-bit index arithmetic, the rank of the sorted triple from per-value terms in shared memory
+// (rank = C(d+2, 3) - 1 - F2[x] - F1[y] - F0[z]) -- ~25 instructions per element instead of ~300 (26 ms -> HBM time per operand).
+__global__ void __launch_bounds__(256) expand_pairs_k1_kernel(PlanView P, const float* __restrict__ flat, float* __restrict__ hi,
+                                                              float* __restrict__ lo, int Kp, int kch) {
+  extern __shared__ int32_t F[];  // [3][d]: F[t][v] = C(d - 1 + t - v, t + 1)
+  const int d = (int)P.dim;
+  for (int e = threadIdx.x; e < 3 * d; e += blockDim.x) {
+    const int t = e / d, v = e % d;
+    F[e] = (int32_t)binom_at(P.binom, P.rank, d - 1 + t - v, t + 1);
+  }
+  __syncthreads();
+  const int base = (int)(binom_at(P.binom, P.rank, d + 2, 3) - 1);
+  const int nchunk = Kp / kch;
+  for (int ca = blockIdx.x; ca < nchunk * d; ca += gridDim.x) {
+    const int a = ca % d, chunk = ca / d;
+    float* __restrict__ ho = hi + (int64_t)ca * d * kch;
+    float* __restrict__ lo_o = lo + (int64_t)ca * d * kch;
+    for (int e = threadIdx.x; e < d * kch; e += blockDim.x) {
+      const int within = e % kch, b = e / kch;
+      const int jj = chunk * kch + within;
+      float v = 0.f;
+      if (jj < d) {
+        const int lo2 = min(a, b), hi2 = max(a, b);
+        const int x = min(lo2, jj), z = max(hi2, jj), y = max(lo2, min(hi2, jj));
+        v = flat[base - F[2 * d + x] - F[d + y] - F[z]];
+      }
+      const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+      ho[e] = h;
+      lo_o[e] = v - h;
+    }
+  }
+}
+
 // X[chunk][first][second][kch]: for all (first, second) in dim x dim the values X[first, second, J], J = chunk * kch + e < Kp
 // (zero beyond K), stored K-chunk-major so that an operand box of the kernel -- 8 or 16 values of `first` times 16 consecutive
 // values of `second`, one chunk -- is a few contiguous runs of 16 * kch * 4 bytes (with J innermost every 64-byte piece sat in
@@ -616,8 +650,14 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   rc = check_cuda(cudaMemsetAsync(d_out, 0, (size_t)(end - begin) * sizeof(float), stream), "cudaMemsetAsync(out)");
   if (rc) return rc;
   const int eg = (int)std::min<int64_t>((n1 + 255) / 256, 148 * 32);
-  expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_a_flat, ah, al, K, Kp, kch, 1);
-  expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_b_flat, bh, bl, K, Kp, kch, 0);
+  if (k == 1 && dim <= 4096 && Kp % kch == 0 && Pin.flat_size < 2147483647LL) {
+    const int cg = (int)std::min<int64_t>((Kp / kch) * dim, 148 * 64);
+    expand_pairs_k1_kernel<<<cg, 256, 3 * dim * sizeof(int32_t), stream>>>(Pin, d_a_flat, ah, al, (int)Kp, kch);
+    expand_pairs_k1_kernel<<<cg, 256, 3 * dim * sizeof(int32_t), stream>>>(Pin, d_b_flat, bh, bl, (int)Kp, kch);
+  } else {
+    expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_a_flat, ah, al, K, Kp, kch, 1);
+    expand_pairs_kernel<<<eg, 256, 0, stream>>>(Pin, k, d_b_flat, bh, bl, K, Kp, kch, 0);
+  }
   count_launch(2);
   rc = check_cuda(cudaGetLastError(), "expand_pairs_kernel");
   if (rc) return rc;
