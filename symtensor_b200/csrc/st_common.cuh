@@ -12,6 +12,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/symtensor_b200.h"
@@ -379,12 +380,25 @@ ST_HD void rowcursor_serve(const PlanView& P, RowCursor& rc, int64_t c, int64_t 
 // info = row_class_info of the row's class; B23[(k - 2) * kRowBinomStride + n] = C(n, k) for k = 2, 3.
 ST_HD void row_component(unsigned long long valsp, int32_t b, int32_t m, int32_t o, unsigned long long info, const int32_t* B23, int32_t* K) {
   const int tau = (int)((info >> 32) & 15), nvals = (int)((info >> 36) & 15), s = (int)((info >> 40) & 15);
-  // the earlier runs' values above b, the only ones the tail has to step over (others: out of the way)
+  // the earlier runs' values: the tail steps over those above b.  One or two of them (most components) are kept in two
+  // registers, ascending; more go through a count to a fixed point
+  int32_t e0 = 0x7fffffff, e1 = 0x7fffffff;
+  if (s == 1) {
+    e0 = (int32_t)(valsp & 0xffull);
+  } else if (s == 2) {
+    const int32_t w0 = (int32_t)(valsp & 0xffull), w1 = (int32_t)((valsp >> 8) & 0xffull);
+    e0 = w0 < w1 ? w0 : w1;
+    e1 = w0 < w1 ? w1 : w0;
+  }
+  if (e0 <= b) e0 = 0x7fffffff;  // (then e1, if any, is the only one above b -- or none)
+  if (e1 <= b) e1 = 0x7fffffff;
   int32_t used[8];
+  if (s > 2) {
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const int32_t w = (int32_t)((valsp >> (8 * u)) & 0xffull);
-    used[u] = (u < s && w > b) ? w : 0x7fffffff;
+    for (int u = 0; u < 8; ++u) {
+      const int32_t w = (int32_t)((valsp >> (8 * u)) & 0xffull);
+      used[u] = (u < s && w > b) ? w : 0x7fffffff;
+    }
   }
   int32_t prev = -1, r = o;
 #pragma unroll
@@ -394,6 +408,19 @@ ST_HD void row_component(unsigned long long valsp, int32_t b, int32_t m, int32_t
     int32_t y;
     if (k == 1) {
       y = prev + 1 + r;
+    } else if (k == 2) {
+      // pairs (y, .) of the N values above prev: z = y - prev - 1 is the largest z with z (2N - z - 1) / 2 <= r
+      const int32_t N = m - 1 - prev, t2 = 2 * N - 1;
+#ifdef __CUDA_ARCH__
+      int32_t z = (int32_t)(((float)t2 - sqrtf((float)(t2 * t2 - 8 * r))) * 0.5f);
+#else
+      int32_t z = (int32_t)(((double)t2 - sqrt((double)(t2 * t2 - 8 * r))) * 0.5);
+#endif
+      z = z < 0 ? 0 : (z > N - 2 ? N - 2 : z);
+      while (z > 0 && z * (t2 - z) / 2 > r) --z;
+      while (z < N - 2 && (z + 1) * (t2 - z - 1) / 2 <= r) ++z;
+      r -= z * (t2 - z) / 2;
+      y = prev + 1 + z;
     } else {
       const int32_t* Bk = B23 + (k - 2) * kRowBinomStride;
       const int32_t all = Bk[m - 1 - prev];
@@ -408,7 +435,7 @@ ST_HD void row_component(unsigned long long valsp, int32_t b, int32_t m, int32_t
     prev = y;
     // the y-th free value above b
     int32_t v = b + 1 + y;
-    if (s > 0) {
+    if (s > 2) {
       for (;;) {
         int32_t cnt = 0;
 #pragma unroll
@@ -416,6 +443,9 @@ ST_HD void row_component(unsigned long long valsp, int32_t b, int32_t m, int32_t
         if (b + 1 + y + cnt == v) break;
         v = b + 1 + y + cnt;
       }
+    } else {
+      v += (e0 <= v);
+      v += (e1 <= v);
     }
     const int pos = nvals - tau + i;
     valsp = (valsp & ~(0xffull << (8 * pos))) | ((unsigned long long)v << (8 * pos));
