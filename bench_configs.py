@@ -58,26 +58,27 @@ def config3(dev, world, rank, dist, peaks, share_of=8):
     A, B = device_tensor(3, dim, SEED + 3, torch.float32, dev), device_tensor(3, dim, SEED + 33, torch.float32, dev)
     af, bf = ops._flat_buffer(A, torch.float32), ops._flat_buffer(B, torch.float32)
     parts = world if world > 1 else share_of
-    cuts = sharding.tensordot22_bounds(dim, parts)
+    # a GPU's shard: its part of every class with repeated indices + its part of class (1,1,1,1) (sharding.tensordot22_shards),
+    # computed by ONE call over five output ranges
     me = rank if world > 1 else parts // 2
-    b, e = cuts[me], cuts[me + 1]
-    out = torch.empty(e - b, dtype=torch.float32, device=dev)
+    ranges = sharding.tensordot22_shards(dim, parts)[me]
+    outs = [torch.empty(e - b, dtype=torch.float32, device=dev) for b, e in ranges]
     state = {"ws": None}
 
     def step():
-        state["ws"] = ops.tensordot_device(A, B, 1, out, b, e, torch.float32, af=af, bf=bf, ws=state["ws"], check_flag=False)
+        state["ws"] = ops.tensordot_device_ranges(A, B, 1, outs, ranges, af=af, bf=bf, ws=state["ws"], check_flag=False)
     ms, launches = _timed(step, 2, 1, dist if world > 1 else None)
     flag = int(state["ws"][:1].view(torch.int32)[0].item())
     total = sum(comb.class_table(4, dim).sizes)
-    n_done = total if world > 1 else sum(min(e, o + s) - max(b, o) for o, s in zip(comb.class_table(4, dim).offsets, comb.class_table(4, dim).sizes)
-                                         if min(e, o + s) > max(b, o))
+    tab = comb.class_table(4, dim)
+    n_done = total if world > 1 else sum(min(e, o + s) - max(b, o) for b, e in ranges for o, s in zip(tab.offsets, tab.sizes) if min(e, o + s) > max(b, o))
     flops = 12.0 * dim * n_done           # 2 d C(4, 2) per packed output component, fp32-equivalent
     pipe = 3.0 * flops / world            # 3xTF32: three tensor-core products per fp32 product, per GPU
     peak = peaks["bf16_tflops"] / 2.0     # kind::tf32 runs at half the bf16 rate
     ach = pipe / (ms * 1e-3) / 1e12
     res = {"workload": f"tensordot rank 3 . rank 3 over one index, dim {dim}, fp32 -> rank 4 (BASELINE configs[2]); "
-                       + (f"every rank its share of a {world}-way tile-aligned partition of the 167.7 GB output" if world > 1 else
-                          f"one GPU: share {me} of a {parts}-way tile-aligned partition of the 167.7 GB output (what one of {parts} GPUs computes)"),
+                       + (f"every rank its shard of a {world}-way tile-balanced partition of the 167.7 GB output (five ranges per rank)" if world > 1 else
+                          f"one GPU: shard {me} of a {parts}-way tile-balanced partition of the 167.7 GB output (what one of {parts} GPUs computes)"),
            "packed_components": int(n_done), "ms": ms, "value": n_done / (ms * 1e-3), "unit": "packed components/s",
            "tflops_fp32_equivalent": flops / (ms * 1e-3) / 1e12, "kernel_launches": launches, "error_flag": flag,
            "includes": "expansion of both operands into hi/lo pair matrices, zeroing of the output range, the tiled tcgen05 kernel",
@@ -85,7 +86,7 @@ def config3(dev, world, rank, dist, peaks, share_of=8):
                         "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (kind::tf32 issues at half the bf16 rate)" if peaks["measured"]
                         else "half of the fallback bf16 figure of B200_PROFILING.md",
                         "kernel": "sym22_umma_kernel (tcgen05.mma kind::tf32, TMA-staged 4-D operand boxes, 3xTF32: per-GPU tensor-pipe flops = 3 x 12 d per component)"}}
-    del out, state
+    del outs, state
     return res
 
 

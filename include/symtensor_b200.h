@@ -220,6 +220,14 @@ int st_tensordot_f64(int ra, int rb, int k, int64_t dim, const double* d_a_flat,
 int st_tensordot_f32(int ra, int rb, int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out,
                      int64_t begin, int64_t end, void* d_workspace, void* stream);
 
+/* Several DISJOINT output ranges in one call (fp32): range q of the packed output goes to d_outs[q] (which starts at coordinate
+ * begins[q]); at most 8 ranges.  For the tiled kernel a tile that serves several ranges runs once -- the multi-GPU shard of
+ * sharding.tensordot22_shards: a GPU's part of every class with repeated indices plus its part of class (1,1,1,1), so that the
+ * tiles that hold a diagonal are spread over the GPUs instead of all landing on the one that owns the start of the buffer.
+ * begins / ends / d_outs are HOST arrays. */
+int st_tensordot_ranges_f32(int ra, int rb, int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, int nranges,
+                            const int64_t* begins, const int64_t* ends, float* const* d_outs, void* d_workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * contract_all_indices_with_matrix  (symtensor/symalg.py:475-496):
  *     C[j1..jr] = sum A[i1..ir] W[i1,j1] ... W[ir,jr]      (W is dim x dim, row-major, contracted on axis 0)
@@ -306,6 +314,8 @@ int64_t st_debug_rowwalk(int rank, int64_t dim, int64_t begin, int64_t end, int6
 /* debug (host only): the tile words p | q << 16 | r << 32 | s << 48 (index blocks 16 / 16 / 16 / 8) the tiled tensordot kernel
  * runs for the output range [begin, end) of a rank-4 result; returns their number (writes at most `cap`). */
 int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end, unsigned long long* h_out, int64_t cap);
+/* ... for the union of several ranges (host arrays), as st_tensordot_ranges_f32 runs them */
+int64_t st_debug_sym22_tiles_ranges(int64_t dim, int nranges, const int64_t* begins, const int64_t* ends, unsigned long long* h_out, int64_t cap);
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 int64_t st_launch_count(void);
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "st_tensordot_is_tiled": (c_int, [c_int, c_int, c_int, c_i64, c_int]),
     "st_tensordot_f64": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "st_tensordot_f32": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
+    "st_tensordot_ranges_f32": (c_int, [c_int, c_int, c_int, c_i64, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "st_contract_mat_workspace_bytes": (c_int, [c_int, c_i64, c_int, c_i64p]),
     "st_contract_mat_f64": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "st_contract_mat_f32": (c_int, [c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -85,6 +86,7 @@ SIGNATURES = {
     "st_debug_permcls_successors": (c_i64, [c_int, c_i64, ctypes.c_int32, c_i64, c_i64, c_vp]),
     "st_debug_rowwalk": (c_i64, [c_int, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "st_debug_sym22_tiles": (c_i64, [c_i64, c_i64, c_i64, c_vp, c_i64]),
+    "st_debug_sym22_tiles_ranges": (c_i64, [c_i64, c_int, c_vp, c_vp, c_vp, c_i64]),
     "st_launch_count": (c_i64, []),
 }
 

@@ -72,6 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
                  : "r"(bar), "r"(parity)
                  : "memory");
     if (ok) return;
+    if (it > 4) __nanosleep(it > 64 ? 256 : 32);  // (polls take issue slots from the warps that have work: 40 % of the kernel's instructions without this)
   }
   __trap();
 }

@@ -1176,6 +1176,8 @@ namespace s22 {
 int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin, int64_t end, void* d_ws,
                     cudaStream_t stream);
 int workspace_bytes(int k, int64_t dim, int64_t* out);
+int tensordot_sym22_ranges(int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, int nranges, const int64_t* begins,
+                           const int64_t* ends, float* const* d_outs, void* d_ws, cudaStream_t stream);
 }
 int g_sym22 = 1;             // fp32 tensordot with 2 + 2 free indices through the tiled kernel (0: always the materialised Gram matrix)
 int64_t g_sym22_min_dim = 96;  // ... from this dimension on (tuning key "sym22_min_dim": tests lower it to reach the kernel at small sizes)
@@ -1414,6 +1416,28 @@ int st_tensordot_f64(int ra, int rb, int k, int64_t dim, const double* d_a_flat,
 int st_tensordot_f32(int ra, int rb, int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin,
                      int64_t end, void* d_workspace, void* stream) {
   return tensordot<float>(ra, rb, k, dim, d_a_flat, d_b_flat, d_out, begin, end, d_workspace, (cudaStream_t)stream);
+}
+
+int st_tensordot_ranges_f32(int ra, int rb, int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, int nranges, const int64_t* begins,
+                            const int64_t* ends, float* const* d_outs, void* d_workspace, void* stream) {
+  if (nranges < 1 || !begins || !ends || !d_outs) { set_error("null pointer / no range"); return ST_ERR_INVALID; }
+  if (!use_sym22(ra, rb, k, dim, 4)) {  // shapes without the tiled kernel: one call per range
+    for (int q = 0; q < nranges; ++q) {
+      const int rc = tensordot<float>(ra, rb, k, dim, d_a_flat, d_b_flat, d_outs[q], begins[q], ends[q], d_workspace, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    return ST_OK;
+  }
+  PlanView Pn;
+  int rc = get_device_plan(4, dim, &Pn);
+  if (rc) return rc;
+  if (!d_a_flat || !d_b_flat || !d_workspace) { set_error("null pointer"); return ST_ERR_INVALID; }
+  for (int q = 0; q < nranges; ++q) {
+    if (begins[q] < 0 || ends[q] < begins[q] || ends[q] > Pn.total || (ends[q] > begins[q] && !d_outs[q])) { set_error("range %d outside the packed output / null buffer", q); return ST_ERR_INVALID; }
+    for (int p = 0; p < q; ++p)
+      if (begins[q] < ends[p] && begins[p] < ends[q]) { set_error("output ranges %d and %d overlap", p, q); return ST_ERR_INVALID; }
+  }
+  return s22::tensordot_sym22_ranges(k, dim, d_a_flat, d_b_flat, nranges, begins, ends, d_outs, d_workspace, (cudaStream_t)stream);
 }
 
 int st_contract_mat_workspace_bytes(int rank, int64_t dim, int elem_size, int64_t* out_bytes) {

@@ -63,6 +63,15 @@ struct Geo {
   static constexpr uint64_t LAYOUT = KCH == 32 ? 2ull : 4ull;   // SWIZZLE_128B : SWIZZLE_64B
 };
 
+// the output ranges of one call (a GPU's shard: its part of every class with repeated indices + its part of class (1,1,1,1)),
+// each with its own destination buffer; disjoint
+constexpr int kMaxRanges = 8;
+struct OutRanges {
+  int32_t n;
+  int64_t begin[kMaxRanges], end[kMaxRanges];
+  float* out[kMaxRanges];
+};
+
 struct Params {
   PlanView P;          // plan of the rank-4 output
   int64_t begin, end;  // packed output coordinates served by this launch
@@ -171,7 +180,7 @@ __device__ __forceinline__ int64_t element_coord(const PlanView& P, int64_t base
 // once (by the one tile that holds it).  Strictly increasing indices take the four-term formula from shared-memory tables,
 // repeated indices the generic class rank.
 __global__ void __launch_bounds__(256) sym22_scatter_kernel(PlanView P, const unsigned long long* __restrict__ tiles, const float* __restrict__ scratch,
-                                                            float* __restrict__ out, int64_t begin, int64_t end) {
+                                                            const OutRanges R) {
   __shared__ long long Ti[BJ], Tj[BJ], Tk[BJ], Tl[BL];
   const unsigned long long tw = tiles[blockIdx.x];
   const int i0 = (int)(tw & 0xffff) * BJ, j0 = (int)((tw >> 16) & 0xffff) * BJ, k0 = (int)((tw >> 32) & 0xffff) * BJ,
@@ -192,7 +201,9 @@ __global__ void __launch_bounds__(256) sym22_scatter_kernel(PlanView P, const un
     int64_t coord;
     if (gi < gj && gj < gk && gk < gl) coord = base1111 - Ti[i] - Tj[j] - Tk[k] - Tl[l];
     else coord = element_coord(P, base1111, gi, gj, gk, gl);
-    if (coord >= begin && coord < end) out[coord - begin] = slot[L];
+#pragma unroll
+    for (int q = 0; q < kMaxRanges; ++q)
+      if (q < R.n && coord >= R.begin[q] && coord < R.end[q]) R.out[q][coord - R.begin[q]] = slot[L];
   }
 }
 
@@ -538,8 +549,9 @@ int workspace_bytes(int k, int64_t dim, int64_t* out) {
 
 struct TileKey {
   int dev;
-  int64_t dim, begin, end;
-  bool operator<(const TileKey& o) const { return std::tie(dev, dim, begin, end) < std::tie(o.dev, o.dim, o.begin, o.end); }
+  int64_t dim;
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  bool operator<(const TileKey& o) const { return std::tie(dev, dim, ranges) < std::tie(o.dev, o.dim, o.ranges); }
 };
 struct TileList { unsigned long long* d; int64_t n; };
 static std::mutex g_tmu;
@@ -554,13 +566,43 @@ static int64_t rank1111(const HostPlan* hp, int64_t base, int64_t a, int64_t b, 
 // tiles (p, q, r, s) that can hold components of [begin, end); s runs fastest so that the CTAs working side by side
 // share the (i, j), (i, k) and (j, k) operand boxes in L2.  Pure host arithmetic (tests/test_cabi.py checks it against a
 // brute-force enumeration through st_debug_sym22_tiles).
-void build_tiles(const HostPlan* hp, int64_t begin, int64_t end, std::vector<unsigned long long>& tiles) {
+void build_tiles(const HostPlan* hp, const std::vector<std::pair<int64_t, int64_t>>& ranges, std::vector<unsigned long long>& tiles) {
   const int64_t d = hp->dim;
   const int64_t off4 = hp->h_cls[hp->ncls - 1].offset;
   const int64_t base = off4 + hp->h_binom[d * 5 + 4] - 1;
   const int64_t nbj = (d + BJ - 1) / BJ, nbl = (d + BL - 1) / BL;
   tiles.clear();
-  if (end <= begin) return;
+  // Components with repeated indices live in the classes before (1,1,1,1).  In each of them the FIRST class-order value a
+  // (the value with the highest multiplicity; the smaller one in class (2,2)) is the most significant digit of the position,
+  // so the part of [begin, end) inside the class is an interval of a -- and a is a REPEATED index of the component: a tile
+  // can hold it only where two neighbouring index blocks overlap in a.  (Round 1 gave every range that touched these classes
+  // ALL diagonal tiles: 244,250 of them at dim 1000, all on the first GPU of a partition.)
+  std::vector<int64_t> alo, ahi;
+  bool any = false;
+  {
+    const PlanView P = hp->host_view();
+    for (const auto& rg : ranges) {
+      if (rg.second <= rg.first) continue;
+      any = true;
+      for (int c = 0; c + 1 < hp->ncls; ++c) {
+        const ClassDesc& C = hp->h_cls[c];
+        const int64_t lo = std::max(rg.first, C.offset), hi = std::min(rg.second, C.offset + C.size);
+        if (lo >= hi) continue;
+        int32_t v0[ST_MAX_RANK], v1[ST_MAX_RANK];
+        permcls_unrank_vals(P, C, lo - C.offset, v0);
+        permcls_unrank_vals(P, C, hi - 1 - C.offset, v1);
+        alo.push_back(v0[0]);
+        ahi.push_back(v1[0]);
+      }
+    }
+  }
+  if (!any) return;
+  const int na = (int)alo.size();
+  auto hits = [&](int64_t x0, int64_t x1) {  // does the value interval [x0, x1] meet one of the intervals of a?
+    for (int i = 0; i < na; ++i)
+      if (x0 <= ahi[i] && x1 >= alo[i]) return true;
+    return false;
+  };
   for (int64_t p = 0; p < nbj; ++p) {
     const int64_t i0 = p * BJ;
     for (int64_t q = p; q < nbj; ++q) {
@@ -570,7 +612,12 @@ void build_tiles(const HostPlan* hp, int64_t begin, int64_t end, std::vector<uns
         for (int64_t s = k0 / BL; s < nbl; ++s) {
           const int64_t l0 = s * BL;
           const bool diag = p == q || q == r || l0 <= k0 + BJ - 1;
-          bool take = diag && begin < off4;  // components with repeated indices live in the classes before (1,1,1,1)
+          bool take = false;
+          if (diag && na) {  // a repeated index can sit in I_p (p == q), in I_q (q == r), or in the overlap of I_r and L_s
+            if (p == q && hits(i0, i0 + BJ - 1)) take = true;
+            if (q == r && hits(j0, j0 + BJ - 1)) take = true;
+            if (l0 <= k0 + BJ - 1 && hits(std::max(k0, l0), std::min(k0 + BJ - 1, l0 + BL - 1))) take = true;
+          }
           if (!take) {
             // smallest / largest strictly increasing tuple of the tile (componentwise bounds; lexicographic rank is monotone)
             const int64_t a0 = i0, b0 = std::max(j0, a0 + 1), c0 = std::max(k0, b0 + 1), e0 = std::max(l0, c0 + 1);
@@ -578,7 +625,7 @@ void build_tiles(const HostPlan* hp, int64_t begin, int64_t end, std::vector<uns
                           a1 = std::min(i0 + BJ - 1, b1 - 1);
             if (b0 <= j0 + BJ - 1 && c0 <= k0 + BJ - 1 && e0 <= e1 && a1 >= a0 && b1 >= b0 && c1 >= c0) {
               const int64_t lo = rank1111(hp, base, a0, b0, c0, e0), hi = rank1111(hp, base, a1, b1, c1, e1);
-              take = lo < end && hi >= begin;
+              for (const auto& rg : ranges) take = take || (rg.second > rg.first && lo < rg.second && hi >= rg.first);
             }
           }
           if (take) tiles.push_back((unsigned long long)p | ((unsigned long long)q << 16) | ((unsigned long long)r << 32) | ((unsigned long long)s << 48));
@@ -589,16 +636,16 @@ void build_tiles(const HostPlan* hp, int64_t begin, int64_t end, std::vector<uns
   // (generation order: s runs fastest, so the CTAs working side by side share the three column boxes (i, j), (i, k), (j, k))
 }
 
-static int get_tiles(const HostPlan* hp, int64_t begin, int64_t end, TileList* out) {
+static int get_tiles(const HostPlan* hp, const std::vector<std::pair<int64_t, int64_t>>& ranges, TileList* out) {
   int dev = 0;
   int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(g_tmu);
-  const TileKey key{dev, hp->dim, begin, end};
+  const TileKey key{dev, hp->dim, ranges};
   auto it = g_tiles.find(key);
   if (it != g_tiles.end()) { *out = it->second; return ST_OK; }
   std::vector<unsigned long long> tiles;
-  build_tiles(hp, begin, end, tiles);
+  build_tiles(hp, ranges, tiles);
   TileList tl{nullptr, (int64_t)tiles.size()};
   if (tl.n) {
     rc = check_cuda(cudaMalloc(&tl.d, tiles.size() * sizeof(unsigned long long)), "cudaMalloc(tiles)");
@@ -627,8 +674,27 @@ static int launch(const CUtensorMap* maps, const Params& prm, int grid, cudaStre
 }
 
 // d_ws: workspace_bytes(); layout: [0, 4096) control (error flag), then wA hi, wA lo, B hi, B lo (dim x dim x Kp floats each)
+int tensordot_sym22_ranges(int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, int nranges, const int64_t* begins,
+                           const int64_t* ends, float* const* d_outs, void* d_ws, cudaStream_t stream);
+
 int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, float* d_out, int64_t begin, int64_t end, void* d_ws,
                     cudaStream_t stream) {
+  return tensordot_sym22_ranges(k, dim, d_a_flat, d_b_flat, 1, &begin, &end, &d_out, d_ws, stream);
+}
+
+// the same for several disjoint output ranges at once (a tile that serves two of them runs once)
+int tensordot_sym22_ranges(int k, int64_t dim, const float* d_a_flat, const float* d_b_flat, int nranges, const int64_t* begins,
+                           const int64_t* ends, float* const* d_outs, void* d_ws, cudaStream_t stream) {
+  if (nranges < 1 || nranges > kMaxRanges) { set_error("1 .. %d output ranges per call", kMaxRanges); return ST_ERR_INVALID; }
+  OutRanges R;
+  R.n = nranges;
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  for (int q = 0; q < kMaxRanges; ++q) {
+    R.begin[q] = q < nranges ? begins[q] : 0;
+    R.end[q] = q < nranges ? ends[q] : 0;
+    R.out[q] = q < nranges ? d_outs[q] : nullptr;
+    if (q < nranges) ranges.emplace_back(begins[q], ends[q]);
+  }
   if (dim >= 65536 * BL) { set_error("dim too large for the tile words"); return ST_ERR_UNSUPPORTED; }
   const int64_t K = contracted_count(k, dim);
   if (K <= 0) { set_error("nothing to contract"); return ST_ERR_INVALID; }
@@ -647,8 +713,11 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   float *ah = x, *al = x + n1, *bh = x + 2 * n1, *bl = x + 3 * n1;
   rc = check_cuda(cudaMemsetAsync(d_err, 0, 4096, stream), "cudaMemsetAsync(ctl)");
   if (rc) return rc;
-  rc = check_cuda(cudaMemsetAsync(d_out, 0, (size_t)(end - begin) * sizeof(float), stream), "cudaMemsetAsync(out)");
-  if (rc) return rc;
+  for (int q = 0; q < nranges; ++q) {
+    if (ends[q] <= begins[q]) continue;
+    rc = check_cuda(cudaMemsetAsync(d_outs[q], 0, (size_t)(ends[q] - begins[q]) * sizeof(float), stream), "cudaMemsetAsync(out)");
+    if (rc) return rc;
+  }
   const int eg = (int)std::min<int64_t>((n1 + 255) / 256, 148 * 32);
   if (k == 1 && dim <= 4096 && Kp % kch == 0 && Pin.flat_size < 2147483647LL) {
     const int cg = (int)std::min<int64_t>((Kp / kch) * dim, 148 * 64);
@@ -662,7 +731,7 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   rc = check_cuda(cudaGetLastError(), "expand_pairs_kernel");
   if (rc) return rc;
   TileList tl;
-  rc = get_tiles(hp, begin, end, &tl);
+  rc = get_tiles(hp, ranges, &tl);
   if (rc) return rc;
   if (tl.n == 0) return ST_OK;
   CUtensorMap maps[8];
@@ -680,9 +749,9 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
   for (int64_t t0 = 0; t0 < tl.n; t0 += cap) {
     Params prm;
     prm.P = Pn;
-    prm.begin = begin;
-    prm.end = end;
-    prm.out = d_out;
+    prm.begin = begins[0];
+    prm.end = ends[0];
+    prm.out = d_outs[0];
     prm.scratch = scratch;
     prm.tiles = tl.d + t0;
     prm.ntiles = std::min<int64_t>(cap, tl.n - t0);
@@ -692,7 +761,7 @@ int tensordot_sym22(int k, int64_t dim, const float* d_a_flat, const float* d_b_
     const int grid = (int)std::min<int64_t>(prm.ntiles, sms);
     rc = kch == 32 ? launch<32>(maps, prm, grid, stream) : launch<16>(maps, prm, grid, stream);
     if (rc) return rc;
-    sym22_scatter_kernel<<<(unsigned)prm.ntiles, 256, 0, stream>>>(Pn, prm.tiles, scratch, d_out, begin, end);
+    sym22_scatter_kernel<<<(unsigned)prm.ntiles, 256, 0, stream>>>(Pn, prm.tiles, scratch, R);
     count_launch();
     rc = check_cuda(cudaGetLastError(), "sym22_scatter_kernel");
     if (rc) return rc;
@@ -707,7 +776,19 @@ extern "C" int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end,
   const st::HostPlan* hp = st::get_host_plan(4, dim);
   if (!hp) return -1;
   std::vector<unsigned long long> tiles;
-  st::s22::build_tiles(hp, begin, end, tiles);
+  st::s22::build_tiles(hp, {{begin, end}}, tiles);
+  for (int64_t i = 0; i < (int64_t)tiles.size() && i < cap; ++i) h_out[i] = tiles[i];
+  return (int64_t)tiles.size();
+}
+
+extern "C" int64_t st_debug_sym22_tiles_ranges(int64_t dim, int nranges, const int64_t* begins, const int64_t* ends, unsigned long long* h_out,
+                                               int64_t cap) {
+  const st::HostPlan* hp = st::get_host_plan(4, dim);
+  if (!hp || nranges < 0 || (nranges && (!begins || !ends))) return -1;
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  for (int q = 0; q < nranges; ++q) ranges.emplace_back(begins[q], ends[q]);
+  std::vector<unsigned long long> tiles;
+  st::s22::build_tiles(hp, ranges, tiles);
   for (int64_t i = 0; i < (int64_t)tiles.size() && i < cap; ++i) h_out[i] = tiles[i];
   return (int64_t)tiles.size();
 }

@@ -329,6 +329,29 @@ def tensordot_device(a, b, k: int, out_range_buf: torch.Tensor, begin: int, end:
     return ws
 
 
+def tensordot_device_ranges(a, b, k: int, outs, ranges, af=None, bf=None, ws=None, check_flag: bool = True):
+    """Raw launch (fp32): several DISJOINT coordinate ranges ``[(begin, end), ...]`` of the permcls buffer of ``tensordot(a, b, axes=k)``
+    into the buffers ``outs`` in ONE call (``st_tensordot_ranges_f32``): the shard a GPU gets from ``sharding.tensordot22_shards``."""
+    tdt = torch.float32
+    af = _flat_buffer(a, tdt) if af is None else af
+    bf = _flat_buffer(b, tdt) if bf is None else bf
+    nbytes = c_i64(0)
+    check(lib.st_tensordot_workspace_bytes(a.rank, b.rank, k, c_i64(a.dim), 4, ctypes.byref(nbytes)))
+    tiled = bool(lib.st_tensordot_is_tiled(a.rank, b.rank, k, c_i64(a.dim), 4))
+    n = len(ranges)
+    begins = (ctypes.c_int64 * n)(*[int(r[0]) for r in ranges])
+    ends = (ctypes.c_int64 * n)(*[int(r[1]) for r in ranges])
+    ptrs = (ctypes.c_void_p * n)(*[o.data_ptr() for o in outs])
+    with torch.cuda.device(af.device):
+        if ws is None:
+            ws = torch.empty(max(1, (nbytes.value + 3) // 4), dtype=tdt, device=af.device)
+        check(lib.st_tensordot_ranges_f32(a.rank, b.rank, k, c_i64(a.dim), af.data_ptr(), bf.data_ptr(), n, begins, ends, ptrs, ws.data_ptr(),
+                                          _stream_ptr(af.device)))
+        if tiled and check_flag and int(ws[:1].view(torch.int32)[0].item()) != 0:
+            raise RuntimeError("symtensor_b200.tensordot: the tiled tcgen05 kernel gave up on a barrier (internal error; the result is invalid)")
+    return ws
+
+
 def _contract_all_indices_with_matrix(symtensor, W):
     """symtensor/symalg.py:475-496: C[j1..jr] = sum A[i1..ir] W[i1,j1]...W[ir,jr] (W contracted on its first axis)."""
     if not isinstance(symtensor, _SYM):

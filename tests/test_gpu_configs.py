@@ -23,7 +23,7 @@ from oracle import packed_oracle as po
 
 import symtensor_b200 as st
 from symtensor_b200 import combinatorics as comb
-from symtensor_b200 import ops
+from symtensor_b200 import ops, sharding
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -308,3 +308,40 @@ def test_config3_full_operands_output_ranges_windows(c3_operands):
             if lo < hi:
                 assert float(out[lo - begin:hi - begin].abs().max()) == 0.0
         del out
+
+
+def test_config3_shard_of_an_8_gpu_partition_in_one_call(c3_operands):
+    """What one GPU of an 8-GPU run of BASELINE config 3 computes (sharding.tensordot22_shards: its part of EVERY class with
+    repeated indices plus its part of class (1,1,1,1), five disjoint ranges in one st_tensordot_ranges_f32 call -- the tiles
+    that hold a diagonal are spread over the GPUs).  Shards 0 and 5 restricted to 60 M components of their last range; windows
+    of every range against the packed formula in fp64; the ranges of all shards tile the buffer."""
+    A, B = c3_operands
+    dim = 1000
+    table = comb.class_table(4, dim)
+    shards = sharding.tensordot22_shards(dim, 8)
+    covered = sorted(r for sh in shards for r in sh)
+    assert covered[0][0] == 0 and covered[-1][1] == table.total
+    assert all(a[1] <= b[0] and b[0] - a[1] < 32 for a, b in zip(covered[:-1], covered[1:]))  # disjoint; gaps are alignment padding only
+    af_d, bf_d = ops._flat_buffer(A, torch.float32), ops._flat_buffer(B, torch.float32)
+    af, bf = af_d.cpu().numpy().astype(np.float64), bf_d.cpu().numpy().astype(np.float64)
+    rng = np.random.default_rng(3333)
+    ws = None
+    for g in (0, 5):
+        ranges = list(shards[g])
+        assert len(ranges) == 5
+        b4, e4 = ranges[-1]
+        ranges[-1] = (b4, min(e4, b4 + 60_000_000 // 32 * 32))
+        outs = [torch.full((e - b,), -7.0, dtype=torch.float32, device=DEV) for b, e in ranges]
+        ws = ops.tensordot_device_ranges(A, B, 1, outs, ranges, af=af_d, bf=bf_d, ws=ws)
+        for (begin, end), out in zip(ranges, outs):
+            for ci, cls in enumerate(table.classes):
+                lo, hi = max(begin, table.offsets[ci]), min(end, table.offsets[ci] + table.sizes[ci])
+                if lo >= hi:
+                    continue
+                pos = np.unique(np.concatenate([np.arange(lo, min(hi, lo + 4)), np.arange(max(lo, hi - 4), hi), rng.integers(lo, hi, 16)]))
+                K = sorted_indices(cls, dim, pos - table.offsets[ci])
+                want, mag = _tensordot_components(af, bf, 3, 3, dim, K)
+                got = out[torch.as_tensor(pos - begin, device=DEV)].cpu().numpy().astype(np.float64)
+                assert np.all(np.abs(got - want) <= 1e-5 * mag), (g, begin, cls, np.max(np.abs(got - want) / mag))
+        del outs
+

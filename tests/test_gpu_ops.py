@@ -325,6 +325,37 @@ def test_matrix_pipeline_kernel_agrees_with_the_first_dmma_kernel():
         assert torch.allclose(C0, C1, rtol=1e-13, atol=1e-13), (rank, dim)
 
 
+def test_tensordot_several_output_ranges_in_one_call_equal_the_single_range_calls():
+    """st_tensordot_ranges_f32 (the multi-GPU shard: up to 8 disjoint ranges, a tile that serves several of them runs once)
+    against one st_tensordot_f32 call per range, through the tiled tcgen05 kernel (dims below its default threshold are
+    admitted with the tuning key) and through the materialised path: bit-identical."""
+    from symtensor_b200 import combinatorics as comb, ops, sharding
+    from symtensor_b200._cabi import c_i64, check, lib
+    for ra, rb, k, dim, tiled in [(3, 3, 1, 40, True), (3, 3, 1, 24, True), (4, 4, 2, 9, True), (3, 2, 1, 30, False)]:
+        rng = np.random.default_rng(ra * 1000 + rb * 100 + k * 10 + dim)
+        TA = st.PermClsTorchSymmetricTensor(rank=ra, dim=dim, data=rand_packed(ra, dim, rng, "normal"), device=DEV).astype(np.float32)
+        TB = st.PermClsTorchSymmetricTensor(rank=rb, dim=dim, data=rand_packed(rb, dim, rng, "normal"), device=DEV).astype(np.float32)
+        n = ra + rb - 2 * k
+        total = comb.class_table(n, dim).total
+        try:
+            check(lib.st_set_tuning(b"sym22_min_dim", c_i64(8 if tiled else 96)))
+            assert bool(lib.st_tensordot_is_tiled(ra, rb, k, c_i64(dim), 4)) == tiled
+            if n == 4:
+                sets = sharding.tensordot22_shards(dim, 3)
+            else:
+                cuts = sharding.shard_bounds(total, 5)
+                sets = [[(cuts[0], cuts[1]), (cuts[3], cuts[4])], [(cuts[1], cuts[3]), (cuts[4], cuts[5])]]
+            for ranges in sets:
+                outs = [torch.full((e - b,), -3.0, dtype=torch.float32, device=DEV) for b, e in ranges]
+                ops.tensordot_device_ranges(TA, TB, k, outs, ranges)
+                for (b, e), got in zip(ranges, outs):
+                    one = torch.full((e - b,), -5.0, dtype=torch.float32, device=DEV)
+                    ops.tensordot_device(TA, TB, k, one, b, e, torch.float32)
+                    assert torch.equal(got, one), (ra, rb, k, dim, b, e)
+        finally:
+            check(lib.st_set_tuning(b"sym22_min_dim", c_i64(96)))
+
+
 def test_outer_row_walk_kernel_agrees_with_the_per_component_unrank_kernels():
     """multiply.outer through the row-walk kernel (outer_rows_kernel: warp-uniform odometer over the rows that cover 32
     consecutive coordinates, half-split subset sums) against the kernel that unranks every component (outer_fast_kernel) and

@@ -43,3 +43,38 @@ def test_tile_lists_cover_every_output_range():
                 union |= got
             assert union == tiles_listed(dim, 0, total) == tiles_needed(dim, 0, total)
     assert tiles_listed(40, 64, 64) == set()
+
+
+def test_tile_lists_of_ranges_inside_the_small_classes_are_pruned_but_complete():
+    """Ranges that cut the classes with repeated indices (the two-range shards of sharding.tensordot22_shards): the list still
+    holds every tile that the range needs, and a narrow range no longer drags in every diagonal tile."""
+    rng = np.random.default_rng(5)
+    for dim in (17, 40):
+        tab = comb.class_table(4, dim)
+        off4 = tab.offsets[tab.ncls - 1]
+        cutsets = [sorted({0, off4} | {int(v) // 32 * 32 for v in rng.integers(0, off4, size=5)}) for _ in range(2)]
+        for cuts in cutsets:
+            for b, e in zip(cuts[:-1], cuts[1:]):
+                need, got = tiles_needed(dim, b, e), tiles_listed(dim, b, e)
+                assert need <= got, (dim, b, e, sorted(need - got)[:5])
+        if dim >= 40:
+            allt = tiles_listed(dim, 0, off4)
+            b = tab.offsets[3] + (tab.sizes[3] // 2) // 32 * 32  # a narrow window in the middle of class (2,1,1)
+            assert len(tiles_listed(dim, b, b + 64)) < len(allt)
+    import ctypes
+    for dim, world in ((40, 3), (33, 4)):
+        shards = sharding.tensordot22_shards(dim, world)
+        total = comb.class_table(4, dim).total
+        covered = sorted(r for sh in shards for r in sh if r[1] > r[0])
+        assert covered[0][0] == 0 and covered[-1][1] == total
+        assert all(a[1] <= b[0] and b[0] - a[1] < 32 for a, b in zip(covered[:-1], covered[1:]))  # disjoint; gaps: alignment padding
+        for sh in shards:  # the tile list of a shard (all its ranges in one call) holds what each of its ranges needs, once
+            n = len(sh)
+            bs, es = (ctypes.c_int64 * n)(*[r[0] for r in sh]), (ctypes.c_int64 * n)(*[r[1] for r in sh])
+            buf = np.zeros(1 << 16, dtype=np.uint64)
+            cnt = lib.st_debug_sym22_tiles_ranges(c_i64(dim), n, bs, es, buf.ctypes.data, c_i64(buf.size))
+            words = [int(w) for w in buf[:cnt]]
+            assert len(set(words)) == cnt
+            got = {(w & 0xffff, (w >> 16) & 0xffff, (w >> 32) & 0xffff, (w >> 48) & 0xffff) for w in words}
+            for b, e in sh:
+                assert tiles_needed(dim, b, e) <= got

@@ -35,13 +35,14 @@ def main():
     ap.add_argument("--shares", default="0,4")
     ap.add_argument("--kch", default="16,32")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--balanced", type=int, default=0, help="1: the tile-balanced cuts of sharding.tensordot22_bounds (what bench.py shards with)")
     ap.add_argument("--debug", default="0", help="ablation masks to time (sym22_debug): 1 no adds, 2 no drains, 4 no TMA, 8 no MMA")
     args = ap.parse_args()
     dim = args.dim
     A, B = device_tensor(3, dim, 1, torch.float32), device_tensor(3, dim, 2, torch.float32)
     af, bf = ops._flat_buffer(A, torch.float32), ops._flat_buffer(B, torch.float32)
     table = comb.class_table(4, dim)
-    cuts = sharding.shard_bounds(table.total, args.world)
+    cuts = sharding.tensordot22_bounds(dim, args.world) if args.balanced else sharding.shard_bounds(table.total, args.world)
     ws = None
     for dbg, kch in [(int(g), int(v)) for g in args.debug.split(",") for v in args.kch.split(",")]:
         check(lib.st_set_tuning(b"sym22_kch", c_i64(kch)))
