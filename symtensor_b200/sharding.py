@@ -205,33 +205,16 @@ def tensordot22_shards(dim: int, world: int, align: int = ALIGN) -> List[List[tu
             out.append((b, max(b, e)))
         return out
 
-    d_all = ntiles(small_ranges(0, dim))
-    acuts = [0]
-    for g in range(1, world):
-        target = d_all * g / world
-        lo, hi = acuts[-1], dim
-        while lo < hi:
-            mid = (lo + hi) // 2
-            if ntiles(small_ranges(0, mid)) >= target:
-                hi = mid
-            else:
-                lo = mid + 1
-        acuts.append(min(max(lo, acuts[-1]), dim))
-    acuts.append(dim)
-    small = [small_ranges(acuts[g], acuts[g + 1]) for g in range(world)]
-    n_small = [ntiles(r) for r in small]
-
-    # class (1,1,1,1): first component whose smallest index is i0 = (i0, i0+1, i0+2, i0+3), lexicographic rank
+    # class (1,1,1,1) first: cut where the first index enters a new block of 16 (a boundary inside a block would make both
+    # neighbours run the block's tiles), as even as that coarse grid allows
     def first_coord(i0):
         r = math.comb(dim, 4) - 1 - (math.comb(dim - 1 - i0, 4) + math.comb(dim - 2 - i0, 3) + math.comb(dim - 3 - i0, 2) + math.comb(dim - 4 - i0, 1))
         return off4 + r
     cands = sorted(set([off4] + [min(total, max(off4, first_coord(i0) // align * align)) for i0 in range(16, dim - 3, 16)] + [total]))
-    n_big = ntiles([(off4, total)])
-    per_gpu = (sum(n_small) + n_big) / world
     big = [off4]
     idx = 0
     for g in range(world - 1):
-        target = max(0.0, per_gpu - n_small[g])
+        target = ntiles([(big[-1], total)]) / (world - g)
         lo, hi = idx, max(idx, len(cands) - 1 - (world - 2 - g))
         a, b = lo, hi
         while a < b:
@@ -247,6 +230,26 @@ def tensordot22_shards(dim: int, world: int, align: int = ALIGN) -> List[List[tu
         big.append(cands[best])
         idx = best
     big.append(total)
+    n_big = [ntiles([(big[g], big[g + 1])]) for g in range(world)]
+
+    # then the intervals of a: GPU g gets the diagonal tiles that bring it to the common total (the grid of a is fine: dim values)
+    d_all = ntiles(small_ranges(0, dim))
+    per_gpu = (d_all + sum(n_big)) / world
+    want = [max(0.0, per_gpu - n) for n in n_big]
+    scale = d_all / max(sum(want), 1.0)
+    want = [w * scale for w in want]
+    acuts = [0]
+    for g in range(world - 1):
+        lo, hi = acuts[-1], dim
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if ntiles(small_ranges(acuts[-1], mid)) >= want[g]:
+                hi = mid
+            else:
+                lo = mid + 1
+        acuts.append(min(max(lo, acuts[-1]), dim))
+    acuts.append(dim)
+    small = [small_ranges(acuts[g], acuts[g + 1]) for g in range(world)]
     return [[r for r in small[g] if r[1] > r[0]] + ([(big[g], big[g + 1])] if big[g + 1] > big[g] else []) for g in range(world)]
 
 
