@@ -253,39 +253,52 @@ def tensordot22_shards(dim: int, world: int, align: int = ALIGN) -> List[List[tu
     return [[r for r in small[g] if r[1] > r[0]] + ([(big[g], big[g + 1])] if big[g + 1] > big[g] else []) for g in range(world)]
 
 
+def mat_mode_work(rank: int, dim: int) -> List[float]:
+    """Tensor-pipe work of the matrix contraction's mode chain per value j1 of the FIRST output mode, in tiles of 64 rows x 8
+    columns x dim: step k multiplies, for every row J = (j1 <= ... <= jk) and every tile of 64 I, only the 8-column blocks
+    that hold a column j >= jk (st_mat.cu), so the work of a slice is far from proportional to SURVEY.md 8d's flop count (all
+    dim columns for every J), which round 1 balanced.  Step 0 (J empty) is charged per column."""
+    import math
+
+    def flat(k):
+        return math.comb(dim + k - 1, k) if k > 0 else 1
+
+    def count(j1, jl, k):  # sorted k-tuples over range(dim) that start with j1 and end with jl
+        if k == 1:
+            return 1 if jl == j1 else 0
+        return math.comb(jl - j1 + k - 2, k - 2) if jl >= j1 else 0
+    nblk_all = (dim + 7) // 8
+    work = []
+    for j1 in range(dim):
+        c = math.ceil(flat(rank - 1) / 64) / 8.0 if rank >= 1 else 0.0
+        for k in range(1, rank):
+            m = rank - k - 1
+            tiles = math.ceil(flat(m) / 64) if m > 0 else 1.0 / 64
+            c += tiles * sum(count(j1, jl, k) * (nblk_all - jl // 8) for jl in range(j1, dim))
+        work.append(c)
+    return work
+
+
 def mat_mode_bounds(rank: int, dim: int, world: int) -> List[int]:
     """Cut points ``j_0 = 0 < j_1 < ... < j_world = dim`` of the FIRST output mode for the matrix contraction on ``world`` GPUs
     (``ops.contract_mat_device``): GPU g computes the output components whose smallest index lies in ``[j_g, j_{g+1})``.  Balanced
-    by the flops of the slice's mode chain: step k does 2 d rows_k(range) C(d + r - k - 2, r - k - 1) d flops, where rows_k counts
-    the sorted k-tuples whose first element is in the range (step 0: d times the width of the range).  Pure host arithmetic."""
-    import math
+    by the tensor-pipe work the slice's mode chain actually does (``mat_mode_work``).  Pure host arithmetic."""
     if world < 1:
         raise ValueError("world must be >= 1")
-
-    def below(k, v):  # sorted k-tuples over range(dim) whose first element is < v
-        if k == 0:
-            return 1 if v > 0 else 0
-        return math.comb(dim + k - 1, k) - math.comb(dim - v + k - 1, k)
-
-    def cost(v):  # chain flops for the first mode in [0, v)
-        c = 0
-        for k in range(rank):
-            rows = v if k == 0 else below(k, v) * dim
-            c += rows * math.comb(dim + rank - k - 2, rank - k - 1)
-        return c
-    total = cost(dim)
+    if rank < 1 or dim < 1:
+        return [0] + [dim] * world
+    work = mat_mode_work(rank, dim)
+    total = sum(work)
     cuts = [0]
+    acc = 0.0
+    j = 0
     for g in range(1, world):
         target = total * g / world
-        lo, hi = cuts[-1], dim
-        while lo < hi:
-            mid = (lo + hi) // 2
-            if cost(mid) >= target:
-                hi = mid
-            else:
-                lo = mid + 1
-        v = lo
-        if v > cuts[-1] + 1 and abs(cost(v - 1) - target) < abs(cost(v) - target):
-            v -= 1
-        cuts.append(min(max(v, cuts[-1]), dim))
+        while j < dim and acc + work[j] < target:
+            acc += work[j]
+            j += 1
+        if j < dim and abs(acc + work[j] - target) < abs(acc - target):
+            acc += work[j]
+            j += 1
+        cuts.append(max(j, cuts[-1]))
     return cuts + [dim]
