@@ -16,7 +16,7 @@ from . import combinatorics as comb
 from ._cabi import LAYOUT_FLAT, c_i64, check, lib
 from .base import SymmetricTensor
 from .elementwise import PackedElementwise
-from .permcls import _TORCH2NP, _is_host, _kernel_dtype, _stream_ptr, pack_dense_device, to_torch_dtype, unpack_dense_device
+from .permcls import _TORCH2NP, _gpu_for_host, _is_host, _kernel_dtype, _stream_ptr, pack_dense_device, to_torch_dtype, unpack_dense_device
 
 
 class CudaFlatSymmetricTensor(PackedElementwise, SymmetricTensor):
@@ -50,6 +50,13 @@ class CudaFlatSymmetricTensor(PackedElementwise, SymmetricTensor):
         if self.rank and not self._host and _kernel_dtype(self._tdtype):  # CUDA pack kernel
             if not pack_dense_device(LAYOUT_FLAT, self.rank, self.dim, dense, self._buf, symmetrize):
                 raise RuntimeError("data is not symmetric")
+            return
+        gpu = _gpu_for_host() if self.rank and _kernel_dtype(self._tdtype) else None
+        if gpu is not None:  # host-resident tensor: pack on the device, keep the packed buffer on the host
+            tmp = torch.zeros(n, dtype=self._tdtype, device=gpu)
+            if not pack_dense_device(LAYOUT_FLAT, self.rank, self.dim, dense.to(gpu), tmp, symmetrize):
+                raise RuntimeError("data is not symmetric")
+            self._buf.copy_(tmp)
             return
         idx = self._rep_index_tensor()
         if symmetrize:
@@ -132,6 +139,9 @@ class CudaFlatSymmetricTensor(PackedElementwise, SymmetricTensor):
             return self._buf.reshape(()).clone()
         if not self._host and _kernel_dtype(self._tdtype):
             return unpack_dense_device(LAYOUT_FLAT, self.rank, self.dim, self._buf)
+        gpu = _gpu_for_host() if _kernel_dtype(self._tdtype) else None
+        if gpu is not None:  # host-resident tensor: unpack on the device
+            return unpack_dense_device(LAYOUT_FLAT, self.rank, self.dim, self._buf.to(gpu)).cpu()
         dense = torch.zeros(self.shape, dtype=self._tdtype, device=self.device)
         idx = self._rep_index_tensor()
         for p in itertools.permutations(range(self.rank)):

@@ -18,7 +18,7 @@ import ctypes
 import itertools
 import math
 from numbers import Number
-from typing import Dict, Iterable, Tuple
+from typing import Optional, Dict, Iterable, Tuple
 
 import numpy as np
 import torch
@@ -89,6 +89,13 @@ def unpack_dense_device(layout: int, rank: int, dim: int, buf: torch.Tensor) -> 
 
 def _kernel_dtype(tdt: torch.dtype) -> bool:
     return tdt in (torch.float32, torch.float64)
+
+
+def _gpu_for_host() -> Optional[torch.device]:
+    """Host-resident tensors run their dense <-> packed conversions on the GPU as well (copy in, kernel, copy out) whenever a
+    device exists; the index-gather loops below them are the container logic for machines WITHOUT any CUDA device (the CPU
+    test-suite of the host logic) -- no contraction runs there."""
+    return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
 
 
 class CudaPermClsSymmetricTensor(PackedElementwise, SymmetricTensor):
@@ -215,6 +222,13 @@ class CudaPermClsSymmetricTensor(PackedElementwise, SymmetricTensor):
             if not pack_dense_device(LAYOUT_PERMCLS, self.rank, self.dim, dense, self._buf, symmetrize):
                 raise ValueError("Data array is not symmetric.")
             return
+        gpu = _gpu_for_host() if _kernel_dtype(self._tdtype) else None
+        if gpu is not None:  # host-resident tensor: pack on the device, keep the packed buffer on the host
+            tmp = torch.zeros(self._buf.numel(), dtype=self._tdtype, device=gpu)
+            if not pack_dense_device(LAYOUT_PERMCLS, self.rank, self.dim, dense.to(gpu), tmp, symmetrize):
+                raise ValueError("Data array is not symmetric.")
+            self._buf.copy_(tmp)
+            return
         perms = list(itertools.permutations(range(self.rank)))
         for c in self._table.classes:
             if len(c) > self.dim:
@@ -319,6 +333,9 @@ class CudaPermClsSymmetricTensor(PackedElementwise, SymmetricTensor):
                     check(fn(self.rank, c_i64(self.dim), self._buf.data_ptr(), flat.data_ptr(), _stream_ptr(self.device)))
                 return unpack_dense_device(1, self.rank, self.dim, flat)
             return unpack_dense_device(LAYOUT_PERMCLS, self.rank, self.dim, self._buf)
+        gpu = _gpu_for_host() if _kernel_dtype(self._tdtype) else None
+        if gpu is not None:  # host-resident tensor: unpack on the device
+            return unpack_dense_device(LAYOUT_PERMCLS, self.rank, self.dim, self._buf.to(gpu)).cpu()
         dense = torch.zeros(self.shape, dtype=self._tdtype, device=self.device)
         perms = list(itertools.permutations(range(self.rank)))
         for c in self._table.classes:

@@ -132,3 +132,28 @@ def test_dense_round_trip_at_a_size_beyond_the_oracle():
     assert torch.equal(dense, dense.permute(3, 1, 0, 2)) and torch.equal(dense, dense.permute(1, 2, 3, 0))
     B = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=dense, device=DEV)
     assert torch.equal(B.packed, A.packed)
+
+
+def test_host_resident_tensors_pack_and_unpack_through_the_gpu_kernels():
+    """device="host" tensors (the end-to-end path with host buffers) run todense / the constructor from a dense array through
+    the same CUDA kernels (copy in, kernel, copy out) -- the index-gather loops in permcls.py / flat.py are only reached on a
+    machine without any CUDA device: the launch counter of the library grows and the results equal the device-resident ones."""
+    rng = np.random.default_rng(77)
+    for rank, dim in [(3, 6), (4, 5), (2, 9)]:
+        data = rand_packed(rank, dim, rng)
+        ref = do.todense(data, rank, dim)
+        n0 = lib.st_launch_count()
+        H = st.PermClsTorchSymmetricTensor(rank=rank, dim=dim, data=data, device="host")
+        dense = H.todense()
+        assert dense.device.type == "cpu" and np.array_equal(dense.numpy(), ref)
+        assert lib.st_launch_count() > n0
+        n1 = lib.st_launch_count()
+        H2 = st.PermClsTorchSymmetricTensor(data=ref, device="host")
+        assert lib.st_launch_count() > n1
+        assert all(np.array_equal(H2.to_numpy_dict()[c], data[c]) for c in data)
+        bad = ref.copy()
+        bad[(0,) * (rank - 1) + (1,)] += 1.0
+        with pytest.raises(ValueError, match="not symmetric"):
+            st.PermClsTorchSymmetricTensor(data=bad, device="host")
+        F = st.FlatSymmetricTensor(rank, dim, data=ref, device="host")
+        assert np.array_equal(F.todense().numpy(), ref)
