@@ -40,7 +40,7 @@ constexpr int NCONS = 256 * NGROUP, NPROD = 128, NTHREADS = NCONS + NPROD;
 constexpr int STAGES = 2;                      // operand tiles in the ring (two CTAs per SM: W + 2 tiles = 104 KB each)
 constexpr int CTAS_PER_SM = 2;
 constexpr int CH = 8;                          // items per claim
-constexpr int kSmemBytes = ((1 + STAGES) * TA * LD) * 8 + 512;
+constexpr int kSmemBytes = ((1 + STAGES) * TA * LD) * 8 + 512 + ST_MAX_RANK * TA * 4;  // + the rank terms of the on-the-fly gather map
 
 struct Desc {
   long long i0;        // first row I of the tile
@@ -112,7 +112,11 @@ __device__ __forceinline__ void tile_mma(const double* __restrict__ ap, const do
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mat_pipe_kernel(PlanView P, int k, const double* __restrict__ Tk, const double* __restrict__ W,
+// ONFLY: no gather map in memory -- the producers rank sort(a, I) themselves (step 0, whose map would be used exactly once:
+// 2.8 GB written and read back at rank 6 dim 64): one unrank of the thread's I per tile, then
+// rank = base - PS[p] - F[m-p][a] with p = #{q: I[q] <= a} growing along the thread's ascending a (see mat_index_kernel).
+template <bool ONFLY>
+__global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mat_pipe_kernel(PlanView P, int k, int m, const double* __restrict__ Tk, const double* __restrict__ W,
                                                                double* __restrict__ Tn, long long nJ, long long nI, long long nI1,
                                                                const int32_t* __restrict__ tbl, long long rlo, int clo, int chi,
                                                                unsigned long long* __restrict__ counter) {
@@ -122,11 +126,18 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mat_pipe_kernel(PlanVie
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(Ss + STAGES * TA * LD);  // full[STAGES], empty[STAGES]
   Desc* desc = reinterpret_cast<Desc*>(bars + 2 * STAGES);       // [STAGES]
   long long* s_claim = reinterpret_cast<long long*>(desc + STAGES);  // [2]
+  int32_t* Fm = reinterpret_cast<int32_t*>(smem_raw + ((1 + STAGES) * TA * LD) * 8 + 512);  // [m + 1][TA]: F[t][v] = C(d-1+t-v, t+1)
   const int d = (int)P.dim;
   const int tid = threadIdx.x;
   for (int e = tid; e < TA * LD; e += NTHREADS) {
     const int a = e / LD, j = e % LD;
     Ws[e] = (a < d && j < d) ? W[a * d + j] : 0.0;
+  }
+  if (ONFLY) {
+    for (int e = tid; e < (m + 1) * TA; e += NTHREADS) {
+      const int t = e / TA, v = e % TA;
+      Fm[e] = v < d ? (int32_t)binom_at(P.binom, P.rank, d - 1 + t - v, t + 1) : 0;
+    }
   }
   if (tid == 0) {
     for (int b = 0; b < STAGES; ++b) {
@@ -163,10 +174,34 @@ __global__ void __launch_bounds__(NTHREADS, CTAS_PER_SM) mat_pipe_kernel(PlanVie
     };
     // gather-map entries of an item's column: issued a whole tile ahead, so that their latency overlaps the wait for the stage
     int32_t idx[PER];
+    const int32_t gbase = ONFLY ? (int32_t)(binom_at(P.binom, P.rank, d + m, m + 1) - 1) : 0;
     auto load_idx = [&](long long wi) {
       if (wi >= total) return;
       const long long jrel = wi / tilesI, i0 = (wi - jrel * tilesI) * TI;
       const bool rvalid = i0 + r < nI;
+      if (ONFLY) {
+        int32_t I[ST_MAX_RANK];
+        int32_t ps = 0;
+        if (rvalid) {
+          flat_unrank_r(P, i0 + r, m, I);
+          for (int q = 0; q < m; ++q) ps += Fm[(m - 1 - q) * TA + I[q]];
+        }
+        int p = 0;
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+          const int a = AQ * u + aq;
+          if (rvalid && a < d) {
+            while (p < m && I[p] <= a) {
+              ps += Fm[(m - p) * TA + I[p]] - Fm[(m - 1 - p) * TA + I[p]];
+              ++p;
+            }
+            idx[u] = gbase - ps - Fm[(m - p) * TA + a];
+          } else {
+            idx[u] = -1;
+          }
+        }
+        return;
+      }
       const int32_t* __restrict__ tcol = tbl + i0 + r;
 #pragma unroll
       for (int u = 0; u < PER; ++u) {
@@ -275,18 +310,24 @@ static unsigned long long* counter_for(cudaStream_t stream) {
   return p;
 }
 
-// launches one step through the pipeline kernel; false (nothing enqueued): shape not covered (dim > 64, no gather map)
-bool launch_step(const PlanView& P, int k, const double* Tk, const double* W, double* Tn, int64_t nJ, int64_t nI, int64_t nI1, const int32_t* tbl,
-                 int64_t rlo, int clo, int chi, cudaStream_t stream) {
-  if (P.dim > TA || !tbl || nI < 1 || nJ < 1) return false;
+// launches one step through the pipeline kernel (tbl == nullptr: the producers rank the gathers themselves); false (nothing
+// enqueued): shape not covered (dim > 64, positions beyond int32)
+bool launch_step(const PlanView& P, int k, int m, const double* Tk, const double* W, double* Tn, int64_t nJ, int64_t nI, int64_t nI1,
+                 const int32_t* tbl, int64_t rlo, int clo, int chi, cudaStream_t stream) {
+  if (P.dim > TA || nI < 1 || nJ < 1 || m < 1 || nI1 >= 2147483647LL) return false;
+  const bool onfly = tbl == nullptr;
   unsigned long long* ctr = counter_for(stream);
   if (!ctr) return false;
-  if (set_max_dynamic_smem(reinterpret_cast<const void*>(mat_pipe_kernel), kSmemBytes) != ST_OK) return false;
+  const void* fn = onfly ? reinterpret_cast<const void*>(mat_pipe_kernel<true>) : reinterpret_cast<const void*>(mat_pipe_kernel<false>);
+  if (set_max_dynamic_smem(fn, kSmemBytes) != ST_OK) return false;
   cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream);
   const int64_t tilesI = (nI + TI - 1) / TI;
   const int64_t chunks = (nJ * tilesI + CH - 1) / CH;
   const int grid = (int)std::min<int64_t>(chunks, (int64_t)sm_count() * CTAS_PER_SM);
-  mat_pipe_kernel<<<grid, NTHREADS, kSmemBytes, stream>>>(P, k, Tk, W, Tn, (long long)nJ, (long long)nI, (long long)nI1, tbl, (long long)rlo, clo, chi, ctr);
+  if (onfly)
+    mat_pipe_kernel<true><<<grid, NTHREADS, kSmemBytes, stream>>>(P, k, m, Tk, W, Tn, (long long)nJ, (long long)nI, (long long)nI1, tbl, (long long)rlo, clo, chi, ctr);
+  else
+    mat_pipe_kernel<false><<<grid, NTHREADS, kSmemBytes, stream>>>(P, k, m, Tk, W, Tn, (long long)nJ, (long long)nI, (long long)nI1, tbl, (long long)rlo, clo, chi, ctr);
   return true;
 }
 

@@ -1278,10 +1278,14 @@ static int64_t mat_range_elems(const HostPlan* hp, int rank, int64_t jlo, int64_
 
 // st_mat.cu: persistent producer / consumer pipeline for one step (fp64, dim <= 64, gather map present)
 namespace matpipe {
-bool launch_step(const PlanView& P, int k, const double* Tk, const double* W, double* Tn, int64_t nJ, int64_t nI, int64_t nI1, const int32_t* tbl,
-                 int64_t rlo, int clo, int chi, cudaStream_t stream);
+bool launch_step(const PlanView& P, int k, int m, const double* Tk, const double* W, double* Tn, int64_t nJ, int64_t nI, int64_t nI1,
+                 const int32_t* tbl, int64_t rlo, int clo, int chi, cudaStream_t stream);
 }
 int g_mat_pipe = 1;  // (0: the first DMMA kernel for every step; test hook "mat_pipe")
+// steps with at most this many rows J rank their gathers in the producers instead of building a map ("mat_onfly_rows").  Off by
+// default: at BASELINE config 4 step 0 took 7.8 ms that way against 2.9 (map) + 3.3 ms -- the per-tile unrank of every column
+// makes the producers the bottleneck.  The path also serves steps whose map would not fit the workspace.
+int64_t g_mat_onfly_rows = 0;
 
 // C = (W^T)^{(x) r} . A restricted to the output components whose FIRST (smallest) mode j1 lies in [jlo, jhi): the flat
 // range [rows_below(r, jlo), rows_below(r, jhi)) of the output, written to d_out_slice (which starts at that position).
@@ -1330,10 +1334,14 @@ static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, 
         const dim3 lgrid((unsigned)((nJ + 63) / 64), (unsigned)((dim + 63) / 64));
         mat_last_dmma_kernel<<<lgrid, 256, 0, stream>>>(P, k, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
                                                        reinterpret_cast<double*>(dst), rhi, rlo);
+      } else if (g_mat_pipe && (nJ <= g_mat_onfly_rows || tb == 0) && dim <= 64 &&
+                 matpipe::launch_step(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W), reinterpret_cast<double*>(dst),
+                                      nJ, nI, nI1, nullptr, rlo, clo, chi, stream)) {
+        // (few rows J -- step 0: the gather map would be used about once; the producers rank the gathers themselves)
       } else if (tb > 0) {
         mat_index_kernel<<<(unsigned)((nI + 255) / 256), 256, 0, stream>>>(P, m, nI, tbl);
         count_launch();
-        if (!g_mat_pipe || !matpipe::launch_step(P, k, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
+        if (!g_mat_pipe || !matpipe::launch_step(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
                                                  reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, rlo, clo, chi, stream))
           mat_step_dmma_kernel<true><<<sgrid, 256, 0, stream>>>(P, k, m, reinterpret_cast<const double*>(src), reinterpret_cast<const double*>(d_W),
                                                                 reinterpret_cast<double*>(dst), nJ, nI, nI1, tbl, NT, rlo, clo, chi);

@@ -727,6 +727,7 @@ unsigned long long* g_timeline = nullptr;  // debug: device buffer of kTimelineS
 static const size_t kTimelineSlots = 148 * 16 + 4096 + 4096 * 8;
 int g_ring_direct = 1;                 // ring kernel: allow the table-free pair walk (2: with vec_force_tau 2, force it)
 int64_t g_ring_table_max = 72 * 1024;  // ring kernel: largest tail table in bytes before the pair walk takes over
+extern int64_t g_mat_onfly_rows;
 extern int g_mat_dmma, g_mat_pipe, g_conv_rows, g_outer_fast, g_outer_rows, g_gram_umma, g_sym22;  // st_ops.cu
 extern int64_t g_sym22_min_dim;
 namespace s22 { extern int g_kch, g_debug; }  // st_sym22.cu
@@ -1416,6 +1417,7 @@ int st_set_tuning(const char* key, int64_t value) {
   const std::string k(key);
   if (k == "mat_dmma" && (value == 0 || value == 1)) { g_mat_dmma = (int)value; return ST_OK; }
   if (k == "mat_pipe" && (value == 0 || value == 1)) { g_mat_pipe = (int)value; return ST_OK; }
+  if (k == "mat_onfly_rows" && value >= 0) { g_mat_onfly_rows = value; return ST_OK; }
   if (k == "conv_rows" && (value == 0 || value == 1)) { g_conv_rows = (int)value; return ST_OK; }
   if (k == "outer_fast" && (value == 0 || value == 1)) { g_outer_fast = (int)value; return ST_OK; }
   if (k == "outer_rows" && (value == 0 || value == 1)) { g_outer_rows = (int)value; return ST_OK; }

@@ -321,8 +321,16 @@ def test_matrix_pipeline_kernel_agrees_with_the_first_dmma_kernel():
             C0 = st.contract_all_indices_with_matrix(TA, W).packed.clone()
         finally:
             check(lib.st_set_tuning(b"mat_pipe", c_i64(1)))
-        C1 = st.contract_all_indices_with_matrix(TA, W).packed
+        C1 = st.contract_all_indices_with_matrix(TA, W).packed.clone()
         assert torch.allclose(C0, C1, rtol=1e-13, atol=1e-13), (rank, dim)
+        # gather positions ranked by the producers (default: only steps whose map does not fit) against the gather maps
+        for rows in (1, 1 << 40):
+            try:
+                check(lib.st_set_tuning(b"mat_onfly_rows", c_i64(rows)))
+                C2 = st.contract_all_indices_with_matrix(TA, W).packed
+                assert torch.equal(C1, C2), (rank, dim, rows)
+            finally:
+                check(lib.st_set_tuning(b"mat_onfly_rows", c_i64(0)))
 
 
 def test_tensordot_several_output_ranges_in_one_call_equal_the_single_range_calls():

@@ -1,1 +1,3 @@
-timeout 1500 python -m pytest tests/test_gpu_ops.py tests/test_gpu_configs.py -x -q -m gpu -k "several_output_ranges or shard_of_an_8" > gpurun_out/r2d_pytest_tdot.log 2>&1; tail -4 gpurun_out/r2d_pytest_tdot.log
+timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_configs.py tests/test_gpu_pack.py -x -q -m gpu -k "matrix or config4 or host_resident" > gpurun_out/r2b_pytest_mat.log 2>&1; tail -3 gpurun_out/r2b_pytest_mat.log
+timeout 300 python tools/bench_ops.py mat > gpurun_out/r2d_mat_plain.log 2>&1; tail -1 gpurun_out/r2d_mat_plain.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 15 --csv --log-file gpurun_out/r2d_mat_launches.csv python tools/bench_ops.py mat > gpurun_out/r2b_mat_ncu.log 2>&1
