@@ -110,12 +110,17 @@ def config4(dev, world, rank, dist, peaks):
         what = f"partition by the first output mode over {world} GPUs (cuts {cuts}); the result stays sharded"
     peak = 40.0
     ach = flops / world / (ms * 1e-3) / 1e12 if world > 1 else flops / (ms * 1e-3) / 1e12
+    # what the kernels multiply: only the 8-column blocks that hold a column j >= max(J) (sharding.mat_mode_work, in tiles of
+    # 64 rows x 8 columns x dim) -- a third of SURVEY.md 8d's count, which charges all dim columns for every J
+    mult = sum(sharding.mat_mode_work(r, dim)) * 64 * 8 * dim * 2
     return {"workload": f"contract_all_indices_with_matrix rank {r} dim {dim} fp64, W {dim} x {dim} (BASELINE configs[3]); " + what,
             "packed_components": n, "ms": ms, "value": n / (ms * 1e-3), "unit": "packed components/s", "kernel_launches": launches,
             "roofline": {"bound": "fp64 tensor pipe", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                          "peak_source": "nominal B200 FP64 (DMMA) rate, 40 TFLOP/s (tcgen05 has no f64 kind; MEASURED_PEAKS.json has no fp64 entry)",
-                         "kernel": "mat_step_dmma_kernel / mat_last_dmma_kernel (mma.sync m8n8k4 f64 mode chain); algorithmic flops 2.534e12 (SURVEY.md 8d)"
-                                   + ("; per-GPU average of the partition" if world > 1 else "")}}
+                         "kernel": "mat_pipe_kernel / mat_last_dmma_kernel (persistent cp.async producer / DMMA consumer pipeline, mma.sync m8n8k4 f64 "
+                                   "mode chain); algorithmic flops 2.534e12 (SURVEY.md 8d: all dim columns for every J)"
+                                   + ("; per-GPU average of the partition" if world > 1 else ""),
+                         "flops_multiplied": mult, "achieved_multiplied_tflops": mult / world / (ms * 1e-3) / 1e12}}
 
 
 def config5(dev, world, rank, dist, peaks):
@@ -160,20 +165,28 @@ def config5(dev, world, rank, dist, peaks):
     ms_fused, l3 = _timed(fused_step, 2, 1, d)
     fused = float(fres[0])
     xa = float(ops._contract_all_indices_with_vector(A, x)) * float(ops._contract_all_indices_with_vector(B, x))
-    peak = peaks["hbm_gbs"]
-    ach = n * 4 / world / (ms_outer * 1e-3) / 1e9
+    # The kernel writes 4 B per component and does 70 products of two GATHERED operand entries for it (the operands, 494 KB
+    # each, live in L1 / L2): its ceiling is the rate at which an SM's load pipe takes warp-wide loads -- one instruction (32
+    # lanes) per clock per SM when the lanes fall into one or two cache lines, which consecutive components mostly do.
+    sms, clk = torch.cuda.get_device_properties(dev).multi_processor_count, 1.965e9
+    peak = sms * clk * 32 / 1e9
+    ach = 140.0 * n / world / (ms_outer * 1e-3) / 1e9
     return {"workload": f"multiply.outer rank 4 (x) rank 4 dim {dim} fp32 -> rank 8, then contract_all_indices_with_vector (BASELINE configs[4]); "
                         + ("one GPU" if world == 1 else f"output range sharded over {world} GPUs, scalar all-reduce after the vector contraction"),
             "packed_components": n, "ms_outer": ms_outer, "ms_vector": ms_vec, "ms_fused_outer_vector": ms_fused,
             "ms": ms_outer + ms_vec, "value": n / ((ms_outer + ms_vec) * 1e-3), "unit": "packed components/s",
-            "value_fused": n / (ms_fused * 1e-3), "gathers_per_s": 70.0 * n / (ms_outer * 1e-3),
+            "value_fused": n / (ms_fused * 1e-3), "gathers_per_s": 140.0 * n / (ms_outer * 1e-3),
+            "hbm_written_gbs_per_gpu": n * 4 / world / (ms_outer * 1e-3) / 1e9,
             "result_unfused": unfused, "result_fused": fused, "identity_(A.x^4)(B.x^4)": xa,
             "rel_err_unfused": abs(unfused - xa) / abs(xa), "rel_err_fused": abs(fused - xa) / abs(xa),
             "kernel_launches": l1 + l2 + l3,
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks["measured"] else "fallback of B200_PROFILING.md",
-                         "kernel": "outer_fast_kernel<float,4,4> (algorithmic bytes: 4 B written per output component, per GPU; the real work is "
-                                   "70 gathered FMAs per component from the L1/L2-resident operands -- see gathers_per_s)"}}
+            "roofline": {"bound": "l1 load pipe (gathered operand loads)", "achieved": ach, "peak": peak, "unit": "G lane-loads/s", "frac": ach / peak,
+                         "traffic": None,
+                         "peak_source": f"{sms} SMs x 1.965 GHz x 32 lanes: one warp-wide load per clock per SM (B300_MICROARCH.md); HBM is not the bound -- "
+                                        "4 B are written per component (hbm_written_gbs_per_gpu)",
+                         "kernel": "outer_rows_kernel<float,4,4> (warp-uniform row walk, lanes decode their component, 70 products = 140 gathered "
+                                   "operand loads per output component; ncu: 37 warp instructions per component, issue slots 56 % busy, "
+                                   "profiles/r2_outer_rows_ncu_full.txt)"}}
 
 
 def cpu_legs():

@@ -1,3 +1,12 @@
-timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_configs.py tests/test_gpu_pack.py -x -q -m gpu -k "matrix or config4 or host_resident" > gpurun_out/r2b_pytest_mat.log 2>&1; tail -3 gpurun_out/r2b_pytest_mat.log
-timeout 300 python tools/bench_ops.py mat > gpurun_out/r2d_mat_plain.log 2>&1; tail -1 gpurun_out/r2d_mat_plain.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 15 --csv --log-file gpurun_out/r2d_mat_launches.csv python tools/bench_ops.py mat > gpurun_out/r2b_mat_ncu.log 2>&1
+timeout 2400 python -m pytest tests -x -q -m gpu > gpurun_out/r2e_pytest_all.log 2>&1; tail -4 gpurun_out/r2e_pytest_all.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 1200 python bench.py > gpurun_out/r2e_bench_n1.json 2> gpurun_out/r2e_bench_n1.err; tail -c 300 gpurun_out/r2e_bench_n1.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2e_bench_ref.json 2> gpurun_out/r2e_bench_ref.err; tail -c 400 gpurun_out/r2e_bench_ref.json
+python - <<'P'
+import json
+d=json.loads(open('gpurun_out/r2e_bench_n1.json').read().strip().splitlines()[-1])
+print(d['ms_per_step'], d['roofline']['frac'], d['e2e']['value'], d['steps'], d['warmup'])
+for k in ('config3','config4','config5'):
+    c=d.get(k,{})
+    print(k, {kk:c.get(kk) for kk in ('ms','ms_outer','ms_fused_outer_vector','value','error')}, (c.get('roofline') or {}).get('frac'))
+P
