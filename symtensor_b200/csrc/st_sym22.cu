@@ -566,6 +566,8 @@ static int64_t rank1111(const HostPlan* hp, int64_t base, int64_t a, int64_t b, 
 // tiles (p, q, r, s) that can hold components of [begin, end); s runs fastest so that the CTAs working side by side
 // share the (i, j), (i, k) and (j, k) operand boxes in L2.  Pure host arithmetic (tests/test_cabi.py checks it against a
 // brute-force enumeration through st_debug_sym22_tiles).
+int g_tile_rgroup = 1;  // tiles of this many consecutive k blocks are interleaved in the list (1: s fastest); tuning key "sym22_rgroup"
+
 void build_tiles(const HostPlan* hp, const std::vector<std::pair<int64_t, int64_t>>& ranges, std::vector<unsigned long long>& tiles) {
   const int64_t d = hp->dim;
   const int64_t off4 = hp->h_cls[hp->ncls - 1].offset;
@@ -633,7 +635,25 @@ void build_tiles(const HostPlan* hp, const std::vector<std::pair<int64_t, int64_
       }
     }
   }
-  // (generation order: s runs fastest, so the CTAs working side by side share the three column boxes (i, j), (i, k), (j, k))
+  // Order.  Generated with s fastest, the CTAs working side by side share the three column boxes (p, q), (p, r), (q, r) but every
+  // one of their row boxes (r, s), (q, s), (p, s) is its own (6 MB per tile from HBM; the GEMM kernel reads 3.6 TB/s of DRAM
+  // with the tensor pipe 72 % busy).  Interleaving groups of consecutive r (same p, q) s-major -- neighbours then share (q, s)
+  // and (p, s) and differ in the column boxes of r -- was measured and is SLOWER: 515 ms (s fastest) / 519 / 549 / 568 / 576 ms for
+  // groups of 2 / 4 / 8 / 16 on 1/8 of BASELINE config 3; the column boxes are twice the size of the row boxes.  Kept as a knob.
+  if (g_tile_rgroup > 1) {
+    const unsigned long long G = (unsigned long long)g_tile_rgroup;
+    auto key = [G](unsigned long long w) {
+      const unsigned long long p = w & 0xffff, q = (w >> 16) & 0xffff, r = (w >> 32) & 0xffff, sidx = (w >> 48) & 0xffff;
+      return std::make_tuple(p, q, r / G, sidx, r);
+    };
+    std::stable_sort(tiles.begin(), tiles.end(), [&](unsigned long long a, unsigned long long b) { return key(a) < key(b); });
+  }
+}
+
+void clear_tile_cache() {
+  std::lock_guard<std::mutex> lk(g_tmu);
+  for (auto& kv : g_tiles) cudaFree(kv.second.d);
+  g_tiles.clear();
 }
 
 static int get_tiles(const HostPlan* hp, const std::vector<std::pair<int64_t, int64_t>>& ranges, TileList* out) {

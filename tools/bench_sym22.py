@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--shares", default="0,4")
     ap.add_argument("--kch", default="16,32")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--rgroup", default="", help="values of the tile-order key sym22_rgroup to time (default: the library's)")
     ap.add_argument("--balanced", type=int, default=0, help="1: the tile-balanced cuts of sharding.tensordot22_bounds (what bench.py shards with)")
     ap.add_argument("--debug", default="0", help="ablation masks to time (sym22_debug): 1 no adds, 2 no drains, 4 no TMA, 8 no MMA")
     args = ap.parse_args()
@@ -44,7 +45,11 @@ def main():
     table = comb.class_table(4, dim)
     cuts = sharding.tensordot22_bounds(dim, args.world) if args.balanced else sharding.shard_bounds(table.total, args.world)
     ws = None
-    for dbg, kch in [(int(g), int(v)) for g in args.debug.split(",") for v in args.kch.split(",")]:
+    for rg, dbg, kch in [(r, int(g), int(v)) for r in (args.rgroup.split(",") if args.rgroup else [""]) for g in args.debug.split(",")
+                         for v in args.kch.split(",")]:
+        if rg:
+            check(lib.st_set_tuning(b"sym22_rgroup", c_i64(int(rg))))
+            print("tile order: groups of", rg, "k blocks")
         check(lib.st_set_tuning(b"sym22_kch", c_i64(kch)))
         check(lib.st_set_tuning(b"sym22_debug", c_i64(dbg)))
         print("ablation mask", dbg)
