@@ -51,6 +51,7 @@ constexpr int NTHREADS = 384;
 constexpr int CHAIN_K = 256;  // products per TMEM accumulation chain
 constexpr int SMEM_STAGE_BUDGET = 192 * 1024;
 constexpr int64_t kBatchTiles = 32768;  // tiles per launch: their slots (4 GB) are the scratch part of the workspace
+int64_t g_batch_tiles = kBatchTiles;    // (tests lower it -- key "sym22_batch_tiles" -- to run several batches at small sizes; the workspace is sized for kBatchTiles)
 
 template <int KCH>
 struct Geo {
@@ -764,8 +765,11 @@ int tensordot_sym22_ranges(int k, int64_t dim, const float* d_a_flat, const floa
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   float* scratch = x + 4 * n1;
   const int64_t nbj = (dim + BJ - 1) / BJ, nbl = (dim + BL - 1) / BL;
-  const int64_t cap = std::min<int64_t>(kBatchTiles, nbj * nbj * nbj * nbl);
-  // batches of tiles: GEMM kernel into the slots, then the scatter of the slots into the packed output (same stream)
+  const int64_t cap = std::min<int64_t>(std::min<int64_t>(g_batch_tiles, kBatchTiles), nbj * nbj * nbj * nbl);
+  // batches of tiles: GEMM kernel into the slots, then the scatter of the slots into the packed output (same stream).
+  // (Measured in round 2: the scatter of a batch on a side stream, beside the GEMMs of the next batch and into a second slot
+  // buffer, does not help -- 506 ms against 500 ms on 1/8 of BASELINE config 3: the GEMM kernel already draws 3.6 TB/s from
+  // HBM, and the scatter is pure HBM traffic.)
   for (int64_t t0 = 0; t0 < tl.n; t0 += cap) {
     Params prm;
     prm.P = Pn;

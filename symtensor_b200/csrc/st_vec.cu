@@ -730,7 +730,7 @@ int64_t g_ring_table_max = 72 * 1024;  // ring kernel: largest tail table in byt
 extern int64_t g_mat_onfly_rows;
 extern int g_mat_dmma, g_mat_pipe, g_conv_rows, g_outer_fast, g_outer_rows, g_gram_umma, g_sym22;  // st_ops.cu
 extern int64_t g_sym22_min_dim;
-namespace s22 { extern int g_kch, g_debug, g_tile_rgroup; void clear_tile_cache(); }  // st_sym22.cu
+namespace s22 { extern int g_kch, g_debug, g_tile_rgroup; extern int64_t g_batch_tiles; void clear_tile_cache(); }  // st_sym22.cu
 int64_t g_short_segment = 1024;  // classes whose segments are shorter than this take the per-component phase (tuning knob)
 int64_t g_small_class = 128 * 1024;  // classes up to this many components take the per-component phase (tuning knob)
 
@@ -1425,6 +1425,7 @@ int st_set_tuning(const char* key, int64_t value) {
   if (k == "sym22" && (value == 0 || value == 1)) { g_sym22 = (int)value; return ST_OK; }
   if (k == "sym22_min_dim" && value >= 1) { g_sym22_min_dim = value; return ST_OK; }
   if (k == "sym22_kch" && (value == 16 || value == 32)) { s22::g_kch = (int)value; return ST_OK; }
+  if (k == "sym22_batch_tiles" && value >= 1) { s22::g_batch_tiles = value; return ST_OK; }
   if (k == "sym22_rgroup" && value >= 1 && value <= 64) { s22::g_tile_rgroup = (int)value; s22::clear_tile_cache(); return ST_OK; }
   if (k == "sym22_debug" && value >= 0 && value < 128) { s22::g_debug = (int)value; return ST_OK; }
   if (k == "vec_short_segment" && value >= 0) {

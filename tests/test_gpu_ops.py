@@ -360,8 +360,16 @@ def test_tensordot_several_output_ranges_in_one_call_equal_the_single_range_call
                     one = torch.full((e - b,), -5.0, dtype=torch.float32, device=DEV)
                     ops.tensordot_device(TA, TB, k, one, b, e, torch.float32)
                     assert torch.equal(got, one), (ra, rb, k, dim, b, e)
+                if tiled:  # several batches of tiles per call (BASELINE config 3 runs 7 batches of 32768 per GPU)
+                    check(lib.st_set_tuning(b"sym22_batch_tiles", c_i64(3)))
+                    again = [torch.full((e - b,), -9.0, dtype=torch.float32, device=DEV) for b, e in ranges]
+                    ops.tensordot_device_ranges(TA, TB, k, again, ranges)
+                    check(lib.st_set_tuning(b"sym22_batch_tiles", c_i64(32768)))
+                    for got, ref in zip(again, outs):
+                        assert torch.equal(got, ref), (ra, rb, k, dim)
         finally:
             check(lib.st_set_tuning(b"sym22_min_dim", c_i64(96)))
+            check(lib.st_set_tuning(b"sym22_batch_tiles", c_i64(32768)))
 
 
 def test_outer_row_walk_kernel_agrees_with_the_per_component_unrank_kernels():
