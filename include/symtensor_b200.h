@@ -316,6 +316,9 @@ int64_t st_debug_rowwalk(int rank, int64_t dim, int64_t begin, int64_t end, int6
 int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end, unsigned long long* h_out, int64_t cap);
 /* ... for the union of several ranges (host arrays), as st_tensordot_ranges_f32 runs them */
 int64_t st_debug_sym22_tiles_ranges(int64_t dim, int nranges, const int64_t* begins, const int64_t* ends, unsigned long long* h_out, int64_t cap);
+/* ... and the terms of its cost model: stats[0] = number of tiles, stats[1] = sum over the tiles of 1 / (l blocks of the tile's k
+ * block) */
+int st_debug_sym22_tiles_stats(int64_t dim, int nranges, const int64_t* begins, const int64_t* ends, double* stats);
 /* number of kernel launches issued by this library since load (bench.py reports it) */
 int64_t st_launch_count(void);
 

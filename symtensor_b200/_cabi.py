@@ -87,6 +87,7 @@ SIGNATURES = {
     "st_debug_rowwalk": (c_i64, [c_int, c_i64, c_i64, c_i64, c_i64, c_vp]),
     "st_debug_sym22_tiles": (c_i64, [c_i64, c_i64, c_i64, c_vp, c_i64]),
     "st_debug_sym22_tiles_ranges": (c_i64, [c_i64, c_int, c_vp, c_vp, c_vp, c_i64]),
+    "st_debug_sym22_tiles_stats": (c_int, [c_i64, c_int, c_vp, c_vp, c_vp]),
     "st_launch_count": (c_i64, []),
 }
 

@@ -816,3 +816,23 @@ extern "C" int64_t st_debug_sym22_tiles_ranges(int64_t dim, int nranges, const i
   for (int64_t i = 0; i < (int64_t)tiles.size() && i < cap; ++i) h_out[i] = tiles[i];
   return (int64_t)tiles.size();
 }
+
+// count and cost terms of the tile list of several ranges: stats[0] = tiles, stats[1] = sum over the tiles of 1 / (number of l
+// blocks of the tile's k block) -- the fewer tiles share their three column boxes, the more a tile costs (sharding.py)
+extern "C" int st_debug_sym22_tiles_stats(int64_t dim, int nranges, const int64_t* begins, const int64_t* ends, double* stats) {
+  const st::HostPlan* hp = st::get_host_plan(4, dim);
+  if (!hp || !stats || nranges < 0 || (nranges && (!begins || !ends))) return ST_ERR_INVALID;
+  std::vector<std::pair<int64_t, int64_t>> ranges;
+  for (int q = 0; q < nranges; ++q) ranges.emplace_back(begins[q], ends[q]);
+  std::vector<unsigned long long> tiles;
+  st::s22::build_tiles(hp, ranges, tiles);
+  const int64_t nbl = (dim + st::s22::BL - 1) / st::s22::BL;
+  double inv = 0.0;
+  for (unsigned long long w : tiles) {
+    const int64_t r = (int64_t)((w >> 32) & 0xffff);
+    inv += 1.0 / (double)std::max<int64_t>(1, nbl - r * st::s22::BJ / st::s22::BL);
+  }
+  stats[0] = (double)tiles.size();
+  stats[1] = inv;
+  return ST_OK;
+}

@@ -164,7 +164,7 @@ def tensordot22_shards(dim: int, world: int, align: int = ALIGN) -> List[List[tu
     against ~400).  Here GPU g takes (i) the components of EVERY small class whose first class-order value a -- a repeated
     index -- lies in its interval ``[a_g, a_g+1)``: four ranges that need the same diagonal tiles (those whose overlapping
     index blocks meet the interval), the intervals cut where the tile count of the prefix reaches g / world; (ii) its part
-    of class (1,1,1,1), cut where the first index enters a new block of 16 so that small + large tile counts are even.
+    of class (1,1,1,1), cut where the first index enters a new block of 16 so that small + large tile COSTS are even.
     No collective: the result stays sharded, five pieces per GPU.  Pure host arithmetic."""
     import ctypes
     import math
@@ -182,13 +182,19 @@ def tensordot22_shards(dim: int, world: int, align: int = ALIGN) -> List[List[tu
         return [[(0, total)]]
 
     def ntiles(ranges):
+        """Cost of the tiles the ranges need, in tiles: a tile whose k block r leaves few l blocks shares its three column boxes
+        with few neighbours and costs more -- measured on the eight shards of dim 1000 (tools/shard_times_c3.py):
+        ms = 0.001995 tiles + 0.006384 sum 1 / (l blocks of r), residuals below 1 % (the last shard: 2.41 us per tile against 2.15)."""
         ranges = [r for r in ranges if r[1] > r[0]]
         if not ranges:
-            return 0
+            return 0.0
         n = len(ranges)
         b = (ctypes.c_int64 * n)(*[r[0] for r in ranges])
         e = (ctypes.c_int64 * n)(*[r[1] for r in ranges])
-        return int(lib.st_debug_sym22_tiles_ranges(c_i64(dim), n, b, e, ctypes.c_void_p(0), c_i64(0)))
+        stats = (ctypes.c_double * 2)()
+        if lib.st_debug_sym22_tiles_stats(c_i64(dim), n, b, e, stats) != 0:
+            raise RuntimeError("st_debug_sym22_tiles_stats failed")
+        return stats[0] + 3.2 * stats[1]
 
     # first position of the value a in each small class (a = dim: the end of the class)
     first = [lambda a: a,
@@ -213,18 +219,19 @@ def tensordot22_shards(dim: int, world: int, align: int = ALIGN) -> List[List[tu
     cands = sorted(set([off4] + [min(total, max(off4, first_coord(i0) // align * align)) for i0 in range(16, dim - 3, 16)] + [total]))
     big = [off4]
     idx = 0
-    for g in range(world - 1):
-        target = ntiles([(big[-1], total)]) / (world - g)
-        lo, hi = idx, max(idx, len(cands) - 1 - (world - 2 - g))
+    big_all = ntiles([(off4, total)])
+    for g in range(1, world):
+        target = big_all * g / world  # cost of the prefix [off4, cut): errors of the coarse grid do not pile up on the last GPU
+        lo, hi = idx, max(idx, len(cands) - 1 - (world - 1 - g))
         a, b = lo, hi
         while a < b:
             mid = (a + b) // 2
-            if ntiles([(big[-1], cands[mid])]) >= target:
+            if ntiles([(off4, cands[mid])]) >= target:
                 b = mid
             else:
                 a = mid + 1
         best = a
-        if a > lo and abs(ntiles([(big[-1], cands[a - 1])]) - target) <= abs(ntiles([(big[-1], cands[a])]) - target):
+        if a > lo and abs(ntiles([(off4, cands[a - 1])]) - target) <= abs(ntiles([(off4, cands[a])]) - target):
             best = a - 1
         best = min(best, len(cands) - 1)
         big.append(cands[best])

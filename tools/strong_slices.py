@@ -21,7 +21,11 @@ out = torch.zeros(1, dtype=torch.float64, device=dev)
 ws = torch.empty(2 * int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
 cuts = sharding.shard_bounds(t.total, n)
 whole = None
-for slots in (3, 4, 6, 8):
+tmax = int(sys.argv[3]) if len(sys.argv) > 3 else -1
+if tmax >= 0:
+    check(lib.st_set_tuning(b"vec_ring_table_max", c_i64(tmax)))
+    print("vec_ring_table_max", tmax)
+for slots in (4,):
     check(lib.st_set_tuning(b"vec_short_launch_bytes", c_i64(0 if slots == 0 else 160 << 20)))
     if slots:
         check(lib.st_set_tuning(b"vec_short_launch_slots", c_i64(slots)))
