@@ -135,9 +135,33 @@ def config5(dev, world, rank, dist, peaks):
     x = ((torch.rand(dim, generator=g, dtype=torch.float32) + 0.5) / dim ** 0.5).to(dev)
     table = comb.class_table(ra + rb, dim)
     n = sum(table.sizes)
-    b, e = sharding.my_range(table.total, rank, world)
-    out = torch.empty(e - b, dtype=torch.float32, device=dev)
+    cuts = sharding.shard_bounds(table.total, world)
     d = dist if world > 1 else None
+    balance = None
+    if world > 1:
+        # the cost per coordinate varies along the packed range (the small classes at the start: short rows, more class
+        # changes): every rank times its own slice and the cuts move until the slices take the same time (sharding.rebalance)
+        for _ in range(2):
+            b, e = cuts[rank], cuts[rank + 1]
+            tmp = torch.empty(max(e - b, 1), dtype=torch.float32, device=dev)
+            for _w in range(2):
+                ops.outer_device(A, B, tmp, b, e, torch.float32, af=af, bf=bf)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            ops.outer_device(A, B, tmp, b, e, torch.float32, af=af, bf=bf)
+            e1.record()
+            torch.cuda.synchronize()
+            tl = torch.zeros(world, dtype=torch.float64, device=dev)
+            tl[rank] = e0.elapsed_time(e1)
+            dist.all_reduce(tl)
+            times = [float(v) for v in tl.cpu()]
+            cuts = sharding.rebalance(cuts, times)
+            balance = {"slice_ms_before_last_round": [round(v, 3) for v in times],
+                       "slice_fractions": [round((cuts[r + 1] - cuts[r]) / table.total, 4) for r in range(world)]}
+            del tmp
+    b, e = cuts[rank], cuts[rank + 1]
+    out = torch.empty(e - b, dtype=torch.float32, device=dev)
     ms_outer, l1 = _timed(lambda: ops.outer_device(A, B, out, b, e, torch.float32, af=af, bf=bf), 2, 1, d)
     res = torch.zeros(1, dtype=torch.float32, device=dev)
     ws = torch.empty(int(lib.st_contract_vec_workspace_bytes()) // 8, dtype=torch.float64, device=dev)
@@ -179,7 +203,7 @@ def config5(dev, world, rank, dist, peaks):
             "hbm_written_gbs_per_gpu": n * 4 / world / (ms_outer * 1e-3) / 1e9,
             "result_unfused": unfused, "result_fused": fused, "identity_(A.x^4)(B.x^4)": xa,
             "rel_err_unfused": abs(unfused - xa) / abs(xa), "rel_err_fused": abs(fused - xa) / abs(xa),
-            "kernel_launches": l1 + l2 + l3,
+            "kernel_launches": l1 + l2 + l3, "balance": balance,
             "roofline": {"bound": "l1 load pipe (gathered operand loads)", "achieved": ach, "peak": peak, "unit": "G lane-loads/s", "frac": ach / peak,
                          "traffic": None,
                          "peak_source": f"{sms} SMs x 1.965 GHz x 32 lanes: one warp-wide load per clock per SM (B300_MICROARCH.md); HBM is not the bound -- "
