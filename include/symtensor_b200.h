@@ -298,7 +298,12 @@ int st_set_vec_variant(int variant);
 /* tuning hooks (process-wide; defaults are the tuned values): "vec_force_tau" in [0, ST_MAX_RANK] (0 = cost model),
  * "vec_small_class", "vec_use_dir", and for the ring kernel "vec_ring_warps", "vec_ring_slots", "vec_ring_bytes",
  * "vec_ring_bytes_max", "vec_ring_tile_bytes", "vec_ring_table_max", "vec_ring_direct", "vec_ring_dynamic"
- * (0: static tile deal), "vec_timeline" (debug stamps, see st_debug_vec_timeline). */
+ * (0: static tile deal), "vec_timeline" (debug stamps, see st_debug_vec_timeline), "vec_short_launch_bytes" /
+ * "vec_short_launch_slots" (launches over a slice of at most that many bytes use tiles of that many ring slots).
+ * Kernel selection (test hooks; 1 = the round-2 kernel): "outer_fast", "outer_rows" (row-walk multiply.outer), "conv_rows" (row-walk
+ * layout converters), "mat_dmma", "mat_pipe" (persistent producer / consumer step kernel), "mat_onfly_rows" (steps with at most
+ * that many rows rank their gathers in the producers), "gram_umma", "sym22", "sym22_min_dim", "sym22_kch", "sym22_debug"
+ * (ablation mask), "sym22_rgroup" (tile order), "sym22_batch_tiles" (tiles per launch, at most 32768). */
 int st_set_tuning(const char* key, int64_t value);
 /* debug: with st_set_tuning("vec_timeline", 1) the vector-contraction kernel stamps %globaltimer at its phase
  * boundaries ([cta][16] stamps, then one finish stamp per warp of the grid); this copies the first n stamps of
