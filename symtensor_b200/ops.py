@@ -77,7 +77,7 @@ def contract_all_indices_with_vectors(symtensor, X):
     with torch.cuda.device(dev):
         Xd = Xt.to(device=dev, dtype=tdt).contiguous()
         out = torch.zeros(max(n, 1), dtype=tdt, device=dev)
-        ws = torch.empty(2 * _WS_BYTES // 8, dtype=torch.float64, device=dev)
+        ws = _vec_workspace(dev)
         torch.cuda.current_stream(dev).synchronize()  # the operands are complete: the launches below may start early
         fn = lib.st_contract_vec_ex_f64 if tdt == torch.float64 else lib.st_contract_vec_ex_f32
         sp = _stream_ptr(dev)
@@ -85,6 +85,19 @@ def contract_all_indices_with_vectors(symtensor, X):
             check(fn(type(symtensor).layout, symtensor.rank, c_i64(symtensor.dim), buf.data_ptr(), c_i64(0), c_i64(buf.numel()),
                      Xd[i].data_ptr(), out[i:].data_ptr(), ws.data_ptr(), VEC_OVERLAP, sp))
     return out[:n]
+
+
+_VEC_WS = {}
+
+
+def _vec_workspace(dev: torch.device) -> torch.Tensor:
+    """The vector contraction's 4 MiB partial-sum workspace, one per (device, stream): calls on one stream are ordered, so they can
+    share it (a fresh allocation per call cost more than the kernel of a small tensor)."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), _stream_ptr(dev))
+    ws = _VEC_WS.get(key)
+    if ws is None:
+        ws = _VEC_WS[key] = torch.empty(2 * _WS_BYTES // 8, dtype=torch.float64, device=dev)
+    return ws
 
 
 def _contract_all_indices_with_vector(symtensor, x):
@@ -111,7 +124,7 @@ def _contract_all_indices_with_vector(symtensor, x):
     with torch.cuda.device(dev):
         xd = (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(device=dev, dtype=tdt).contiguous()
         out = torch.zeros(32 if cls.layout == 0 else 1, dtype=tdt, device=dev)  # packed buffer of a rank-0 tensor
-        ws = torch.empty(_WS_BYTES // 8, dtype=torch.float64, device=dev)
+        ws = _vec_workspace(dev)
         fn = lib.st_contract_vec_f64 if tdt == torch.float64 else lib.st_contract_vec_f32
         check(fn(cls.layout, symtensor.rank, c_i64(symtensor.dim), buf.data_ptr(), c_i64(0), c_i64(buf.numel()),
                  xd.data_ptr(), out.data_ptr(), ws.data_ptr(), _stream_ptr(dev)))
