@@ -316,6 +316,10 @@ int64_t st_debug_permcls_successors(int rank, int64_t dim, int32_t cls, int64_t 
  * alignment padding) as the multiply.outer kernel's row walk hands them to its lanes (spans of `span` coordinates, batches of
  * 32); dim <= 255; returns end - begin. */
 int64_t st_debug_rowwalk(int rank, int64_t dim, int64_t begin, int64_t end, int64_t span, int32_t* h_idx);
+/* ... and the same walk run on the DEVICE by the code the kernels use (d_idx: device buffer; span: a multiple of 32) */
+int st_debug_rowwalk_device(int rank, int64_t dim, int64_t begin, int64_t end, int64_t span, int32_t* d_idx, void* stream);
+/* ... with the latch of every coordinate (8 ints each: packed values lo / hi, b, m, offset, class, state, cursor values) in d_dbg */
+int st_debug_rowwalk_device2(int rank, int64_t dim, int64_t begin, int64_t end, int64_t span, int32_t* d_idx, int32_t* d_dbg, void* stream);
 /* debug (host only): the tile words p | q << 16 | r << 32 | s << 48 (index blocks 16 / 16 / 16 / 8) the tiled tensordot kernel
  * runs for the output range [begin, end) of a rank-4 result; returns their number (writes at most `cap`). */
 int64_t st_debug_sym22_tiles(int64_t dim, int64_t begin, int64_t end, unsigned long long* h_out, int64_t cap);

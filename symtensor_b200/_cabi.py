@@ -85,6 +85,8 @@ SIGNATURES = {
     "st_debug_vec_timeline": (c_int, [c_vp, c_i64]),
     "st_debug_permcls_successors": (c_i64, [c_int, c_i64, ctypes.c_int32, c_i64, c_i64, c_vp]),
     "st_debug_rowwalk": (c_i64, [c_int, c_i64, c_i64, c_i64, c_i64, c_vp]),
+    "st_debug_rowwalk_device": (c_int, [c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "st_debug_rowwalk_device2": (c_int, [c_int, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "st_debug_sym22_tiles": (c_i64, [c_i64, c_i64, c_i64, c_vp, c_i64]),
     "st_debug_sym22_tiles_ranges": (c_i64, [c_i64, c_int, c_vp, c_vp, c_vp, c_i64]),
     "st_debug_sym22_tiles_stats": (c_int, [c_i64, c_int, c_vp, c_vp, c_vp]),

@@ -265,6 +265,7 @@ struct RowCursor {
   int64_t next_off;  // first coordinate of class ci + 1
   int32_t vals[ST_MAX_RANK];  // the row's component values in class order (the last tau: any component of the row)
   unsigned long long valsp;   // ... packed one per byte (0xff fill), refreshed whenever the row changes
+  int32_t b, m, len;          // of the row at the cursor (rowcursor_refresh): previous value, free values above it, C(m, tau) components
 };
 
 struct RowLatch {
@@ -297,7 +298,7 @@ ST_HD void rowcursor_enter_class(const PlanView& P, RowCursor& rc, int ci) {
   rc.cls_end = C.offset + C.size;
   rc.next_off = P.offsets[ci + 1];
   for (int i = 0; i < C.nvals; ++i) rc.vals[i] = i;  // first component: every run takes the smallest values left
-  rc.valsp = 0x0706050403020100ull | (C.nvals < 8 ? ~0ull << (8 * C.nvals) : 0ull);
+  rc.valsp = ~0ull; rc.b = -1; rc.m = 0; rc.len = 0;  // (rowcursor_refresh: by the caller, once the cursor is final)
 }
 
 // the row at the cursor: previous value b of the last run (-1 if the tail is the whole run), the number m of free values
@@ -321,11 +322,23 @@ ST_HD void rowcursor_pack(const PlanView& P, RowCursor& rc) {
   rc.valsp = p;
 }
 
+// b, m, len and the packed values of the row at the cursor: once per row, so that a batch inside a long row costs the walk a
+// dozen instructions
+ST_HD void rowcursor_refresh(const PlanView& P, RowCursor& rc) {
+  if (rc.cur >= rc.cls_end) { rc.b = -1; rc.m = 0; rc.len = 0; return; }
+  int32_t b, m;
+  const int32_t len = rowcursor_row(P, rc, &b, &m);
+  rc.b = b;
+  rc.m = m;
+  rc.len = len;
+  rowcursor_pack(P, rc);
+}
+
 ST_HD void rowcursor_seek(const PlanView& P, RowCursor& rc, int64_t c) {
   const int ci = class_of_coord(P, c);
   rowcursor_enter_class(P, rc, ci);
   rc.cur = c;
-  if (c >= rc.cls_end) return;
+  if (c >= rc.cls_end) { rowcursor_refresh(P, rc); return; }
   const ClassDesc& C = P.cls[ci];
   permcls_unrank_vals(P, C, c - C.offset, rc.vals);
   // position inside the row: the lexicographic rank of the tail among the combinations of the free values above b
@@ -340,37 +353,40 @@ ST_HD void rowcursor_seek(const PlanView& P, RowCursor& rc, int64_t c) {
     r -= (int32_t)binom_at(P.binom, P.rank, m - 1 - y, k + 1);
   }
   rc.off = r;
-  rowcursor_pack(P, rc);
+  rowcursor_refresh(P, rc);
 }
 
 // Serve the coordinates below `batch_end`: every lane of a warp calls this with the same cursor (so the walk is uniform) and
 // its own coordinate c, and leaves with the latch of the row that holds c.  The cursor ends at batch_end (inside a row if one
 // straddles it) or at the start of a later class.
 ST_HD void rowcursor_serve(const PlanView& P, RowCursor& rc, int64_t c, int64_t batch_end, RowLatch& L) {
+  // (every field initialised: with the latch left undefined for the lanes no row serves, nvcc 12.9 merged L.valsp with the
+  // cursor's register and every lane saw the values of the LAST row of the call -- found with st_debug_rowwalk_device)
   L.state = 0;
+  L.valsp = 0; L.b = 0; L.m = 0; L.o = 0; L.ci = 0;
   while (rc.cur < batch_end) {
     if (rc.cur >= rc.cls_end) {  // alignment padding, then the next class
       if (c >= rc.cur && c < rc.next_off) L.state = 2;
       rowcursor_enter_class(P, rc, rc.ci + 1);
+      if (rc.ci < P.ncls) rowcursor_refresh(P, rc);
       continue;
     }
-    int32_t b, m;
-    const int32_t len = rowcursor_row(P, rc, &b, &m) - rc.off;  // what is left of the row
+    const int32_t len = rc.len - rc.off;  // what is left of the row
     const int64_t left = batch_end - rc.cur;
     const int32_t take = left < (int64_t)len ? (int32_t)left : len;
     if (c >= rc.cur && c < rc.cur + take) {
-      L.valsp = rc.valsp; L.b = b; L.m = m; L.o = rc.off + (int32_t)(c - rc.cur); L.ci = rc.ci; L.state = 1;
+      L.valsp = rc.valsp; L.b = rc.b; L.m = rc.m; L.o = rc.off + (int32_t)(c - rc.cur); L.ci = rc.ci; L.state = 1;
     }
     rc.cur += take;
     if (take < len) {
       rc.off += take;  // the row straddles the batch
     } else {
       rc.off = 0;
-      const ClassDesc& C = P.cls[rc.ci];
-      const int g = C.run_len[C.nruns - 1];
       if (rc.cur < rc.cls_end) {
+        const ClassDesc& C = P.cls[rc.ci];
+        const int g = C.run_len[C.nruns - 1];
         permcls_advance(P, C, rc.vals, g < kRowTauMax ? g : kRowTauMax);
-        rowcursor_pack(P, rc);
+        rowcursor_refresh(P, rc);
       }
     }
   }

@@ -94,6 +94,41 @@ __global__ void __launch_bounds__(256) rowwalk_convert_kernel(PlanView P, const 
   }
 }
 
+// debug: the row walk on the DEVICE, exactly as the kernels run it (st_debug_rowwalk replays it on the host)
+__global__ void __launch_bounds__(256) rowwalk_debug_kernel(PlanView P, int64_t begin, int64_t end, int span, int32_t* __restrict__ idx, int32_t* __restrict__ dbg) {
+  __shared__ int32_t B23[2 * kRowBinomStride];
+  __shared__ unsigned long long cinfo[32];
+  for (int e = threadIdx.x; e < 2 * kRowBinomStride; e += blockDim.x) {
+    const int n = e % kRowBinomStride;
+    B23[e] = e < kRowBinomStride ? n * (n - 1) / 2 : n * (n - 1) * (n - 2) / 6;
+  }
+  for (int e = threadIdx.x; e < P.ncls && e < 32; e += blockDim.x) cinfo[e] = row_class_info(P.cls[e], P.rank);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const int64_t ntasks = (end - begin + span - 1) / span;
+  for (int64_t task = (int64_t)blockIdx.x * wpb + warp; task < ntasks; task += (int64_t)gridDim.x * wpb) {
+    const int64_t s0 = begin + task * span, s1 = s0 + span < end ? s0 + span : end;
+    RowCursor rc;
+    rowcursor_seek(P, rc, s0);
+    for (int64_t b = s0; b < s1; b += 32) {
+      const int64_t c = b + lane, be = b + 32 < s1 ? b + 32 : s1;
+      RowLatch R;
+      rowcursor_serve(P, rc, c, be, R);
+      if (c >= be) continue;
+      int32_t* o = idx + (c - begin) * P.rank;
+      if (dbg) {
+        int32_t* g = dbg + (c - begin) * 8;
+        g[0] = (int32_t)(R.valsp & 0xffffffffu); g[1] = (int32_t)(R.valsp >> 32); g[2] = R.b; g[3] = R.m; g[4] = R.o; g[5] = R.ci; g[6] = R.state;
+        g[7] = (int32_t)(rc.valsp & 0xffffffffu);
+      }
+      if (R.state != 1) { for (int i = 0; i < P.rank; ++i) o[i] = -1; continue; }
+      int32_t K[8];
+      row_component(R.valsp, R.b, R.m, R.o, cinfo[R.ci], B23, K);
+      for (int i = 0; i < P.rank; ++i) o[i] = K[i];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // symmetrized outer product: one thread per packed output component, C(n, ra) gathered products
 // ------------------------------------------------------------------------------------------------------
@@ -1375,6 +1410,20 @@ static int contract_mat(int rank, int64_t dim, const T* d_a_flat, const T* d_W, 
 using namespace st;
 
 extern "C" {
+
+int st_debug_rowwalk_device(int rank, int64_t dim, int64_t begin, int64_t end, int64_t span, int32_t* d_idx, void* stream) {
+  return st_debug_rowwalk_device2(rank, dim, begin, end, span, d_idx, nullptr, stream);
+}
+int st_debug_rowwalk_device2(int rank, int64_t dim, int64_t begin, int64_t end, int64_t span, int32_t* d_idx, int32_t* d_dbg, void* stream) {
+  PlanView P;
+  int rc = get_device_plan(rank, dim, &P);
+  if (rc) return rc;
+  if (rank < 1 || rank > 8 || dim > 255 || span < 32 || span % 32 || begin < 0 || end < begin || end > P.total || !d_idx) { set_error("bad arguments"); return ST_ERR_INVALID; }
+  if (end == begin) return ST_OK;
+  const int64_t ntasks = (end - begin + span - 1) / span;
+  rowwalk_debug_kernel<<<(unsigned)std::min<int64_t>((ntasks + 7) / 8, 148 * 8), 256, 0, (cudaStream_t)stream>>>(P, begin, end, (int)span, d_idx, d_dbg);
+  return check_cuda(cudaGetLastError(), "rowwalk_debug_kernel");
+}
 
 int st_permcls_to_flat_f64(int rank, int64_t dim, const double* d_permcls, double* d_flat, void* stream) {
   return permcls_to_flat<double>(rank, dim, d_permcls, d_flat, (cudaStream_t)stream);

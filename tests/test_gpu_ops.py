@@ -278,6 +278,26 @@ def test_outer_compile_time_rank_and_run_time_rank_kernels_agree():
         assert abs(v0 - v1) <= 1e-12 * abs(v0)
 
 
+def test_row_walk_on_the_device_equals_its_host_replay():
+    """The warp-uniform row walk as the kernels run it (rowwalk_debug_kernel: seek per span, batches of 32 lanes, latch, lane-side
+    decode) against the host replay of the same code (st_debug_rowwalk, which tests/test_oracle_index.py pins to the oracle's
+    enumeration): every coordinate, several span lengths.  (A latch left undefined for unserved lanes once compiled into a
+    kernel whose lanes all saw the last row of the call -- the host replay could not see that.)"""
+    from symtensor_b200 import combinatorics as comb
+    from symtensor_b200._cabi import c_i64, check, lib
+    for rank, dim, span in [(1, 7, 2048), (2, 9, 2048), (3, 6, 64), (4, 11, 2048), (5, 5, 96), (6, 7, 2048), (8, 5, 2048), (8, 9, 2048),
+                            (4, 40, 1024), (3, 255, 2048), (7, 6, 32), (8, 12, 4096)]:
+        total = comb.class_table(rank, dim).total
+        host = np.full((total, rank), -7, dtype=np.int32)
+        assert lib.st_debug_rowwalk(rank, c_i64(dim), c_i64(0), c_i64(total), c_i64(span), host.ctypes.data) == total
+        dev = torch.full((total, rank), -9, dtype=torch.int32, device=DEV)
+        check(lib.st_debug_rowwalk_device(rank, c_i64(dim), c_i64(0), c_i64(total), c_i64(span), dev.data_ptr(), None))
+        torch.cuda.synchronize()
+        got = dev.cpu().numpy()
+        bad = np.nonzero((got != host).any(axis=1))[0]
+        assert len(bad) == 0, (rank, dim, span, bad[:5], got[bad[:3]], host[bad[:3]])
+
+
 def test_row_walk_layout_converters_agree_with_the_unrank_kernels():
     """permcls <-> flat re-ordering through the row-walk kernels (rowwalk_convert_kernel) against the kernels that unrank /
     classify / rank every component: bit-identical buffers, including output ranges that start and end mid-row."""
