@@ -125,6 +125,27 @@ def test_matrix_mode_bounds_balance_the_chain_work():
     assert work[0] > 4 * work[dim // 2] > 0
 
 
+def test_matrix_mode_work_matches_a_brute_force_count():
+    """sharding.mat_mode_work against a direct enumeration of the items the step kernel runs: for every step k >= 1, every sorted
+    k-tuple J that starts with j1, every tile of 64 I, the 8-column blocks that hold a column j >= max(J); step 0 per column."""
+    import itertools
+    import math
+
+    from symtensor_b200 import sharding
+    for rank, dim in [(3, 9), (4, 12), (5, 7), (2, 20), (4, 17)]:
+        work = sharding.mat_mode_work(rank, dim)
+        nblk = (dim + 7) // 8
+        for j1 in (0, 1, dim // 2, dim - 1):
+            want = math.ceil(math.comb(dim + rank - 2, rank - 1) / 64) / 8.0
+            for k in range(1, rank):
+                m = rank - k - 1
+                tiles = math.ceil(math.comb(dim + m - 1, m) / 64) if m > 0 else 1.0 / 64
+                for J in itertools.combinations_with_replacement(range(j1, dim), k - 1):
+                    jl = J[-1] if J else j1
+                    want += tiles * (nblk - jl // 8)
+            assert abs(work[j1] - want) <= 1e-9 * max(1.0, want), (rank, dim, j1, work[j1], want)
+
+
 def test_tensordot22_bounds_are_aligned_and_cover():
     from symtensor_b200 import combinatorics as comb
     from symtensor_b200 import sharding
