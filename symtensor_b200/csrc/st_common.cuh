@@ -417,6 +417,7 @@ ST_HD void row_component(unsigned long long valsp, int32_t b, int32_t m, int32_t
     }
   }
   int32_t prev = -1, r = o;
+  uint32_t tailw = 0;
 #pragma unroll
   for (int i = 0; i < kRowTauMax; ++i) {
     if (i >= tau) break;
@@ -463,12 +464,29 @@ ST_HD void row_component(unsigned long long valsp, int32_t b, int32_t m, int32_t
       v += (e0 <= v);
       v += (e1 <= v);
     }
-    const int pos = nvals - tau + i;
-    valsp = (valsp & ~(0xffull << (8 * pos))) | ((unsigned long long)v << (8 * pos));
+    tailw |= (uint32_t)v << (8 * i);
   }
-  // class order -> one value per index entry -> sorted (odd-even merge sort network for 8 keys)
+  {  // the tail's bytes replace the bytes [nvals - tau, nvals) of the packed values (one 64-bit shift instead of one per value)
+    const int sh = 8 * (nvals - tau);
+    const unsigned long long tm = (unsigned long long)((1u << (8 * tau)) - 1u) << sh;
+    valsp = (valsp & ~tm) | ((unsigned long long)tailw << sh);
+  }
+  // class order -> one value per index entry (the entry -> value-position nibbles of `info` are a byte-permute selector) -> sorted
+  // (odd-even merge sort network for 8 keys)
+#ifdef __CUDA_ARCH__
+  {
+    const uint32_t vlo = (uint32_t)valsp, vhi = (uint32_t)(valsp >> 32);
+    const uint32_t w0 = __byte_perm(vlo, vhi, (uint32_t)info & 0xffffu), w1 = __byte_perm(vlo, vhi, ((uint32_t)info >> 16) & 0xffffu);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      K[e] = (int32_t)((w0 >> (8 * e)) & 0xffu);
+      K[4 + e] = (int32_t)((w1 >> (8 * e)) & 0xffu);
+    }
+  }
+#else
 #pragma unroll
   for (int e = 0; e < 8; ++e) K[e] = (int32_t)((valsp >> (8 * ((info >> (4 * e)) & 7))) & 0xffull);
+#endif
 #define ST_CE(i, j) { const int32_t lo_ = K[i] < K[j] ? K[i] : K[j], hi_ = K[i] < K[j] ? K[j] : K[i]; K[i] = lo_; K[j] = hi_; }
   ST_CE(0, 1) ST_CE(2, 3) ST_CE(4, 5) ST_CE(6, 7)
   ST_CE(0, 2) ST_CE(1, 3) ST_CE(4, 6) ST_CE(5, 7)
