@@ -392,6 +392,33 @@ def test_tensordot_several_output_ranges_in_one_call_equal_the_single_range_call
             check(lib.st_set_tuning(b"sym22_batch_tiles", c_i64(32768)))
 
 
+def test_tensordot_ranges_argument_checks():
+    """st_tensordot_ranges_f32 rejects overlapping ranges, ranges outside the packed output and more than 8 ranges (status
+    ST_ERR_INVALID -> ValueError), and accepts empty ranges."""
+    from symtensor_b200 import combinatorics as comb, ops
+    from symtensor_b200._cabi import c_i64, check, lib
+    dim = 24
+    rng = np.random.default_rng(1)
+    TA = st.PermClsTorchSymmetricTensor(rank=3, dim=dim, data=rand_packed(3, dim, rng, "normal"), device=DEV).astype(np.float32)
+    total = comb.class_table(4, dim).total
+    try:
+        check(lib.st_set_tuning(b"sym22_min_dim", c_i64(8)))
+        buf = lambda n: torch.zeros(max(n, 1), dtype=torch.float32, device=DEV)
+        with pytest.raises(ValueError, match="overlap"):
+            ops.tensordot_device_ranges(TA, TA, 1, [buf(64), buf(64)], [(0, 64), (32, 96)])
+        with pytest.raises(ValueError):
+            ops.tensordot_device_ranges(TA, TA, 1, [buf(64)], [(total - 32, total + 32)])
+        with pytest.raises(ValueError):
+            ops.tensordot_device_ranges(TA, TA, 1, [buf(32)] * 9, [(32 * i, 32 * i + 32) for i in range(9)])
+        one, two = buf(64), buf(0)
+        ops.tensordot_device_ranges(TA, TA, 1, [one, two], [(0, 64), (128, 128)])  # an empty range is fine
+        ref = buf(64)
+        ops.tensordot_device(TA, TA, 1, ref, 0, 64, torch.float32)
+        assert torch.equal(one, ref)
+    finally:
+        check(lib.st_set_tuning(b"sym22_min_dim", c_i64(96)))
+
+
 def test_outer_row_walk_kernel_agrees_with_the_per_component_unrank_kernels():
     """multiply.outer through the row-walk kernel (outer_rows_kernel: warp-uniform odometer over the rows that cover 32
     consecutive coordinates, half-split subset sums) against the kernel that unranks every component (outer_fast_kernel) and
