@@ -328,7 +328,7 @@ def test_config3_shard_of_an_8_gpu_partition_in_one_call(c3_operands):
     ws = None
     for g in (0, 5):
         ranges = list(shards[g])
-        assert len(ranges) == 5
+        assert 2 <= len(ranges) <= 5
         b4, e4 = ranges[-1]
         ranges[-1] = (b4, min(e4, b4 + 60_000_000 // 32 * 32))
         outs = [torch.full((e - b,), -7.0, dtype=torch.float32, device=DEV) for b, e in ranges]

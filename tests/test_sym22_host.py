@@ -78,3 +78,21 @@ def test_tile_lists_of_ranges_inside_the_small_classes_are_pruned_but_complete()
             got = {(w & 0xffff, (w >> 16) & 0xffff, (w >> 32) & 0xffff, (w >> 48) & 0xffff) for w in words}
             for b, e in sh:
                 assert tiles_needed(dim, b, e) <= got
+
+
+def test_config3_shards_are_balanced_by_the_tile_cost_model():
+    """sharding.tensordot22_shards at BASELINE config 3 (dim 1000, 8 GPUs): at most five ranges per GPU, and the modelled cost of the
+    tiles each GPU runs (tiles + 3.2 sum 1 / (l blocks of the tile's k block), fitted to measured shard times) within 8 % of
+    the mean -- one contiguous range per GPU put 1.9x the mean on the first."""
+    import ctypes
+    dim, world = 1000, 8
+    shards = sharding.tensordot22_shards(dim, world)
+    costs = []
+    for ranges in shards:
+        assert 1 <= len(ranges) <= 5  # (a GPU whose part of class (1,1,1,1) is already above the mean gets no small-class interval)
+        n = len(ranges)
+        bs, es = (ctypes.c_int64 * n)(*[r[0] for r in ranges]), (ctypes.c_int64 * n)(*[r[1] for r in ranges])
+        stats = (ctypes.c_double * 2)()
+        assert lib.st_debug_sym22_tiles_stats(c_i64(dim), n, bs, es, stats) == 0
+        costs.append(stats[0] + 3.2 * stats[1])
+    assert max(costs) <= 1.08 * sum(costs) / world, costs
